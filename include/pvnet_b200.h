@@ -1,0 +1,151 @@
+/*
+ * pvnet_b200.h -- C ABI of libpvnet_b200.so: the B200 (sm_100a) implementation of
+ * PVNet's per-image inference hot path (voting layer + Resnet18_8s backbone).
+ *
+ * Boundary rules:
+ *   - plain C types only: device pointers, sizes, strides; no torch/ATen types;
+ *   - the CALLER owns every buffer, including the workspace; the library allocates
+ *     nothing on the hot path and launches only on the given stream (CUDA-graph
+ *     capturable); it never synchronises and never calls exit();
+ *   - every function returns 0 on success, a negative PVNET_E_* code on failure;
+ *     pvnet_last_error() returns a thread-local message for the last failure;
+ *   - all pointers are DEVICE pointers on the current CUDA device unless a
+ *     parameter says "host".
+ *
+ * Reference interfaces these entry points stand in for (paths relative to the
+ * zju3dv/pvnet tree):
+ *   lib/ransac_voting_gpu_layer/src/ransac_voting.cpp:20-31,103   generate_hypothesis
+ *   lib/ransac_voting_gpu_layer/src/ransac_voting.cpp:41-55,104   voting_for_hypothesis
+ *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:514-598      ransac_voting_layer_v3
+ *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:333-406      estimate_voting_distribution_with_mean
+ *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:983-1034     generate_hypothesis (python level)
+ *   lib/networks/model_repository.py:64-80                        Resnet18_8s.forward
+ * INTEGRATION.md shows the ctypes binding the reference's Python wrapper uses.
+ */
+#ifndef PVNET_B200_H_
+#define PVNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PVNET_API __attribute__((visibility("default")))
+#else
+#define PVNET_API
+#endif
+
+/* opaque: a cudaStream_t passed as void* (torch: torch.cuda.current_stream().cuda_stream) */
+typedef void *pvnet_stream_t;
+
+enum {
+    PVNET_OK = 0,
+    PVNET_E_INVALID = -1,   /* bad argument (shape, stride, null pointer, size) */
+    PVNET_E_WORKSPACE = -2, /* workspace too small */
+    PVNET_E_CUDA = -3,      /* a CUDA runtime / driver call failed */
+    PVNET_E_STATE = -4      /* object used before it was initialised */
+};
+
+/* How a mask element becomes "foreground". */
+enum {
+    PVNET_MASK_NONZERO_BYTE = 0, /* v3: `.byte()` then nonzero  (ransac_voting_gpu.py:527) */
+    PVNET_MASK_EQUALS_ONE = 1    /* with_mean: `mask == 1`      (ransac_voting_gpu.py:339) */
+};
+
+PVNET_API const char *pvnet_last_error(void);
+PVNET_API int pvnet_version(void);
+
+/* ------------------------------------------------------------------ voting layer */
+
+/* Bytes of workspace the fused voting entry points need for a batch of `b` images
+ * of h*w pixels, `vn` keypoints and `hn_total` hypotheses per keypoint. */
+PVNET_API int pvnet_vote_workspace_bytes(int b, int h, int w, int vn, int hn_total, size_t *bytes);
+
+/* Per-image foreground counts (before any subsampling): fg_out[b] int32.
+ * mask: [b,h,w] contiguous, elements of mask_elem_size bytes (1,2,4,8; integer or bool).
+ * The host reads fg_out to replay the reference's torch RNG calls in the reference's
+ * order (ransac_voting_gpu.py:531-547); nothing else in the layer needs the host. */
+PVNET_API int pvnet_mask_foreground_count(const void *mask, int mask_elem_size, int mask_mode,
+                                          int b, int h, int w, int32_t *fg_out,
+                                          void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
+
+/* ransac_voting_layer_v3 (ransac_voting_gpu.py:514-598), whole batch, no host sync.
+ *
+ *   mask       [b,h,w] contiguous, foreground = low byte nonzero
+ *   vertex     f32, logical shape [b,h,w,vn,2], addressed through vertex_strides[5]
+ *              (in ELEMENTS).  The reference passes a permuted view of an NCHW tensor
+ *              (tools/demo.py:48-50): strides {C*H*W, W, 1, 2*H*W, H*W}; it is read
+ *              in place, never copied.
+ *   idxs       int32 [b,hn,vn,2]: the pixel-pair samples (ransac_voting_gpu.py:547).
+ *              Each value is reduced modulo the image's pixel count tn (identity for
+ *              values already in [0,tn)).
+ *   selection  f32 [b,h,w] or NULL: the uniform field of ransac_voting_gpu.py:538.
+ *              Read only for images whose foreground count exceeds max_num; NULL means
+ *              "never subsample" (all foreground pixels take part).
+ *   out_pts    f32 [b,vn,2]  voted + least-squares-refitted keypoints (x,y);
+ *              zeros for images with fewer than min_num foreground pixels (:531-534).
+ *   out_counts int32 [b,hn,vn] or NULL: inlier count of every hypothesis (:561).
+ *   out_hyp    f32 [b,hn,vn,2] or NULL: the hypotheses (:554).
+ *   out_tn     int32 [b] or NULL: pixels that took part per image (after subsampling).
+ *
+ * The reference's `while True` (:552-576) re-scores the same idxs each round, so its
+ * output does not depend on confidence/max_iter; one scoring pass is performed.
+ */
+PVNET_API int pvnet_ransac_voting_v3(const void *mask, int mask_elem_size,
+                                     const float *vertex, const int64_t vertex_strides[5],
+                                     const int32_t *idxs, const float *selection,
+                                     int b, int h, int w, int vn, int hn,
+                                     float inlier_thresh, int min_num, int max_num,
+                                     float *out_pts, int32_t *out_counts, float *out_hyp, int32_t *out_tn,
+                                     void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
+
+/* estimate_voting_distribution_with_mean (ransac_voting_gpu.py:333-406).
+ *
+ *   mask       foreground = element == 1
+ *   idxs       int32 [b,rounds*hn,vn,2], rounds = ceil(min_hyp_num/hn) (fresh draw per
+ *              round, :367; the rounds are simply concatenated, :381-384)
+ *   mean       f32 [b,vn,2] (from v3)
+ *   out_cov    f32 [b,vn,2,2]: sum_h w_h d_h d_h^T / (sum_h w_h + 1e-3), d_h = hyp_h - mean,
+ *              w_h = count_h/tn, zeroed where below (max_h w_h - 0.1)   (:394-401)
+ *   Images with fewer than min_num foreground pixels use min_hyp_num hypotheses at
+ *   (0,0) with weight 1 (:343-348).
+ */
+PVNET_API int pvnet_vote_cov_with_mean(const void *mask, int mask_elem_size,
+                                       const float *vertex, const int64_t vertex_strides[5],
+                                       const int32_t *idxs, const float *selection, const float *mean,
+                                       int b, int h, int w, int vn, int hn, int rounds, int min_hyp_num,
+                                       float inlier_thresh, int min_num, int max_num,
+                                       float *out_cov, int32_t *out_counts, float *out_hyp, int32_t *out_tn,
+                                       void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
+
+/* 1:1 stand-ins for the reference extension's two functions, same layouts:
+ * direct [tn,vn,2] f32, coords [tn,2] f32 (x,y), idxs [hn,vn,2] i32, hypo [hn,vn,2] f32.
+ * pvnet_generate_hypothesis writes every element of hypo (degenerate pairs -> (0,0),
+ * ransac_voting_kernel.cu:42-43,75).  pvnet_voting_for_hypothesis only SETS inliers
+ * [hn,vn,tn] u8 to 1 where the test passes (caller zero-fills, ransac_voting_gpu.py:557).
+ * pvnet_vote_counts returns sum_t inliers as int32 [hn,vn] without the u8 tensor. */
+PVNET_API int pvnet_generate_hypothesis(const float *direct, const float *coords, const int32_t *idxs,
+                                        float *hypo, int tn, int vn, int hn, pvnet_stream_t stream);
+PVNET_API int pvnet_voting_for_hypothesis(const float *direct, const float *coords, const float *hypo,
+                                          uint8_t *inliers, int tn, int vn, int hn, float inlier_thresh,
+                                          pvnet_stream_t stream);
+PVNET_API int pvnet_vote_counts(const float *direct, const float *coords, const float *hypo,
+                                int32_t *counts, int tn, int vn, int hn, float inlier_thresh,
+                                pvnet_stream_t stream);
+
+/* Number of kernels this library has launched on the calling thread since the last
+ * reset (bench.py's "gpu_launches"). */
+PVNET_API long long pvnet_launch_count(void);
+PVNET_API void pvnet_launch_count_reset(void);
+
+/* -------------------------------------------------------------------- backbone */
+/* Declared in the second half of this header once the conv path lands:
+ * pvnet_backbone_{create,load_weights,workspace_bytes,forward,destroy}. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVNET_B200_H_ */

@@ -1,0 +1,3 @@
+"""`lib.ransac_voting_gpu_layer.ransac_voting` (the reference's native extension module,
+src/ransac_voting.cpp:102-107), served by pvnet_b200."""
+from pvnet_b200.ransac_voting import generate_hypothesis, voting_for_hypothesis  # noqa: F401

@@ -1,0 +1,913 @@
+// vote.cu -- PVNet RANSAC voting layer for B200 (sm_100a).
+//
+// What the reference does per image (lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:514-598):
+// torch.nonzero / masked_select compaction, generate_hypothesis kernel, a u8
+// [hn,vn,tn] inlier tensor written by voting_for_hypothesis_kernel
+// (src/ransac_voting_kernel.cu:88-126), torch.sum over it, max, a second vote for
+// the winner and an fp32 least-squares refit -- with >= 3 host syncs per image.
+//
+// Here the whole batch runs as one short launch sequence with no host sync:
+//   k_chunk_count   per-2048-pixel foreground counts
+//   k_chunk_kept    per-chunk kept counts (only differs when an image is subsampled)
+//   k_compact_write stable (row-major) list of foreground pixels, packed (y<<16|x)
+//   k_gen_hyp       ray-ray intersections, bit-exact op sequence of the reference
+//   k_vote          persistent kernel: pixel tiles staged in shared memory once per
+//                   (image, keypoint, hypothesis group), every lane keeps 4 hypotheses
+//                   in registers, inlier counts accumulate in registers; the [hn,vn,tn]
+//                   tensor never exists
+//   k_refit         argmax (lowest index on ties) + inlier sums of the winner in fp64
+//   k_refit_final   fixed-order reduction + 2x2 solve
+//   k_cov           estimate_voting_distribution_with_mean's weighted covariance
+//
+// Bit-exact inlier counts.  The reference predicate is
+//     num/(norm1*norm2) > thresh,  norm = sqrt.rn(fma(..)),  '/' = div.rn
+// (two correctly rounded sqrt, one correctly rounded division: ~30 issue slots).
+// k_vote evaluates a division/sqrt-free form  num'*|num'| - T^2*d2  with
+// num' = d . n/|n|, which differs from the reference's quotient test only by
+// rounding (relative error < 1.3e-6, bounded in DESIGN.md).  Every test whose
+// margin is inside a guard band of 6e-6 (or involves tiny/non-finite values) is
+// re-evaluated with the reference's exact instruction sequence (exact_inlier()
+// below).  Tests outside the band cannot change sign under either rounding, so
+// the counts are identical to the reference's, at ~13 issue slots per test.
+#include "common.cuh"
+
+#include <cfloat>
+#include <cmath>
+
+namespace {
+
+using pvnet::Carver;
+
+constexpr int CH_PX = 2048;       // pixels per compaction chunk
+constexpr int CH_THREADS = 256;   // 8 consecutive pixels per thread
+constexpr int VT_THREADS = 256;
+constexpr int VT_WARPS = VT_THREADS / 32;
+constexpr int VT_TILE = 2048;     // pixels per shared-memory tile (16 B each)
+constexpr int VT_HPL = 4;         // hypotheses held in registers per lane
+constexpr int VT_MAX_B = 1024;    // images per call (prefix table in shared memory)
+constexpr int RF_CHUNKS = 8;      // CTAs per (image, keypoint) in the refit pass
+constexpr int RF_THREADS = 256;
+constexpr float GUARD_EPS = 6e-6f;
+
+struct Strides {
+    long long s[5];
+};
+
+// ------------------------------------------------------------------ exact sequences
+// src/ransac_voting_kernel.cu:107-125 as nvcc compiles it for sm_100a (SASS checked):
+// intrinsics pin every rounding so this compiler cannot contract differently.
+__device__ __forceinline__ bool exact_inlier(float nx, float ny, float cx, float cy, float hx, float hy,
+                                             float thresh)
+{
+    const float dx = __fsub_rn(hx, cx);
+    const float dy = __fsub_rn(hy, cy);
+    const float norm1 = __fsqrt_rn(__fmaf_rn(nx, nx, __fmul_rn(ny, ny)));
+    const float norm2 = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    if (fmin((double)norm1, (double)norm2) < 1e-6) return false;
+    const float num = __fmaf_rn(dx, nx, __fmul_rn(dy, ny));
+    const float den = __fmul_rn(norm1, norm2);
+    const float ang = __fdiv_rn(num, den);
+    return ang > thresh;
+}
+
+// src/ransac_voting_kernel.cu:28-48 (SASS-derived contraction, DESIGN.md "FP sequence")
+__device__ __forceinline__ float2 exact_hypothesis(float d0x, float d0y, float cx0, float cy0, float d1x,
+                                                   float d1y, float cx1, float cy1)
+{
+    const float p = __fmul_rn(d0y, d1x);
+    const float q = __fmul_rn(d0x, d1y);
+    const float det_y = __fsub_rn(p, q);
+    if ((double)fabsf(det_y) < 1e-6) return make_float2(0.f, 0.f);
+    const float det_x = __fsub_rn(q, p);
+    if ((double)fabsf(det_x) < 1e-6) return make_float2(0.f, 0.f);
+    const float s1 = __fmaf_rn(d1y, cx1, -__fmul_rn(d1x, cy1));
+    const float s0 = __fmaf_rn(d0y, cx0, -__fmul_rn(d0x, cy0));
+    const float y = __fdiv_rn(__fmaf_rn(d1y, s0, -__fmul_rn(d0y, s1)), det_y);
+    const float x = __fdiv_rn(__fmaf_rn(d0x, s1, -__fmul_rn(d1x, s0)), det_x);
+    return make_float2(x, y);
+}
+
+// ------------------------------------------------------------------ block helpers
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sums up to 3 ints over the block; every thread gets the totals. blockDim.x <= 1024
+__device__ __forceinline__ void block_sum3(int &a, int &b, int &c, int *scratch /* >= 3*32 ints */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    c = warp_sum(c);
+    __syncthreads();
+    if (lane == 0) {
+        scratch[warp] = a;
+        scratch[32 + warp] = b;
+        scratch[64 + warp] = c;
+    }
+    __syncthreads();
+    int ta = 0, tb = 0, tc = 0;
+    for (int i = 0; i < nw; ++i) {
+        ta += scratch[i];
+        tb += scratch[32 + i];
+        tc += scratch[64 + i];
+    }
+    a = ta;
+    b = tb;
+    c = tc;
+}
+
+template <typename T>
+__device__ __forceinline__ bool is_foreground(T v, int mode)
+{
+    if (mode == PVNET_MASK_EQUALS_ONE) return v == (T)1;
+    return (unsigned char)v != 0;  // `.byte()` keeps the low 8 bits (ransac_voting_gpu.py:527)
+}
+
+// `max_num / foreground.float()`: torch evaluates int / tensor as reciprocal() * int
+// in float32 (ransac_voting_gpu.py:539)
+__device__ __forceinline__ float subsample_p(int fg, int max_num)
+{
+    return __fmul_rn(__frcp_rn((float)fg), (float)max_num);
+}
+
+// ------------------------------------------------------------------ compaction
+// pass 1: foreground count of every 2048-pixel chunk
+template <typename T>
+__global__ void __launch_bounds__(CH_THREADS) k_chunk_count(const T *__restrict__ mask, int mode, int npx,
+                                                             int nchunk, int *__restrict__ chunk_fg)
+{
+    __shared__ int scratch[96];
+    const int c = blockIdx.x, b = blockIdx.y;
+    const T *m = mask + (size_t)b * npx;
+    const int base = c * CH_PX + threadIdx.x * 8;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int i = base + j;
+        if (i < npx) cnt += is_foreground(m[i], mode) ? 1 : 0;
+    }
+    int z0 = 0, z1 = 0;
+    block_sum3(cnt, z0, z1, scratch);
+    if (threadIdx.x == 0) chunk_fg[b * nchunk + c] = cnt;
+}
+
+// pass 2: kept pixels per chunk.  Equals the foreground count unless the image has
+// more than max_num foreground pixels, in which case pixel i survives iff
+// selection[i] < p (ransac_voting_gpu.py:537-540).  Images below min_num keep nothing.
+template <typename T>
+__global__ void __launch_bounds__(CH_THREADS)
+    k_chunk_kept(const T *__restrict__ mask, int mode, const float *__restrict__ selection, int npx, int nchunk,
+                 int min_num, int max_num, const int *__restrict__ chunk_fg, int *__restrict__ chunk_kept,
+                 int *__restrict__ status)
+{
+    __shared__ int scratch[96];
+    const int c = blockIdx.x, b = blockIdx.y;
+    int tot = 0, z0 = 0, z1 = 0;
+    for (int i = threadIdx.x; i < nchunk; i += blockDim.x) tot += chunk_fg[b * nchunk + i];
+    block_sum3(tot, z0, z1, scratch);
+    const bool skip = tot < min_num;
+    const bool sub = tot > max_num;
+    if (!sub || selection == nullptr) {
+        if (threadIdx.x == 0) {
+            chunk_kept[b * nchunk + c] = skip ? 0 : chunk_fg[b * nchunk + c];
+            if (c == 0) status[b] = (skip ? 1 : 0) | ((sub && selection == nullptr) ? 4 : 0);
+        }
+        return;
+    }
+    const float p = subsample_p(tot, max_num);
+    const T *m = mask + (size_t)b * npx;
+    const float *sel = selection + (size_t)b * npx;
+    const int base = c * CH_PX + threadIdx.x * 8;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int i = base + j;
+        if (i < npx) cnt += (is_foreground(m[i], mode) && sel[i] < p) ? 1 : 0;
+    }
+    block_sum3(cnt, z0, z1, scratch);
+    if (threadIdx.x == 0) {
+        chunk_kept[b * nchunk + c] = cnt;
+        if (c == 0) status[b] = 2;
+    }
+}
+
+// pass 3: write the stable pixel list.  pix[b][r] = (y<<16)|x of the r-th kept pixel
+// in row-major order == row r of torch.nonzero (ransac_voting_gpu.py:542).
+template <typename T>
+__global__ void __launch_bounds__(CH_THREADS)
+    k_compact_write(const T *__restrict__ mask, int mode, const float *__restrict__ selection, int npx, int width,
+                    int nchunk, int max_num, const int *__restrict__ chunk_fg, const int *__restrict__ chunk_kept,
+                    unsigned *__restrict__ pix, int *__restrict__ tn_out, int *__restrict__ fg_out)
+{
+    __shared__ int scratch[96];
+    __shared__ int warp_off[CH_THREADS / 32];
+    const int c = blockIdx.x, b = blockIdx.y;
+    int tot_fg = 0, prefix = 0, tot_kept = 0;
+    for (int i = threadIdx.x; i < nchunk; i += blockDim.x) {
+        const int k = chunk_kept[b * nchunk + i];
+        tot_fg += chunk_fg[b * nchunk + i];
+        tot_kept += k;
+        if (i < c) prefix += k;
+    }
+    block_sum3(tot_fg, prefix, tot_kept, scratch);
+    if (c == 0 && threadIdx.x == 0) {
+        tn_out[b] = tot_kept;
+        fg_out[b] = tot_fg;
+    }
+    if (chunk_kept[b * nchunk + c] == 0) return;
+    const bool sub = (tot_fg > max_num) && selection != nullptr;
+    const float p = sub ? subsample_p(tot_fg, max_num) : 0.f;
+    const T *m = mask + (size_t)b * npx;
+    const float *sel = selection + (size_t)b * npx;
+    const int base = c * CH_PX + threadIdx.x * 8;
+    unsigned flags = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int i = base + j;
+        if (i < npx) {
+            bool keep = is_foreground(m[i], mode);
+            if (sub && keep) keep = sel[i] < p;
+            flags |= (keep ? 1u : 0u) << j;
+        }
+    }
+    const int mine = __popc(flags);
+    // exclusive scan over the block, thread order == pixel order
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_off[warp] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int i = 0; i < warp; ++i) woff += warp_off[i];
+    int r = prefix + woff + inc - mine;
+    unsigned *out = pix + (size_t)b * npx;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (flags & (1u << j)) {
+            const int i = base + j;
+            const int y = i / width, x = i - y * width;
+            out[r++] = ((unsigned)y << 16) | (unsigned)x;
+        }
+    }
+}
+
+// reduce chunk counts to per-image totals (pvnet_mask_foreground_count)
+__global__ void k_sum_chunks(const int *__restrict__ chunk_fg, int nchunk, int *__restrict__ fg_out)
+{
+    __shared__ int scratch[96];
+    const int b = blockIdx.x;
+    int tot = 0, z0 = 0, z1 = 0;
+    for (int i = threadIdx.x; i < nchunk; i += blockDim.x) tot += chunk_fg[b * nchunk + i];
+    block_sum3(tot, z0, z1, scratch);
+    if (threadIdx.x == 0) fg_out[b] = tot;
+}
+
+// ------------------------------------------------------------------ hypotheses
+// idxs [b,hn,vn,2] -> hyp [b][vn][hn] (keypoint-major so a vote CTA reads one row)
+__global__ void __launch_bounds__(256)
+    k_gen_hyp(const float *__restrict__ vertex, Strides st, const int *__restrict__ idxs,
+              const unsigned *__restrict__ pix, const int *__restrict__ tn_arr, int npx, int vn, int hn,
+              float2 *__restrict__ hyp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i >= hn * vn) return;
+    const int hi = i / vn, vi = i - hi * vn;
+    const int tn = tn_arr[b];
+    float2 out = make_float2(0.f, 0.f);
+    if (tn > 0) {
+        const size_t ib = (((size_t)b * hn + hi) * vn + vi) * 2;
+        const unsigned t0 = (unsigned)idxs[ib] % (unsigned)tn;
+        const unsigned t1 = (unsigned)idxs[ib + 1] % (unsigned)tn;
+        const unsigned p0 = pix[(size_t)b * npx + t0], p1 = pix[(size_t)b * npx + t1];
+        const int x0 = p0 & 0xffff, y0 = p0 >> 16, x1 = p1 & 0xffff, y1 = p1 >> 16;
+        const long long base = (long long)b * st.s[0] + (long long)vi * st.s[3];
+        const long long o0 = base + y0 * st.s[1] + x0 * st.s[2];
+        const long long o1 = base + y1 * st.s[1] + x1 * st.s[2];
+        out = exact_hypothesis(vertex[o0], vertex[o0 + st.s[4]], (float)x0, (float)y0, vertex[o1],
+                               vertex[o1 + st.s[4]], (float)x1, (float)y1);
+    }
+    hyp[((size_t)b * vn + vi) * hn + hi] = out;
+}
+
+// ------------------------------------------------------------------ the vote
+// Persistent CTAs walk items (pixel tile, keypoint, hypothesis group).  Warps are
+// split wh (hypothesis groups of 128) x wp (pixel interleave); each lane owns
+// VT_HPL hypotheses; pixels come from shared memory as one broadcast LDS.128.
+__global__ void __launch_bounds__(VT_THREADS, 3)
+    k_vote(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
+           const int *__restrict__ tn_arr, int npx, int nb, int vn, int hn, int wh,
+           const float2 *__restrict__ hyp, int *__restrict__ counts, float thresh, float t2, float band)
+{
+    __shared__ float4 tile[VT_TILE];
+    __shared__ int red[VT_WARPS * 32 * VT_HPL];
+    __shared__ int tile_prefix[VT_MAX_B + 1];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        int acc = 0;
+        for (int i = 0; i < nb; ++i) {
+            tile_prefix[i] = acc;
+            acc += (tn_arr[i] + VT_TILE - 1) / VT_TILE;
+        }
+        tile_prefix[nb] = acc;
+    }
+    __syncthreads();
+    const int total_tiles = tile_prefix[nb];
+    const int HC = wh * 32 * VT_HPL;               // hypotheses per item
+    const int hcn = (hn + HC - 1) / HC;
+    const long long n_items = (long long)total_tiles * vn * hcn;
+    const int wp_count = VT_WARPS / wh;
+    const int my_wh = warp % wh, my_wp = warp / wh;
+
+    for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int hc = (int)(it % hcn);
+        const long long r = it / hcn;
+        const int k = (int)(r % vn);
+        const int g = (int)(r / vn);
+        int lo = 0, hi = nb;                         // b with tile_prefix[b] <= g < tile_prefix[b+1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (tile_prefix[mid] <= g) lo = mid; else hi = mid;
+        }
+        const int b = lo;
+        const int tn = tn_arr[b];
+        const int t0 = (g - tile_prefix[b]) * VT_TILE;
+        const int len = min(VT_TILE, tn - t0);
+        const long long vbase = (long long)b * st.s[0] + (long long)k * st.s[3];
+
+        // ---- stage: gather this tile's pixels and unit directions
+        for (int i = tid; i < len; i += VT_THREADS) {
+            const unsigned p = __ldg(pix + (size_t)b * npx + t0 + i);
+            const int x = p & 0xffff, y = p >> 16;
+            const long long off = vbase + y * st.s[1] + x * st.s[2];
+            const float nx = __ldg(vertex + off), ny = __ldg(vertex + off + st.s[4]);
+            const float n2 = fmaf(nx, nx, ny * ny);
+            const float rinv = rsqrtf(n2);
+            float ux = nx * rinv, uy = ny * rinv;
+            if (!(n2 > 1e-11f && n2 < 1e30f)) ux = uy = __int_as_float(0x7fc00000);  // -> exact path
+            tile[i] = make_float4((float)x, (float)y, ux, uy);
+        }
+        for (int i = tid; i < HC; i += VT_THREADS) red[i] = 0;
+        __syncthreads();
+
+        // ---- this lane's hypotheses
+        const int hbase = hc * HC + my_wh * (32 * VT_HPL);
+        float hx[VT_HPL], hy[VT_HPL];
+        int cnt[VT_HPL];
+#pragma unroll
+        for (int j = 0; j < VT_HPL; ++j) {
+            const int h = hbase + j * 32 + lane;
+            float2 hp = make_float2(3.0e8f, 3.0e8f);   // padding hypothesis, count discarded
+            if (h < hn) hp = __ldg(hyp + ((size_t)b * vn + k) * hn + h);
+            hx[j] = hp.x;
+            hy[j] = hp.y;
+            cnt[j] = 0;
+        }
+
+        // ---- sweep the tile
+#pragma unroll 2
+        for (int i = my_wp; i < len; i += wp_count) {
+            const float4 p = tile[i];
+            unsigned unc = 0;
+#pragma unroll
+            for (int j = 0; j < VT_HPL; ++j) {
+                const float dx = hx[j] - p.x, dy = hy[j] - p.y;
+                const float d2 = fmaf(dx, dx, dy * dy);
+                const float num = fmaf(dx, p.z, dy * p.w);
+                const float s = num * fabsf(num);
+                const float e = fmaf(-t2, d2, s);
+                const float bd = fmaf(band, d2, 4e-12f);
+                cnt[j] += (e > bd) ? 1 : 0;
+                unc |= (fabsf(e) > bd) ? 0u : (1u << j);
+            }
+            if (__any_sync(0xffffffffu, unc != 0)) {
+                if (unc) {
+                    const long long off = vbase + (long long)p.y * st.s[1] + (long long)p.x * st.s[2];
+                    const float nx = __ldg(vertex + off), ny = __ldg(vertex + off + st.s[4]);
+#pragma unroll
+                    for (int j = 0; j < VT_HPL; ++j)
+                        if (unc & (1u << j))
+                            cnt[j] += exact_inlier(nx, ny, p.x, p.y, hx[j], hy[j], thresh) ? 1 : 0;
+                }
+            }
+        }
+
+        // ---- combine the pixel-interleaved warps, then one atomic per hypothesis
+#pragma unroll
+        for (int j = 0; j < VT_HPL; ++j)
+            if (cnt[j]) atomicAdd(&red[my_wh * (32 * VT_HPL) + j * 32 + lane], cnt[j]);
+        __syncthreads();
+        for (int i = tid; i < HC; i += VT_THREADS) {
+            const int h = hc * HC + i;
+            const int v = red[i];
+            if (h < hn && v) atomicAdd(counts + ((size_t)b * vn + k) * hn + h, v);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ argmax + refit
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// grid (RF_CHUNKS, b*vn).  Winner = max count, lowest hypothesis index on ties
+// (torch.max, ransac_voting_gpu.py:562); kept only if its count is > 0 (:567).  Then the
+// inliers of the winner (:582-584) feed  sum n n^T  and  sum n (n.c),  n = (d_y,-d_x)
+// (:579-593), accumulated in fp64.
+__global__ void __launch_bounds__(RF_THREADS)
+    k_refit(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
+            const int *__restrict__ tn_arr, int npx, int vn, int hn, const float2 *__restrict__ hyp,
+            const int *__restrict__ counts, float thresh, double *__restrict__ part, float2 *__restrict__ win)
+{
+    __shared__ unsigned long long s_key[RF_THREADS / 32];
+    __shared__ double s_acc[RF_THREADS / 32][5];
+    const int rc = blockIdx.x, bk = blockIdx.y, b = bk / vn, k = bk - b * vn;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tn = tn_arr[b];
+    double *my_part = part + ((size_t)bk * RF_CHUNKS + rc) * 5;
+    if (tn == 0) {
+        if (tid < 5) my_part[tid] = 0.0;
+        if (rc == 0 && tid == 0) win[bk] = make_float2(0.f, 0.f);
+        return;
+    }
+    unsigned long long key = 0;
+    for (int h = tid; h < hn; h += RF_THREADS) {
+        const unsigned long long kk =
+            ((unsigned long long)(unsigned)counts[(size_t)bk * hn + h] << 32) | (unsigned long long)(0xffffffffu - (unsigned)h);
+        key = kk > key ? kk : key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if (lane == 0) s_key[warp] = key;
+    __syncthreads();
+    key = s_key[0];
+    for (int i = 1; i < RF_THREADS / 32; ++i) key = s_key[i] > key ? s_key[i] : key;
+    const unsigned best_cnt = (unsigned)(key >> 32);
+    const unsigned best_h = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+    float2 wp = make_float2(0.f, 0.f);
+    if (best_cnt > 0) wp = hyp[(size_t)bk * hn + best_h];
+    if (rc == 0 && tid == 0) win[bk] = wp;
+
+    const int per = (tn + RF_CHUNKS - 1) / RF_CHUNKS;
+    const int lo = rc * per, hi = min(tn, lo + per);
+    const long long vbase = (long long)b * st.s[0] + (long long)k * st.s[3];
+    double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
+    for (int t = lo + tid; t < hi; t += RF_THREADS) {
+        const unsigned p = pix[(size_t)b * npx + t];
+        const int x = p & 0xffff, y = p >> 16;
+        const long long off = vbase + y * st.s[1] + x * st.s[2];
+        const float dxv = vertex[off], dyv = vertex[off + st.s[4]];
+        if (exact_inlier(dxv, dyv, (float)x, (float)y, wp.x, wp.y, thresh)) {
+            const double n0 = (double)dyv, n1 = -(double)dxv;
+            const double bb = n0 * (double)x + n1 * (double)y;
+            a00 += n0 * n0;
+            a01 += n0 * n1;
+            a11 += n1 * n1;
+            b0 += n0 * bb;
+            b1 += n1 * bb;
+        }
+    }
+    a00 = warp_sum_d(a00);
+    a01 = warp_sum_d(a01);
+    a11 = warp_sum_d(a11);
+    b0 = warp_sum_d(b0);
+    b1 = warp_sum_d(b1);
+    if (lane == 0) {
+        s_acc[warp][0] = a00;
+        s_acc[warp][1] = a01;
+        s_acc[warp][2] = a11;
+        s_acc[warp][3] = b0;
+        s_acc[warp][4] = b1;
+    }
+    __syncthreads();
+    if (tid < 5) {
+        double v = 0;
+        for (int i = 0; i < RF_THREADS / 32; ++i) v += s_acc[i][tid];
+        my_part[tid] = v;
+    }
+}
+
+// thread per (image, keypoint): fixed-order sum of the partials, 2x2 solve (:594)
+__global__ void k_refit_final(const double *__restrict__ part, const int *__restrict__ tn_arr, int nb, int vn,
+                              float *__restrict__ out_pts)
+{
+    const int bk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bk >= nb * vn) return;
+    const int b = bk / vn;
+    float px = 0.f, py = 0.f;
+    if (tn_arr[b] > 0) {
+        double a[5] = {0, 0, 0, 0, 0};
+        for (int rc = 0; rc < RF_CHUNKS; ++rc)
+            for (int i = 0; i < 5; ++i) a[i] += part[((size_t)bk * RF_CHUNKS + rc) * 5 + i];
+        const double det = a[0] * a[2] - a[1] * a[1];
+        px = (float)((a[2] * a[3] - a[1] * a[4]) / det);
+        py = (float)((a[0] * a[4] - a[1] * a[3]) / det);
+    }
+    out_pts[bk * 2] = px;
+    out_pts[bk * 2 + 1] = py;
+}
+
+// internal [b][vn][hn] -> API layouts [b,hn,vn(,2)]
+__global__ void k_export(const float2 *__restrict__ hyp, const int *__restrict__ counts,
+                         const int *__restrict__ tn_arr, int nb, int vn, int hn, float *__restrict__ out_hyp,
+                         int *__restrict__ out_counts, int *__restrict__ out_tn)
+{
+    const long long n = (long long)nb * vn * hn;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % vn);
+        const long long r = i / vn;
+        const int h = (int)(r % hn);
+        const int b = (int)(r / hn);
+        const size_t src = ((size_t)b * vn + k) * hn + h;
+        if (out_counts) out_counts[i] = counts[src];
+        if (out_hyp) {
+            const float2 v = hyp[src];
+            out_hyp[i * 2] = v.x;
+            out_hyp[i * 2 + 1] = v.y;
+        }
+    }
+    if (out_tn && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) out_tn[i] = tn_arr[i];
+}
+
+// ------------------------------------------------------------------ covariance
+// block per (image, keypoint); ransac_voting_gpu.py:392-401
+__global__ void __launch_bounds__(256)
+    k_cov(const float2 *__restrict__ hyp, const int *__restrict__ counts, const int *__restrict__ tn_arr,
+          const float *__restrict__ mean, int vn, int hn, int min_hyp_num, float *__restrict__ out_cov)
+{
+    __shared__ int s_max[8];
+    __shared__ double s_acc[8][5];
+    const int bk = blockIdx.x, b = bk / vn;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tn = tn_arr[b];
+    const float mx = mean[bk * 2], my = mean[bk * 2 + 1];
+    const bool skipped = tn == 0;
+    const int rows = skipped ? min_hyp_num : hn;       // :343-348 vs :363-384
+    int cmax = 0;
+    if (!skipped)
+        for (int h = tid; h < hn; h += 256) cmax = max(cmax, counts[(size_t)bk * hn + h]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    if (lane == 0) s_max[warp] = cmax;
+    __syncthreads();
+    cmax = s_max[0];
+    for (int i = 1; i < 8; ++i) cmax = max(cmax, s_max[i]);
+    const float ftn = (float)tn;
+    const float rmax = skipped ? 1.0f : __fdiv_rn((float)cmax, ftn);
+    const float thr = __fsub_rn(rmax, 0.1f);                                       // :394
+    double c00 = 0, c01 = 0, c10 = 0, c11 = 0, ws = 0;
+    for (int h = tid; h < rows; h += 256) {
+        float w, hxv, hyv;
+        if (skipped) {
+            w = 1.0f;
+            hxv = 0.f;
+            hyv = 0.f;
+        } else {
+            w = __fdiv_rn((float)counts[(size_t)bk * hn + h], ftn);
+            const float2 hp = hyp[(size_t)bk * hn + h];
+            hxv = hp.x;
+            hyv = hp.y;
+        }
+        if (w < thr) w = 0.0f;                                                     // :395
+        const float dx = __fsub_rn(hxv, mx), dy = __fsub_rn(hyv, my);              // :398
+        const float wdx = __fmul_rn(dx, w), wdy = __fmul_rn(dy, w);                // :399
+        c00 += (double)dx * (double)wdx;                                           // :400
+        c01 += (double)dx * (double)wdy;
+        c10 += (double)dy * (double)wdx;
+        c11 += (double)dy * (double)wdy;
+        ws += (double)w;
+    }
+    c00 = warp_sum_d(c00);
+    c01 = warp_sum_d(c01);
+    c10 = warp_sum_d(c10);
+    c11 = warp_sum_d(c11);
+    ws = warp_sum_d(ws);
+    if (lane == 0) {
+        s_acc[warp][0] = c00;
+        s_acc[warp][1] = c01;
+        s_acc[warp][2] = c10;
+        s_acc[warp][3] = c11;
+        s_acc[warp][4] = ws;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a[5] = {0, 0, 0, 0, 0};
+        for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < 5; ++j) a[j] += s_acc[i][j];
+        const float den = __fadd_rn((float)a[4], 1e-3f);                           // :401
+        for (int j = 0; j < 4; ++j) out_cov[(size_t)bk * 4 + j] = __fdiv_rn((float)a[j], den);
+    }
+}
+
+// ------------------------------------------------------------------ 1:1 stand-ins
+__global__ void k_compat_gen_hyp(const float *__restrict__ direct, const float *__restrict__ coords,
+                                 const int *__restrict__ idxs, float *__restrict__ hypo, int tn, int vn, int hn)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hn * vn) return;
+    const int vi = i % vn;
+    const int t0 = idxs[i * 2], t1 = idxs[i * 2 + 1];
+    (void)tn;
+    const float2 r = exact_hypothesis(direct[((size_t)t0 * vn + vi) * 2], direct[((size_t)t0 * vn + vi) * 2 + 1],
+                                      coords[(size_t)t0 * 2], coords[(size_t)t0 * 2 + 1],
+                                      direct[((size_t)t1 * vn + vi) * 2], direct[((size_t)t1 * vn + vi) * 2 + 1],
+                                      coords[(size_t)t1 * 2], coords[(size_t)t1 * 2 + 1]);
+    hypo[i * 2] = r.x;
+    hypo[i * 2 + 1] = r.y;
+}
+
+// grid (ceil(tn/256), vn, hn)
+__global__ void k_compat_vote(const float *__restrict__ direct, const float *__restrict__ coords,
+                              const float *__restrict__ hypo, unsigned char *__restrict__ inliers, int tn, int vn,
+                              int hn, float thresh)
+{
+    const int ti = blockIdx.x * blockDim.x + threadIdx.x;
+    const int vi = blockIdx.y, hi = blockIdx.z;
+    if (ti >= tn) return;
+    (void)hn;
+    if (exact_inlier(direct[((size_t)ti * vn + vi) * 2], direct[((size_t)ti * vn + vi) * 2 + 1],
+                     coords[(size_t)ti * 2], coords[(size_t)ti * 2 + 1], hypo[(hi * vn + vi) * 2],
+                     hypo[(hi * vn + vi) * 2 + 1], thresh))
+        inliers[((size_t)hi * vn + vi) * tn + ti] = 1;
+}
+
+// block per (hypothesis, keypoint): exact predicate, block-summed
+__global__ void __launch_bounds__(256)
+    k_compat_counts(const float *__restrict__ direct, const float *__restrict__ coords,
+                    const float *__restrict__ hypo, int *__restrict__ counts, int tn, int vn, float thresh)
+{
+    __shared__ int scratch[96];
+    const int vi = blockIdx.x, hi = blockIdx.y;
+    const float hx = hypo[(hi * vn + vi) * 2], hy = hypo[(hi * vn + vi) * 2 + 1];
+    int c = 0, z0 = 0, z1 = 0;
+    for (int ti = threadIdx.x; ti < tn; ti += blockDim.x)
+        c += exact_inlier(direct[((size_t)ti * vn + vi) * 2], direct[((size_t)ti * vn + vi) * 2 + 1],
+                          coords[(size_t)ti * 2], coords[(size_t)ti * 2 + 1], hx, hy, thresh)
+                 ? 1
+                 : 0;
+    block_sum3(c, z0, z1, scratch);
+    if (threadIdx.x == 0) counts[hi * vn + vi] = c;
+}
+
+// ------------------------------------------------------------------ host side
+struct VoteWs {
+    unsigned *pix;
+    int *chunk_fg, *chunk_kept, *tn, *fg, *status, *counts;
+    float2 *hyp, *win;
+    double *part;
+    size_t bytes;
+};
+
+VoteWs carve(void *ws, int b, int h, int w, int vn, int hn_total)
+{
+    const size_t npx = (size_t)h * w;
+    const int nchunk = (int)((npx + CH_PX - 1) / CH_PX);
+    Carver c(ws);
+    VoteWs v;
+    v.pix = c.take<unsigned>((size_t)b * npx);
+    v.chunk_fg = c.take<int>((size_t)b * nchunk);
+    v.chunk_kept = c.take<int>((size_t)b * nchunk);
+    v.tn = c.take<int>(b);
+    v.fg = c.take<int>(b);
+    v.status = c.take<int>(b);
+    v.counts = c.take<int>((size_t)b * vn * hn_total);
+    v.hyp = c.take<float2>((size_t)b * vn * hn_total);
+    v.win = c.take<float2>((size_t)b * vn);
+    v.part = c.take<double>((size_t)b * vn * RF_CHUNKS * 5);
+    v.bytes = pvnet::align_up(c.off, 256);
+    return v;
+}
+
+int check_common(const void *mask, int mask_elem_size, const float *vertex, const long long *strides,
+                 const int32_t *idxs, int b, int h, int w, int vn, int hn)
+{
+    PV_CHECK_ARG(mask && vertex && strides && idxs, "null mask/vertex/strides/idxs pointer");
+    PV_CHECK_ARG(mask_elem_size == 1 || mask_elem_size == 2 || mask_elem_size == 4 || mask_elem_size == 8,
+                 "mask element size %d not in {1,2,4,8}", mask_elem_size);
+    PV_CHECK_ARG(b >= 1 && b <= VT_MAX_B, "batch %d outside [1,%d]", b, VT_MAX_B);
+    PV_CHECK_ARG(h >= 1 && w >= 1 && h <= 65535 && w <= 65535, "image size %dx%d unsupported", h, w);
+    PV_CHECK_ARG(vn >= 1 && vn <= 65535, "keypoint count %d unsupported", vn);
+    PV_CHECK_ARG(hn >= 1 && hn <= (1 << 24), "hypothesis count %d unsupported", hn);
+    return PVNET_OK;
+}
+
+template <typename T>
+int launch_compaction_t(const T *mask, int mode, const float *selection, int b, int h, int w, int min_num,
+                        int max_num, const VoteWs &ws, cudaStream_t s)
+{
+    const int npx = h * w;
+    const int nchunk = (npx + CH_PX - 1) / CH_PX;
+    dim3 grid(nchunk, b);
+    k_chunk_count<T><<<grid, CH_THREADS, 0, s>>>(mask, mode, npx, nchunk, ws.chunk_fg);
+    PV_LAUNCHED("k_chunk_count");
+    k_chunk_kept<T><<<grid, CH_THREADS, 0, s>>>(mask, mode, selection, npx, nchunk, min_num, max_num, ws.chunk_fg,
+                                                ws.chunk_kept, ws.status);
+    PV_LAUNCHED("k_chunk_kept");
+    k_compact_write<T><<<grid, CH_THREADS, 0, s>>>(mask, mode, selection, npx, w, nchunk, max_num, ws.chunk_fg,
+                                                   ws.chunk_kept, ws.pix, ws.tn, ws.fg);
+    PV_LAUNCHED("k_compact_write");
+    return PVNET_OK;
+}
+
+int launch_compaction(const void *mask, int esz, int mode, const float *selection, int b, int h, int w,
+                      int min_num, int max_num, const VoteWs &ws, cudaStream_t s)
+{
+    switch (esz) {
+    case 1: return launch_compaction_t((const unsigned char *)mask, mode, selection, b, h, w, min_num, max_num, ws, s);
+    case 2: return launch_compaction_t((const short *)mask, mode, selection, b, h, w, min_num, max_num, ws, s);
+    case 4: return launch_compaction_t((const int *)mask, mode, selection, b, h, w, min_num, max_num, ws, s);
+    default: return launch_compaction_t((const long long *)mask, mode, selection, b, h, w, min_num, max_num, ws, s);
+    }
+}
+
+// hypotheses + scoring shared by v3 and with_mean
+int launch_hyp_and_vote(const float *vertex, const Strides &st, const int32_t *idxs, int b, int h, int w, int vn,
+                        int hn, float thresh, const VoteWs &ws, cudaStream_t s)
+{
+    const int npx = h * w;
+    PV_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (size_t)b * vn * hn, s));
+    dim3 ghyp((hn * vn + 255) / 256, b);
+    k_gen_hyp<<<ghyp, 256, 0, s>>>(vertex, st, idxs, ws.pix, ws.tn, npx, vn, hn, ws.hyp);
+    PV_LAUNCHED("k_gen_hyp");
+    // hypothesis warps per CTA: 128 hypotheses per warp
+    int wh = 1;
+    while (wh < VT_WARPS && wh * 32 * VT_HPL < hn) wh <<= 1;
+    const int HC = wh * 32 * VT_HPL;
+    const long long max_items = (long long)b * ((npx + VT_TILE - 1) / VT_TILE) * vn * ((hn + HC - 1) / HC);
+    long long grid = (long long)pvnet::sm_count() * 3;
+    if (grid > max_items) grid = max_items;
+    // thresh <= 0 (or NaN) has no squared form: NaN makes every test take the exact path
+    const float t2 = (thresh > 0.f && thresh < 1e18f) ? thresh * thresh : nanf("");
+    const float band = GUARD_EPS * (thresh > 0.f ? thresh * thresh : 1.f);
+    k_vote<<<(unsigned)grid, VT_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, npx, b, vn, hn, wh, ws.hyp, ws.counts,
+                                                 thresh, t2, band);
+    PV_LAUNCHED("k_vote");
+    return PVNET_OK;
+}
+
+int launch_export(const VoteWs &ws, int b, int vn, int hn, float *out_hyp, int32_t *out_counts, int32_t *out_tn,
+                  cudaStream_t s)
+{
+    if (!out_hyp && !out_counts && !out_tn) return PVNET_OK;
+    const long long n = (long long)b * vn * hn;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 4096) grid = 4096;
+    if (grid < 1) grid = 1;
+    k_export<<<grid, 256, 0, s>>>(ws.hyp, ws.counts, ws.tn, b, vn, hn, out_hyp, out_counts, out_tn);
+    PV_LAUNCHED("k_export");
+    return PVNET_OK;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int pvnet_vote_workspace_bytes(int b, int h, int w, int vn, int hn_total, size_t *bytes)
+{
+    PV_CHECK_ARG(bytes, "null bytes pointer");
+    PV_CHECK_ARG(b >= 1 && h >= 1 && w >= 1 && vn >= 1 && hn_total >= 1, "non-positive dimension");
+    *bytes = carve(nullptr, b, h, w, vn, hn_total).bytes + 256;
+    return PVNET_OK;
+}
+
+int pvnet_mask_foreground_count(const void *mask, int mask_elem_size, int mask_mode, int b, int h, int w,
+                                int32_t *fg_out, void *workspace, size_t workspace_bytes, pvnet_stream_t stream)
+{
+    PV_CHECK_ARG(mask && fg_out && workspace, "null pointer");
+    PV_CHECK_ARG(b >= 1 && b <= VT_MAX_B && h >= 1 && w >= 1 && h <= 65535 && w <= 65535, "bad shape");
+    const int npx = h * w, nchunk = (npx + CH_PX - 1) / CH_PX;
+    if (workspace_bytes < sizeof(int) * (size_t)b * nchunk) {
+        pvnet::set_error("workspace %zu < %zu bytes", workspace_bytes, sizeof(int) * (size_t)b * nchunk);
+        return PVNET_E_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int *chunk_fg = (int *)workspace;
+    dim3 grid(nchunk, b);
+    switch (mask_elem_size) {
+    case 1: k_chunk_count<unsigned char><<<grid, CH_THREADS, 0, s>>>((const unsigned char *)mask, mask_mode, npx, nchunk, chunk_fg); break;
+    case 2: k_chunk_count<short><<<grid, CH_THREADS, 0, s>>>((const short *)mask, mask_mode, npx, nchunk, chunk_fg); break;
+    case 4: k_chunk_count<int><<<grid, CH_THREADS, 0, s>>>((const int *)mask, mask_mode, npx, nchunk, chunk_fg); break;
+    case 8: k_chunk_count<long long><<<grid, CH_THREADS, 0, s>>>((const long long *)mask, mask_mode, npx, nchunk, chunk_fg); break;
+    default: pvnet::set_error("mask element size %d not in {1,2,4,8}", mask_elem_size); return PVNET_E_INVALID;
+    }
+    PV_LAUNCHED("k_chunk_count");
+    k_sum_chunks<<<b, 128, 0, s>>>(chunk_fg, nchunk, fg_out);
+    PV_LAUNCHED("k_sum_chunks");
+    return PVNET_OK;
+}
+
+int pvnet_ransac_voting_v3(const void *mask, int mask_elem_size, const float *vertex,
+                           const int64_t vertex_strides[5], const int32_t *idxs, const float *selection, int b,
+                           int h, int w, int vn, int hn, float inlier_thresh, int min_num, int max_num,
+                           float *out_pts, int32_t *out_counts, float *out_hyp, int32_t *out_tn, void *workspace,
+                           size_t workspace_bytes, pvnet_stream_t stream)
+{
+    Strides st;
+    if (vertex_strides)
+        for (int i = 0; i < 5; ++i) st.s[i] = vertex_strides[i];
+    int rc = check_common(mask, mask_elem_size, vertex, (const long long *)vertex_strides, idxs, b, h, w, vn, hn);
+    if (rc) return rc;
+    PV_CHECK_ARG(out_pts && workspace, "null out_pts/workspace");
+    VoteWs ws = carve(workspace, b, h, w, vn, hn);
+    if (workspace_bytes < ws.bytes) {
+        pvnet::set_error("workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+        return PVNET_E_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = launch_compaction(mask, mask_elem_size, PVNET_MASK_NONZERO_BYTE, selection, b, h, w, min_num, max_num, ws, s);
+    if (rc) return rc;
+    rc = launch_hyp_and_vote(vertex, st, idxs, b, h, w, vn, hn, inlier_thresh, ws, s);
+    if (rc) return rc;
+    dim3 grf(RF_CHUNKS, b * vn);
+    k_refit<<<grf, RF_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, h * w, vn, hn, ws.hyp, ws.counts, inlier_thresh,
+                                       ws.part, ws.win);
+    PV_LAUNCHED("k_refit");
+    k_refit_final<<<(b * vn + 127) / 128, 128, 0, s>>>(ws.part, ws.tn, b, vn, out_pts);
+    PV_LAUNCHED("k_refit_final");
+    return launch_export(ws, b, vn, hn, out_hyp, out_counts, out_tn, s);
+}
+
+int pvnet_vote_cov_with_mean(const void *mask, int mask_elem_size, const float *vertex,
+                             const int64_t vertex_strides[5], const int32_t *idxs, const float *selection,
+                             const float *mean, int b, int h, int w, int vn, int hn, int rounds, int min_hyp_num,
+                             float inlier_thresh, int min_num, int max_num, float *out_cov, int32_t *out_counts,
+                             float *out_hyp, int32_t *out_tn, void *workspace, size_t workspace_bytes,
+                             pvnet_stream_t stream)
+{
+    Strides st;
+    if (vertex_strides)
+        for (int i = 0; i < 5; ++i) st.s[i] = vertex_strides[i];
+    PV_CHECK_ARG(rounds >= 1 && min_hyp_num >= 1, "rounds/min_hyp_num must be positive");
+    const long long hnt_ll = (long long)hn * rounds;
+    PV_CHECK_ARG(hnt_ll <= (1 << 24), "too many hypotheses");
+    const int hnt = (int)hnt_ll;
+    int rc = check_common(mask, mask_elem_size, vertex, (const long long *)vertex_strides, idxs, b, h, w, vn, hnt);
+    if (rc) return rc;
+    PV_CHECK_ARG(out_cov && mean && workspace, "null out_cov/mean/workspace");
+    VoteWs ws = carve(workspace, b, h, w, vn, hnt);
+    if (workspace_bytes < ws.bytes) {
+        pvnet::set_error("workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+        return PVNET_E_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = launch_compaction(mask, mask_elem_size, PVNET_MASK_EQUALS_ONE, selection, b, h, w, min_num, max_num, ws, s);
+    if (rc) return rc;
+    rc = launch_hyp_and_vote(vertex, st, idxs, b, h, w, vn, hnt, inlier_thresh, ws, s);
+    if (rc) return rc;
+    k_cov<<<b * vn, 256, 0, s>>>(ws.hyp, ws.counts, ws.tn, mean, vn, hnt, min_hyp_num, out_cov);
+    PV_LAUNCHED("k_cov");
+    return launch_export(ws, b, vn, hnt, out_hyp, out_counts, out_tn, s);
+}
+
+int pvnet_generate_hypothesis(const float *direct, const float *coords, const int32_t *idxs, float *hypo, int tn,
+                              int vn, int hn, pvnet_stream_t stream)
+{
+    PV_CHECK_ARG(direct && coords && idxs && hypo, "null pointer");
+    PV_CHECK_ARG(tn >= 1 && vn >= 1 && hn >= 1, "non-positive dimension");
+    k_compat_gen_hyp<<<(hn * vn + 255) / 256, 256, 0, (cudaStream_t)stream>>>(direct, coords, idxs, hypo, tn, vn, hn);
+    PV_LAUNCHED("k_compat_gen_hyp");
+    return PVNET_OK;
+}
+
+int pvnet_voting_for_hypothesis(const float *direct, const float *coords, const float *hypo, uint8_t *inliers,
+                                int tn, int vn, int hn, float inlier_thresh, pvnet_stream_t stream)
+{
+    PV_CHECK_ARG(direct && coords && hypo && inliers, "null pointer");
+    PV_CHECK_ARG(tn >= 1 && vn >= 1 && hn >= 1 && vn <= 65535 && hn <= 65535, "dimension out of range");
+    dim3 grid((tn + 255) / 256, vn, hn);
+    k_compat_vote<<<grid, 256, 0, (cudaStream_t)stream>>>(direct, coords, hypo, inliers, tn, vn, hn, inlier_thresh);
+    PV_LAUNCHED("k_compat_vote");
+    return PVNET_OK;
+}
+
+int pvnet_vote_counts(const float *direct, const float *coords, const float *hypo, int32_t *counts, int tn, int vn,
+                      int hn, float inlier_thresh, pvnet_stream_t stream)
+{
+    PV_CHECK_ARG(direct && coords && hypo && counts, "null pointer");
+    PV_CHECK_ARG(tn >= 1 && vn >= 1 && hn >= 1 && hn <= 65535, "dimension out of range");
+    dim3 grid(vn, hn);
+    k_compat_counts<<<grid, 256, 0, (cudaStream_t)stream>>>(direct, coords, hypo, counts, tn, vn, inlier_thresh);
+    PV_LAUNCHED("k_compat_counts");
+    return PVNET_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""Host side of the B200 voting layer: the reference's Python API over libpvnet_b200.so.
+
+Same names, argument meaning and defaults as zju3dv/pvnet's
+``lib/ransac_voting_gpu_layer/ransac_voting_gpu.py`` for the functions on the
+inference hot path:
+
+    ransac_voting_layer_v3                   (reference :514-598)
+    estimate_voting_distribution_with_mean   (reference :333-406)
+    generate_hypothesis                      (reference :983-1034)
+
+so ``tools/demo.py`` / ``tools/train_linemod.py --test_model`` keep working when
+``lib/ransac_voting_gpu_layer/ransac_voting_gpu.py`` is this module (the shim under
+``lib/`` re-exports it).  Tensors in, tensors out; the work happens in hand-written
+sm_100a kernels behind the C ABI of ``include/pvnet_b200.h``.  There is no CPU or
+PyTorch fallback: without the library or a CUDA device these functions raise.
+
+Randomness (``rng=``):
+  "reference" (default)  replays the reference's torch RNG calls in the reference's
+        order -- per image, ``uniform_`` only when subsampling (:538), then
+        ``random_(0, tn)`` for idxs (:547; once per round at :367) -- so under a fixed
+        ``torch.manual_seed`` the samples are the ones the reference would draw.  This
+        needs the per-image foreground counts on the host: ONE device->host copy per
+        call (the reference does >= 3 blocking syncs per image).
+  "batched"  one ``random_`` (and, if subsampling is possible, one ``uniform_``) call
+        for the whole batch, no host sync at all; statistically equivalent, different
+        stream.
+  explicit ``idxs=`` / ``selection=`` tensors override both (used by the parity tests).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from . import _native
+
+_MASK_NONZERO_BYTE = 0
+_MASK_EQUALS_ONE = 1
+
+_INT_DTYPES = {torch.uint8: 1, torch.int8: 1, torch.bool: 1, torch.int16: 2, torch.int32: 4, torch.int64: 8}
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"pvnet_b200: `{name}` must be a CUDA tensor (there is no CPU path)")
+
+
+def _prep_mask(mask: torch.Tensor, mode: int):
+    """-> (tensor kept alive, element size).  Integer/bool masks are used in place."""
+    if mask.dtype not in _INT_DTYPES:
+        # float masks: `.byte()` (v3) / `== 1` (with_mean) semantics, evaluated by torch once
+        mask = mask.byte() if mode == _MASK_NONZERO_BYTE else (mask == 1).to(torch.uint8)
+    if not mask.is_contiguous():
+        mask = mask.contiguous()
+    return mask, _INT_DTYPES[mask.dtype]
+
+
+def _prep_vertex(vertex: torch.Tensor):
+    if vertex.dtype != torch.float32:
+        vertex = vertex.float()
+    if vertex.dim() != 5 or vertex.shape[-1] != 2:
+        raise ValueError(f"vertex must be [b,h,w,vn,2], got {tuple(vertex.shape)}")
+    strides = (ctypes.c_int64 * 5)(*vertex.stride())
+    return vertex, strides
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _workspace(b, h, w, vn, hn_total, device):
+    n = ctypes.c_size_t()
+    _native.check(_native.lib().pvnet_vote_workspace_bytes(b, h, w, vn, hn_total, ctypes.byref(n)),
+                  "pvnet_vote_workspace_bytes")
+    return torch.empty(n.value, dtype=torch.uint8, device=device), n.value
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def foreground_counts(mask: torch.Tensor, mode: int = _MASK_NONZERO_BYTE) -> torch.Tensor:
+    """int32 [b] foreground pixels per image, on the device (no sync)."""
+    _require_cuda(mask, "mask")
+    m, esz = _prep_mask(mask, mode)
+    b, h, w = m.shape
+    with torch.cuda.device(m.device):
+        out = torch.empty(b, dtype=torch.int32, device=m.device)
+        nchunk = (h * w + 2047) // 2048
+        ws = torch.empty(b * nchunk * 4, dtype=torch.uint8, device=m.device)
+        _native.check(_native.lib().pvnet_mask_foreground_count(_ptr(m), esz, mode, b, h, w, _ptr(out), _ptr(ws),
+                                                                ws.numel(), _stream(m.device)),
+                      "pvnet_mask_foreground_count")
+    return out
+
+
+def _draw_reference(mask, mode, b, h, w, vn, hn, rounds, min_num, max_num):
+    """Replays the reference's RNG calls (see module docstring).  Returns
+    (idxs [b,rounds*hn,vn,2] int32, selection [b,h,w] f32 or None, fg list)."""
+    dev = mask.device
+    fg = foreground_counts(mask, mode).cpu().tolist()          # the one host sync
+    idxs = torch.zeros([b, rounds * hn, vn, 2], dtype=torch.int32, device=dev)
+    selection = None
+    for bi in range(b):
+        if fg[bi] < min_num:
+            continue
+        tn = fg[bi]
+        if fg[bi] > max_num:
+            if selection is None:
+                selection = torch.empty([b, h, w], dtype=torch.float32, device=dev)
+            sel = torch.zeros([h, w], dtype=torch.float32, device=dev).uniform_(0, 1)
+            selection[bi] = sel
+            cur = (mask[bi].byte() != 0) if mode == _MASK_NONZERO_BYTE else (mask[bi] == 1)
+            p = max_num / torch.tensor(fg[bi], device=dev).float()      # same expression as :539
+            tn = int((cur & (sel < p)).sum().item())                    # rare path: second sync
+        for r in range(rounds):
+            idxs[bi, r * hn:(r + 1) * hn] = torch.zeros([hn, vn, 2], dtype=torch.int32,
+                                                        device=dev).random_(0, max(tn, 1))
+    return idxs, selection, fg
+
+
+def _draw_batched(b, h, w, vn, hn_total, max_num, device):
+    idxs = torch.empty([b, hn_total, vn, 2], dtype=torch.int32, device=device).random_(0, 2 ** 31 - 1)
+    selection = None
+    if max_num < h * w:
+        selection = torch.empty([b, h, w], dtype=torch.float32, device=device).uniform_(0, 1)
+    return idxs, selection
+
+
+def _check_injected(idxs, selection, b, h, w, vn, hn_total, device):
+    idxs = torch.as_tensor(idxs, device=device)
+    if idxs.dtype != torch.int32:
+        idxs = idxs.to(torch.int32)
+    if tuple(idxs.shape) != (b, hn_total, vn, 2):
+        raise ValueError(f"idxs must be [b={b},{hn_total},{vn},2], got {tuple(idxs.shape)}")
+    idxs = idxs.contiguous()
+    if selection is not None:
+        selection = torch.as_tensor(selection, device=device, dtype=torch.float32).contiguous()
+        if tuple(selection.shape) != (b, h, w):
+            raise ValueError(f"selection must be [b,h,w], got {tuple(selection.shape)}")
+    return idxs, selection
+
+
+def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                           min_num=5, max_num=30000, *, idxs=None, selection=None, rng="reference",
+                           return_debug=False):
+    """Reference signature (ransac_voting_gpu.py:514-515) plus keyword-only extras.
+
+    :param mask:      [b,h,w] integer/bool CUDA tensor; nonzero (after `.byte()`) = foreground
+    :param vertex:    [b,h,w,vn,2] float32 CUDA tensor, any strides (the NCHW permuted view
+                      the reference's callers pass is read in place)
+    :param round_hyp_num: hypotheses per keypoint
+    :param inlier_thresh: cosine threshold of the inlier test
+    :param confidence, max_iter: accepted for compatibility; the reference's extra RANSAC
+                      rounds re-score the same samples (idxs drawn once at :547), so they
+                      never change its result and are not executed here
+    :return: [b,vn,2] float32 keypoints (x,y); with return_debug also a dict of
+             counts [b,hn,vn] int32, hyp [b,hn,vn,2], tn [b] int32 (device tensors)
+    """
+    del confidence, max_iter
+    _require_cuda(mask, "mask")
+    _require_cuda(vertex, "vertex")
+    b, h, w, vn, _ = vertex.shape
+    hn = int(round_hyp_num)
+    dev = mask.device
+    m, esz = _prep_mask(mask, _MASK_NONZERO_BYTE)
+    v, strides = _prep_vertex(vertex)
+    with torch.cuda.device(dev):
+        if idxs is not None:
+            idxs, selection = _check_injected(idxs, selection, b, h, w, vn, hn, dev)
+        elif rng == "reference":
+            idxs, selection, _ = _draw_reference(m, _MASK_NONZERO_BYTE, b, h, w, vn, hn, 1, min_num, max_num)
+        elif rng == "batched":
+            idxs, selection = _draw_batched(b, h, w, vn, hn, max_num, dev)
+        else:
+            raise ValueError(f"unknown rng mode {rng!r}")
+        out = torch.empty([b, vn, 2], dtype=torch.float32, device=dev)
+        counts = hyp = tn = None
+        if return_debug:
+            counts = torch.empty([b, hn, vn], dtype=torch.int32, device=dev)
+            hyp = torch.empty([b, hn, vn, 2], dtype=torch.float32, device=dev)
+            tn = torch.empty([b], dtype=torch.int32, device=dev)
+        ws, ws_bytes = _workspace(b, h, w, vn, hn, dev)
+        _native.check(_native.lib().pvnet_ransac_voting_v3(
+            _ptr(m), esz, _ptr(v), strides, _ptr(idxs), _ptr(selection), b, h, w, vn, hn,
+            float(inlier_thresh), int(min_num), int(min(max_num, 2 ** 31 - 1)),
+            _ptr(out), _ptr(counts), _ptr(hyp), _ptr(tn), _ptr(ws), ws_bytes, _stream(dev)),
+            "pvnet_ransac_voting_v3")
+    if return_debug:
+        return out, dict(counts=counts, hyp=hyp, tn=tn, idxs=idxs, selection=selection)
+    return out
+
+
+def estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=256, min_hyp_num=4096, topk=128,
+                                           inlier_thresh=0.99, min_num=5, max_num=30000, output_hyp=False, *,
+                                           idxs=None, selection=None, rng="reference", return_debug=False):
+    """Reference signature (ransac_voting_gpu.py:333-334).  Returns (mean, cov [b,vn,2,2]).
+
+    mask foreground is `mask == 1` here (:339), not `nonzero` as in v3.  `topk` and
+    `output_hyp` are unused by the reference in this variant and are ignored.
+    idxs, when injected, is [b, rounds*round_hyp_num, vn, 2] with rounds =
+    ceil(min_hyp_num/round_hyp_num).
+    """
+    del topk, output_hyp
+    _require_cuda(mask, "mask")
+    _require_cuda(vertex, "vertex")
+    b, h, w, vn, _ = vertex.shape
+    hn = int(round_hyp_num)
+    rounds = int(math.ceil(min_hyp_num / round_hyp_num))
+    hnt = hn * rounds
+    dev = mask.device
+    m, esz = _prep_mask(mask, _MASK_EQUALS_ONE)
+    v, strides = _prep_vertex(vertex)
+    mean_c = mean.to(device=dev, dtype=torch.float32).contiguous()
+    if tuple(mean_c.shape) != (b, vn, 2):
+        raise ValueError(f"mean must be [b,vn,2], got {tuple(mean_c.shape)}")
+    with torch.cuda.device(dev):
+        if idxs is not None:
+            idxs, selection = _check_injected(idxs, selection, b, h, w, vn, hnt, dev)
+        elif rng == "reference":
+            idxs, selection, fg = _draw_reference(m, _MASK_EQUALS_ONE, b, h, w, vn, hn, rounds, min_num, max_num)
+            skipped = [f < min_num for f in fg]
+            if any(skipped) and not all(skipped) and int(min_hyp_num) != hnt:
+                # the reference's torch.cat at :389 fails on this mix
+                raise RuntimeError("Sizes of tensors must match except in dimension 0 "
+                                   f"(skipped images carry {min_hyp_num} rows, others {hnt})")
+        elif rng == "batched":
+            idxs, selection = _draw_batched(b, h, w, vn, hnt, max_num, dev)
+        else:
+            raise ValueError(f"unknown rng mode {rng!r}")
+        cov = torch.empty([b, vn, 2, 2], dtype=torch.float32, device=dev)
+        counts = hyp = tn = None
+        if return_debug:
+            counts = torch.empty([b, hnt, vn], dtype=torch.int32, device=dev)
+            hyp = torch.empty([b, hnt, vn, 2], dtype=torch.float32, device=dev)
+            tn = torch.empty([b], dtype=torch.int32, device=dev)
+        ws, ws_bytes = _workspace(b, h, w, vn, hnt, dev)
+        _native.check(_native.lib().pvnet_vote_cov_with_mean(
+            _ptr(m), esz, _ptr(v), strides, _ptr(idxs), _ptr(selection), _ptr(mean_c), b, h, w, vn, hn, rounds,
+            int(min_hyp_num), float(inlier_thresh), int(min_num), int(min(max_num, 2 ** 31 - 1)),
+            _ptr(cov), _ptr(counts), _ptr(hyp), _ptr(tn), _ptr(ws), ws_bytes, _stream(dev)),
+            "pvnet_vote_cov_with_mean")
+    if return_debug:
+        return mean, cov, dict(counts=counts, hyp=hyp, tn=tn, idxs=idxs, selection=selection)
+    return mean, cov
+
+
+def generate_hypothesis(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                        min_num=5, max_num=30000, *, idxs=None, selection=None, rng="reference"):
+    """Reference ransac_voting_gpu.py:983-1034: the hypotheses [b,hn,vn,2] and their
+    inlier counts [b,hn,vn] (int64, as torch.sum of a uint8 tensor gives).  Used by
+    tools/demo.py:120-134 (`visualize_hypothesis`).  The reference's skip branch hits a
+    NameError (:1003); here an image below min_num contributes zeros."""
+    _, dbg = ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh, confidence, max_iter, min_num,
+                                    max_num, idxs=idxs, selection=selection, rng=rng, return_debug=True)
+    return dbg["hyp"], dbg["counts"].long()

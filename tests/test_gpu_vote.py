@@ -1,0 +1,264 @@
+"""GPU parity tests of the voting layer: libpvnet_b200.so (through its C ABI, via the
+Python host layer) against the CPU oracle on the same seeded inputs.
+
+Bar: hypotheses and inlier counts bit-exact; keypoints / covariances within 1e-4 abs
+of the oracle (the oracle's refit is fp64; the product accumulates in fp64 too).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pvnet_oracle as po
+from pvnet_b200 import ransac_voting as ext
+from pvnet_b200 import ransac_voting_gpu as rv
+from pvnet_b200 import synthetic as syn
+from tests.helpers import cfg1_inputs, demo_fixture
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+KP_TOL = 1e-4
+
+
+def _to_dev(mask_np, field_np, mask_dtype=torch.int64):
+    """mask [b,h,w], field NCHW [b,2k,h,w] -> (mask tensor, vertex as the permuted NCHW view)."""
+    mask = torch.from_numpy(np.ascontiguousarray(mask_np)).to(DEV).to(mask_dtype)
+    ver = torch.from_numpy(np.ascontiguousarray(field_np)).to(DEV)
+    b, c2, h, w = ver.shape
+    vertex = ver.permute(0, 2, 3, 1).view(b, h, w, c2 // 2, 2)
+    assert not vertex.is_contiguous()
+    return mask, vertex
+
+
+def _check_v3(mask_np, field_np, hn, thresh, idxs_list, selection=None, max_num=30000, min_num=5,
+              mask_dtype=torch.int64):
+    b = mask_np.shape[0]
+    vn = field_np.shape[1] // 2
+    mask, vertex = _to_dev(mask_np, field_np, mask_dtype)
+    idxs_dev = np.zeros((b, hn, vn, 2), np.int32)
+    for i, ix in enumerate(idxs_list):
+        if ix is not None:
+            idxs_dev[i] = ix
+    sel_dev = None if selection is None else np.stack(selection)
+    kp, dbg = rv.ransac_voting_layer_v3(mask, vertex, hn, inlier_thresh=thresh, min_num=min_num, max_num=max_num,
+                                        idxs=torch.from_numpy(idxs_dev), selection=sel_dev, return_debug=True)
+    torch.cuda.synchronize()
+    okp, odbg = po.ransac_voting_layer_v3(mask_np, syn.as_reference_view(field_np), hn, inlier_thresh=thresh,
+                                          min_num=min_num, max_num=max_num, idxs=idxs_list, selection=selection,
+                                          return_debug=True)
+    kp, counts, hyp, tn = kp.cpu().numpy(), dbg["counts"].cpu().numpy(), dbg["hyp"].cpu().numpy(), dbg["tn"].cpu().numpy()
+    for bi in range(b):
+        if odbg[bi] is None:
+            assert tn[bi] == 0
+            assert np.array_equal(kp[bi], np.zeros((vn, 2), np.float32))
+            continue
+        assert tn[bi] == odbg[bi]["tn"]
+        assert np.array_equal(hyp[bi].view(np.uint32), odbg[bi]["hyp"].view(np.uint32)), "hypotheses not bit-exact"
+        assert np.array_equal(counts[bi], odbg[bi]["counts"]), "inlier counts not bit-exact"
+        both_nan = np.isnan(kp[bi]) & np.isnan(okp[bi])
+        assert np.all(both_nan | (np.abs(kp[bi] - okp[bi]) <= KP_TOL)), (kp[bi], okp[bi])
+    return kp, okp
+
+
+@pytest.mark.parametrize("kind", ["random", "planted"])
+def test_config1_vs_oracle(kind):
+    mask, field, idxs = cfg1_inputs(kind)
+    _check_v3(mask[None], field[None], 128, 0.99, [idxs])
+
+
+def test_demo_known_answer():
+    mask, field, pts = demo_fixture()
+    idxs = syn.draw_idxs(2289, 512, 9, seed=7)
+    kp, _ = _check_v3(mask[None], field[None], 512, 0.99, [idxs])
+    assert np.abs(kp[0] - pts).max() < 1e-2
+
+
+def test_compat_kernels_bit_exact():
+    """pvnet_generate_hypothesis / pvnet_voting_for_hypothesis / pvnet_vote_counts are the
+    1:1 stand-ins for the reference extension (ransac_voting.cpp:102-107)."""
+    mask, field, idxs = cfg1_inputs("planted")
+    coords, direct = po.compact(mask.astype(np.uint8), syn.as_reference_view(field[None])[0])
+    d, c, i = (torch.from_numpy(a).to(DEV) for a in (direct, coords, idxs))
+    hyp = ext.generate_hypothesis(d, c, i)
+    ohyp = po.generate_hypothesis_kernel(direct, coords, idxs)
+    assert np.array_equal(hyp.cpu().numpy().view(np.uint32), ohyp.view(np.uint32))
+    inl = torch.zeros([16, 9, 10000], dtype=torch.uint8, device=DEV)
+    ext.voting_for_hypothesis(d, c, hyp[:16].contiguous(), inl, 0.99)
+    assert np.array_equal(inl.cpu().numpy(), po.voting_for_hypothesis_kernel(direct, coords, ohyp[:16], 0.99))
+    cnt = ext.vote_counts(d, c, hyp, 0.99)
+    assert np.array_equal(cnt.cpu().numpy(), po.vote_counts(direct, coords, ohyp, 0.99))
+
+
+@pytest.mark.parametrize("thresh", [0.999, 0.9, 0.5, 1e-3, 0.0, -0.5])
+def test_thresholds(thresh):
+    mask = syn.disc_mask(3000)
+    field = syn.planted_field(mask, 5, 33, sigma=0.2)[0]
+    _check_v3(mask[None], field[None], 96, thresh, [syn.draw_idxs(3000, 96, 5, seed=5)])
+
+
+@pytest.mark.parametrize("hn,vn", [(100, 3), (31, 1), (500, 9), (1024, 17), (2048, 2), (3000, 2)])
+def test_ragged_hypothesis_counts(hn, vn):
+    mask = syn.disc_mask(2500)
+    field = syn.random_field(mask, vn, 77)
+    _check_v3(mask[None], field[None], hn, 0.99, [syn.draw_idxs(2500, hn, vn, seed=hn)])
+
+
+def test_batch_with_ragged_images_and_skips():
+    ns = [10000, 0, 4, 5, 2049, 30000, 777]
+    masks = np.stack([syn.disc_mask(n) for n in ns])
+    fields = np.stack([syn.planted_field(masks[i], 9, 100 + i)[0] for i in range(len(ns))])
+    idxs = [syn.draw_idxs(n, 64, 9, seed=i) if n >= 5 else None for i, n in enumerate(ns)]
+    _check_v3(masks, fields, 64, 0.99, idxs)
+
+
+def test_subsample_with_injected_selection():
+    ns = [40000, 20000, 92160]
+    masks = np.stack([syn.disc_mask(n) for n in ns])
+    fields = np.stack([syn.planted_field(masks[i], 4, 200 + i)[0] for i in range(3)])
+    sels = [syn.selection_field(50 + i) for i in range(3)]
+    idxs = []
+    for i, n in enumerate(ns):
+        tn = n
+        if n > 30000:
+            p = po.subsample_probability(30000, n)
+            tn = int(((sels[i] < p) & (masks[i] != 0)).sum())
+        idxs.append(syn.draw_idxs(tn, 128, 4, seed=i))
+    _check_v3(masks, fields, 128, 0.99, idxs, selection=sels, max_num=30000)
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int32, torch.int16, torch.bool])
+def test_mask_dtypes(dtype):
+    mask = syn.disc_mask(1500)
+    field = syn.planted_field(mask, 3, 9)[0]
+    _check_v3(mask[None], field[None], 64, 0.99, [syn.draw_idxs(1500, 64, 3, seed=2)], mask_dtype=dtype)
+
+
+def test_mask_values_above_one_and_low_byte():
+    """v3 foreground = low byte nonzero: 2 counts, 256 does not (.byte(), :527)."""
+    base = syn.disc_mask(2000)
+    mask = base.copy()
+    mask[base == 1] = 2
+    mask[0, :10] = 256
+    field = syn.planted_field(base, 3, 9)[0]
+    _check_v3(mask[None], field[None], 64, 0.99, [syn.draw_idxs(2000, 64, 3, seed=2)])
+
+
+def test_contiguous_vertex_layout():
+    """vertex given as a plain contiguous [b,h,w,vn,2] tensor (generic stride path)."""
+    mask_np = syn.disc_mask(1200)
+    field = syn.planted_field(mask_np, 4, 3)[0]
+    idxs = syn.draw_idxs(1200, 64, 4, seed=1)
+    vertex_np = np.ascontiguousarray(syn.as_reference_view(field[None]))
+    mask = torch.from_numpy(mask_np[None]).to(DEV)
+    kp, dbg = rv.ransac_voting_layer_v3(mask, torch.from_numpy(vertex_np).to(DEV), 64, inlier_thresh=0.99,
+                                        idxs=torch.from_numpy(idxs[None]), return_debug=True)
+    okp, odbg = po.ransac_voting_layer_v3(mask_np[None], vertex_np, 64, inlier_thresh=0.99, idxs=[idxs],
+                                          return_debug=True)
+    assert np.array_equal(dbg["counts"][0].cpu().numpy(), odbg[0]["counts"])
+    assert np.abs(kp.cpu().numpy() - okp).max() <= KP_TOL
+
+
+def test_zero_and_tiny_direction_vectors():
+    """pixels whose vector is 0 or ~1e-6 long: norm1 < 1e-6 -> never an inlier (kernel :121)."""
+    mask = syn.disc_mask(1000)
+    field = syn.planted_field(mask, 2, 4)[0]
+    ys, xs = np.nonzero(mask)
+    field[:, ys[:100], xs[:100]] = 0.0
+    field[:, ys[100:200], xs[100:200]] *= 0.9e-6
+    field[:, ys[200:300], xs[200:300]] *= 1.1e-6
+    _check_v3(mask[None], field[None], 128, 0.99, [syn.draw_idxs(1000, 128, 2, seed=8)])
+
+
+def test_degenerate_hypotheses_are_scored():
+    mask = syn.disc_mask(500)
+    field = np.zeros((2, 480, 640), np.float32)
+    field[0] = (mask != 0)          # every vector (1,0): all pairs parallel -> hypothesis (0,0)
+    _check_v3(mask[None], field[None], 32, 0.99, [syn.draw_idxs(500, 32, 1, seed=1)])
+
+
+def test_covariance_vs_oracle():
+    ns = [6000, 3, 2500]
+    masks = np.stack([syn.disc_mask(n) for n in ns])
+    fields = np.stack([syn.planted_field(masks[i], 5, 300 + i, sigma=0.05)[0] for i in range(3)])
+    vertex_np = syn.as_reference_view(fields)
+    idxs_v3 = [syn.draw_idxs(n, 64, 5, seed=i) if n >= 5 else None for i, n in enumerate(ns)]
+    mean_np = po.ransac_voting_layer_v3(masks, vertex_np, 64, inlier_thresh=0.99, idxs=idxs_v3)
+    rounds, hn = 4, 32                     # min_hyp_num = 128 = rounds*hn so skipped rows match
+    idxs = [syn.draw_idxs(n, hn, 5, seed=10 + i, rounds=rounds) if n >= 5 else None for i, n in enumerate(ns)]
+    _, ocov, odbg = po.estimate_voting_distribution_with_mean(masks, vertex_np, mean_np, round_hyp_num=hn,
+                                                              min_hyp_num=128, inlier_thresh=0.99, idxs=idxs,
+                                                              return_debug=True)
+    mask, vertex = _to_dev(masks, fields)
+    idxs_dev = np.zeros((3, rounds * hn, 5, 2), np.int32)
+    for i, ix in enumerate(idxs):
+        if ix is not None:
+            idxs_dev[i] = ix.reshape(rounds * hn, 5, 2)
+    mean, cov, dbg = rv.estimate_voting_distribution_with_mean(mask, vertex, torch.from_numpy(mean_np).to(DEV),
+                                                               round_hyp_num=hn, min_hyp_num=128, inlier_thresh=0.99,
+                                                               idxs=torch.from_numpy(idxs_dev), return_debug=True)
+    cov = cov.cpu().numpy()
+    for bi in range(3):
+        if odbg[bi] is not None:
+            assert np.array_equal(dbg["counts"][bi].cpu().numpy(), odbg[bi]["counts"])
+    assert np.allclose(cov, ocov, atol=1e-4, rtol=1e-5), np.abs(cov - ocov).max()
+
+
+def test_covariance_mask_equals_one_semantics():
+    """with_mean uses mask == 1 (:339): pixels labelled 2 do not take part."""
+    base = syn.disc_mask(3000)
+    mask = base.copy()
+    ys, xs = np.nonzero(base)
+    mask[ys[:1000], xs[:1000]] = 2
+    field = syn.planted_field(base, 2, 12)[0]
+    vertex_np = syn.as_reference_view(field[None])
+    mean_np = np.array([[[400.0, 240.0], [300.0, 100.0]]], np.float32)
+    idxs = syn.draw_idxs(2000, 64, 2, seed=4, rounds=2)
+    _, ocov, odbg = po.estimate_voting_distribution_with_mean(mask[None], vertex_np, mean_np, round_hyp_num=64,
+                                                              min_hyp_num=128, idxs=[idxs], return_debug=True)
+    assert odbg[0]["tn"] == 2000
+    m, v = _to_dev(mask[None], field[None])
+    _, cov, dbg = rv.estimate_voting_distribution_with_mean(m, v, torch.from_numpy(mean_np).to(DEV), round_hyp_num=64,
+                                                            min_hyp_num=128, idxs=torch.from_numpy(idxs.reshape(1, 128, 2, 2)),
+                                                            return_debug=True)
+    assert int(dbg["tn"][0]) == 2000
+    assert np.array_equal(dbg["counts"][0].cpu().numpy(), odbg[0]["counts"])
+    assert np.allclose(cov.cpu().numpy(), ocov, atol=1e-4, rtol=1e-5)
+
+
+def test_full_size_against_exact_gpu_kernel():
+    """BASELINE config 3's largest point (150k pixels, 2048 hypotheses, K=9) is too slow
+    for the CPU oracle in a test; the fused kernel's counts are checked bit for bit
+    against pvnet_vote_counts (the exact-sequence kernel, itself pinned to the oracle
+    above), and the per-keypoint totals against a float64 torch restatement's ballpark."""
+    n, hn, vn = 150000, 2048, 9
+    mask_np = syn.disc_mask(n)
+    field = syn.planted_field(mask_np, vn, 999)[0]
+    mask, vertex = _to_dev(mask_np[None], field[None])
+    idxs = torch.from_numpy(syn.draw_idxs(n, hn, vn, seed=3)[None])
+    kp, dbg = rv.ransac_voting_layer_v3(mask, vertex, hn, inlier_thresh=0.99, max_num=10 ** 9, idxs=idxs,
+                                        return_debug=True)
+    assert int(dbg["tn"][0]) == n
+    ys, xs = np.nonzero(mask_np)
+    coords = torch.from_numpy(np.stack([xs, ys], 1).astype(np.float32)).to(DEV)
+    direct = vertex[0][torch.from_numpy(ys).to(DEV), torch.from_numpy(xs).to(DEV)].contiguous()
+    exact = ext.vote_counts(direct, coords, dbg["hyp"][0].contiguous(), 0.99)
+    assert torch.equal(exact, dbg["counts"][0])
+    kps = syn.planted_keypoints(vn)
+    assert np.abs(kp[0].cpu().numpy() - kps).max() < 0.5
+
+
+def test_no_cpu_tensors():
+    with pytest.raises(RuntimeError):
+        rv.ransac_voting_layer_v3(torch.zeros(1, 8, 8, dtype=torch.int64), torch.zeros(1, 8, 8, 1, 2), 8)
+
+
+def test_rng_modes_run_and_agree_statistically():
+    mask_np = syn.disc_mask(8000)
+    field, kps = syn.planted_field(mask_np, 9, 5)
+    mask, vertex = _to_dev(np.stack([mask_np] * 3), np.stack([field] * 3))
+    torch.manual_seed(0)
+    a = rv.ransac_voting_layer_v3(mask, vertex, 256, inlier_thresh=0.99)
+    torch.manual_seed(0)
+    a2 = rv.ransac_voting_layer_v3(mask, vertex, 256, inlier_thresh=0.99)
+    assert torch.equal(a, a2)
+    c = rv.ransac_voting_layer_v3(mask, vertex, 256, inlier_thresh=0.99, rng="batched")
+    assert np.abs(a.cpu().numpy() - kps[None]).max() < 20 and np.abs(c.cpu().numpy() - kps[None]).max() < 20
