@@ -142,8 +142,28 @@ PVNET_API long long pvnet_launch_count(void);
 PVNET_API void pvnet_launch_count_reset(void);
 
 /* -------------------------------------------------------------------- backbone */
-/* Declared in the second half of this header once the conv path lands:
- * pvnet_backbone_{create,load_weights,workspace_bytes,forward,destroy}. */
+
+/* One NHWC convolution on the tcgen05 tensor cores (TF32 inputs, fp32 accumulate), the
+ * building block of Resnet18_8s (lib/networks/resnet.py:28-35,54-70; model_repository.py:22-58):
+ *
+ *   out[n,y,x,out_co+co] = act( bias[co] + res[n,y,x,res_co+co]
+ *                               + sum_{kh,kw,ci} w[co][kh][kw][ci] * in[n, y*stride+(kh-c)*dil, x*stride+(kw-c)*dil, in_co+ci] )
+ *
+ *   in        NHWC buffer [b,H,W,in_cs]; the conv reads channels [in_co, in_co+Cin)
+ *   w_packed  [Cout][ksize*ksize][Cin] fp32 (BatchNorm already folded in), bias [Cout]
+ *   res       NHWC [b,H/stride,W/stride,res_cs] read at res_co, or NULL
+ *   out       NHWC [b,H/stride,W/stride,out_cs] written at channel offset out_co
+ *             (writing into a slice of a wider buffer replaces torch.cat)
+ *   ksize 1|3, stride 1|2 (2 needs even H,W, dilation 1), padding = dilation*(ksize-1)/2
+ *   act 0 none, 1 ReLU, 2 LeakyReLU(0.1); round_out != 0 rounds the stored values to TF32
+ *   Cin multiple of 8, Cout multiple of 32; strides/offsets multiples of 4 floats.
+ */
+PVNET_API int pvnet_conv2d_nhwc(const float *in, int in_cs, int in_co, int Cin,
+                                const float *w_packed, const float *bias,
+                                const float *res, int res_cs, int res_co,
+                                float *out, int out_cs, int out_co, int Cout,
+                                int b, int H, int W, int ksize, int stride, int dilation,
+                                int act, int round_out, pvnet_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -87,9 +87,12 @@ def _select_pixels(cur_mask_u8, vertex_img, vn):
 
 
 def layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5,
-             max_num=30000, record=None):
+             max_num=30000, record=None, refit_dtype=torch.float32):
     """The reference's v3, torch op for torch op (RNG calls included).  `record`, if a list,
-    receives per-image dicts (idxs, counts, tn, selection) for the parity tests."""
+    receives per-image dicts (idxs, counts, tn, selection) for the parity tests.
+    refit_dtype=torch.float64 runs the SAME least-squares refit ops (:578-595) in double:
+    the difference to the float32 run is the reference's own rounding noise (cuBLAS /
+    torch.sum fp32 summation order), which no other implementation can reproduce."""
     b, h, w, vn, _ = vertex.shape
     dev = mask.device
     results = []
@@ -137,13 +140,13 @@ def layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, 
         normal[:, :, 1] = -direct[:, :, 0]
         final_inl = torch.zeros([1, vn, tn], dtype=torch.uint8, device=dev)
         voting_for_hypothesis(direct, coords, best_pts[None].contiguous(), final_inl, inlier_thresh)
-        wgt = final_inl.float()[0]                              # [vn,tn]
-        normal = normal.permute(1, 0, 2) * wgt[:, :, None]      # [vn,tn,2]
-        rhs = torch.sum(normal * coords[None], 2)               # [vn,tn]
+        wgt = final_inl.to(refit_dtype)[0]                      # [vn,tn]
+        normal = normal.to(refit_dtype).permute(1, 0, 2) * wgt[:, :, None]      # [vn,tn,2]
+        rhs = torch.sum(normal * coords.to(refit_dtype)[None], 2)               # [vn,tn]
         ata = torch.matmul(normal.permute(0, 2, 1), normal)     # [vn,2,2]
         atb = torch.sum(normal * rhs[:, :, None], 1)            # [vn,2]
         pts = torch.matmul(_inverse_2x2(ata), atb[:, :, None])  # [vn,2,1]
-        results.append(pts[None, :, :, 0])
+        results.append(pts[None, :, :, 0].float())
         rec["rounds"] = rounds
         if record is not None:
             record.append(rec)

@@ -1,0 +1,396 @@
+// conv_tc.cu -- implicit-GEMM 2-D convolution on the 5th-gen tensor cores (sm_100a).
+//
+// One CTA computes a 128-pixel x BN-channel output tile of an NHWC convolution
+// (lib/networks/resnet.py:28-35 `conv3x3`, the 1x1 downsample convs, and the decoder convs
+// of lib/networks/model_repository.py:22-58), with BatchNorm folded into weights/bias and
+// the activation / residual add fused into the epilogue:
+//
+//   M = 128 output pixels (a TH x TW patch of one image), one TMEM lane each
+//   N = BN output channels (<= 256), one TMEM fp32 column each
+//   K = taps x Cin, walked tap by tap in chunks of KC input channels
+//
+//   warp 0    TMA producer: per K-block one 4-D box {KC ch, TW, TH, 1 image} of the NHWC
+//             input, shifted by the tap's (dy,dx)*dilation -- out-of-bounds coordinates are
+//             zero-filled by TMA, which IS the conv padding -- plus one 2-D box {KC, BN} of
+//             the packed weights [Cout][tap][Cin]; 128B/32B-swizzled K-major tiles.
+//   warp 1    TMEM allocation; one elected lane issues tcgen05.mma.kind::tf32 (fp32
+//             accumulate in TMEM) and commits to the stage's "empty" mbarrier.
+//   warps 2-5 epilogue: tcgen05.ld 32 columns at a time -> +bias (+residual) -> ReLU /
+//             LeakyReLU(0.1) -> optional round-to-tf32 -> 128-bit NHWC stores at a channel
+//             offset of a (possibly wider) destination buffer, so torch.cat never happens.
+//
+// Stride-2 convolutions read the input through four "parity plane" tensor maps (even/odd
+// rows x even/odd columns); each tap then is a stride-1 box in one plane.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <mutex>
+
+namespace pvnet {
+
+struct ConvGeom {
+    int Ho, Wo;
+    int tiles_x, tiles_y;
+    int TH, TW;
+    int taps, cin_chunks, cin_pad;
+    int Cout, BN;
+    int out_cs, out_co;
+    int res_cs, res_co;
+    int act;        // 0 none, 1 ReLU, 2 LeakyReLU(0.1)
+    int round_out;  // round stored values to tf32 (they feed another tensor-core conv)
+    signed char tap_map[9];
+    short tap_ox[9], tap_oy[9];
+};
+
+struct AMaps {
+    CUtensorMap m[4];
+};
+
+constexpr int CONV_THREADS = 192;
+
+template <int KC>
+struct ConvCfg {
+    static constexpr int SWIZZLE = KC * 4;              // bytes per K-major row: 128 or 32
+    static constexpr int A_BYTES = 128 * KC * 4;
+    static constexpr int STAGES = KC == 32 ? 4 : 8;
+    static constexpr int b_bytes(int bn) { return bn * KC * 4; }
+    static constexpr size_t smem_bytes(int bn)
+    {
+        return 1024 + (size_t)STAGES * (A_BYTES + b_bytes(bn)) + 256;
+    }
+};
+
+template <int KC>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+    k_conv_tc(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap tmB, const ConvGeom g,
+              const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out)
+{
+    using Cfg = ConvCfg<KC>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_bytes = g.BN * KC * 4;
+    const int stage_bytes = Cfg::A_BYTES + b_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * stage_bytes);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = g.tiles_x * g.tiles_y;
+    const int img = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - img * tiles_per_img;
+    const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
+    const int y0 = tyi * g.TH, x0 = txi * g.TW;
+    const int n0 = blockIdx.y * g.BN;
+    const int nkb = g.taps * g.cin_chunks;
+
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)g.BN) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmB);
+        ptx::prefetch_tensormap(&amaps.m[0]);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        ptx::mbar_init(tmem_full, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                ptx::mbar_wait(&empty[s], ph ^ 1u);
+                ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+                const int tap = kb / g.cin_chunks, cc = kb - tap * g.cin_chunks;
+                uint8_t *sa = smem + (size_t)s * stage_bytes;
+                ptx::tma_load_4d(sa, &amaps.m[g.tap_map[tap]], &full[s], cc * KC, x0 + g.tap_ox[tap],
+                                 y0 + g.tap_oy[tap], img);
+                ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], tap * g.cin_pad + cc * KC, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::make_idesc_tf32(128, g.BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                ptx::mbar_wait(&full[s], ph);
+                ptx::tc_fence_after();
+                const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t adesc = ptx::make_kmajor_desc(sa, Cfg::SWIZZLE);
+                const uint64_t bdesc = ptx::make_kmajor_desc(sa + Cfg::A_BYTES, Cfg::SWIZZLE);
+#pragma unroll
+                for (int k = 0; k < KC / 8; ++k)   // 8 tf32 = 32 B per MMA along K: +2 in 16-byte units
+                    ptx::mma_tf32_ss(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
+                ptx::mma_commit(&empty[s]);
+            }
+            ptx::mma_commit(tmem_full);
+        }
+    } else {
+        // TMEM lane quarter a warp may touch is (warp id % 4)
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int ty = m / g.TW, tx = m - ty * g.TW;
+        const int y = y0 + ty, x = x0 + tx;
+        const bool valid = (y < g.Ho) && (x < g.Wo);
+        const size_t pix = ((size_t)img * g.Ho + y) * g.Wo + x;
+        float *optr = out + pix * g.out_cs + g.out_co + n0;
+        const float *rptr = res ? res + pix * g.res_cs + g.res_co + n0 : nullptr;
+        ptx::mbar_wait(tmem_full, 0);
+        ptx::tc_fence_after();
+        for (int c0 = 0; c0 < g.BN; c0 += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            ptx::tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n0 + c0 + j));
+                    float4 v = make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
+                                           __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w);
+                    if (rptr) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4 *>(rptr + c0 + j));
+                        v.x += rv.x;
+                        v.y += rv.y;
+                        v.z += rv.z;
+                        v.w += rv.w;
+                    }
+                    if (g.act == 1) {
+                        v.x = fmaxf(v.x, 0.f);
+                        v.y = fmaxf(v.y, 0.f);
+                        v.z = fmaxf(v.z, 0.f);
+                        v.w = fmaxf(v.w, 0.f);
+                    } else if (g.act == 2) {
+                        v.x = v.x > 0.f ? v.x : 0.1f * v.x;
+                        v.y = v.y > 0.f ? v.y : 0.1f * v.y;
+                        v.z = v.z > 0.f ? v.z : 0.1f * v.z;
+                        v.w = v.w > 0.f ? v.w : 0.1f * v.w;
+                    }
+                    if (g.round_out) {
+                        v.x = ptx::round_tf32(v.x);
+                        v.y = ptx::round_tf32(v.y);
+                        v.z = ptx::round_tf32(v.z);
+                        v.w = ptx::round_tf32(v.w);
+                    }
+                    *reinterpret_cast<float4 *>(optr + c0 + j) = v;
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+static int encode(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
+                  const cuuint32_t *box, int swizzle_bytes)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return PVNET_E_CUDA;
+    }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                        : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), dims,
+                    strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u, swizzle %d)",
+                  (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1],
+                  swizzle_bytes);
+        return PVNET_E_CUDA;
+    }
+    return PVNET_OK;
+}
+
+// A fully described convolution launch (tensor maps are encoded once and can be reused as
+// long as the pointers and shapes stay the same).
+struct ConvPlan {
+    AMaps amaps;
+    CUtensorMap tmB;
+    ConvGeom g;
+    int kc;
+    dim3 grid;
+    size_t smem;
+    const float *bias, *res;
+    float *out;
+};
+
+struct ConvDesc {
+    const float *in;   // NHWC buffer [b,H,W,in_cs], channels [in_co, in_co+Cin) are the conv input
+    int in_cs, in_co, Cin;
+    const float *w;    // packed [Cout][taps][cin_pad]
+    const float *bias; // [Cout]
+    const float *res;  // NHWC [b,Ho,Wo,res_cs] at res_co, or null
+    int res_cs, res_co;
+    float *out;        // NHWC [b,Ho,Wo,out_cs], written at out_co
+    int out_cs, out_co, Cout;
+    int b, H, W;
+    int ksize, stride, dilation;
+    int act, round_out;
+};
+
+int conv_cin_pad(int Cin) { return Cin % 32 == 0 ? Cin : (Cin + 7) / 8 * 8; }
+int conv_kc(int Cin) { return Cin % 32 == 0 ? 32 : 8; }
+
+int conv_plan(const ConvDesc &d, ConvPlan *p)
+{
+    PV_CHECK_ARG(d.in && d.w && d.bias && d.out, "conv: null pointer");
+    PV_CHECK_ARG(d.ksize == 1 || d.ksize == 3, "conv: kernel size %d unsupported", d.ksize);
+    PV_CHECK_ARG(d.stride == 1 || d.stride == 2, "conv: stride %d unsupported", d.stride);
+    PV_CHECK_ARG(d.stride == 1 || (d.dilation == 1 && d.H % 2 == 0 && d.W % 2 == 0),
+                 "conv: stride 2 needs dilation 1 and even H,W");
+    PV_CHECK_ARG(d.Cout % 32 == 0, "conv: Cout %d must be a multiple of 32", d.Cout);
+    PV_CHECK_ARG(d.in_cs % 4 == 0 && d.in_co % 4 == 0 && d.out_cs % 4 == 0 && d.out_co % 4 == 0,
+                 "conv: channel strides/offsets must be multiples of 4 floats");
+    PV_CHECK_ARG(!d.res || (d.res_cs % 4 == 0 && d.res_co % 4 == 0), "conv: residual stride/offset alignment");
+    PV_CHECK_ARG(((uintptr_t)d.in % 16 == 0) && ((uintptr_t)d.w % 16 == 0) && ((uintptr_t)d.out % 16 == 0) &&
+                     ((uintptr_t)d.bias % 16 == 0),
+                 "conv: pointers must be 16-byte aligned");
+    const int kc = conv_kc(d.Cin);
+    PV_CHECK_ARG(d.Cin % kc == 0, "conv: Cin %d must be a multiple of 8", d.Cin);
+    ConvGeom &g = p->g;
+    g.Ho = d.H / d.stride;
+    g.Wo = d.W / d.stride;
+    // 128-pixel patch: wide for big maps (full 128-byte rows per warp), 8x16 otherwise
+    g.TH = 8;
+    g.TW = 16;
+    g.tiles_x = (g.Wo + g.TW - 1) / g.TW;
+    g.tiles_y = (g.Ho + g.TH - 1) / g.TH;
+    g.taps = d.ksize * d.ksize;
+    g.cin_pad = d.Cin;
+    g.cin_chunks = d.Cin / kc;
+    g.Cout = d.Cout;
+    g.BN = d.Cout > 256 ? 256 : d.Cout;
+    PV_CHECK_ARG(d.Cout % g.BN == 0, "conv: Cout %d not a multiple of the N tile %d", d.Cout, g.BN);
+    g.out_cs = d.out_cs;
+    g.out_co = d.out_co;
+    g.res_cs = d.res_cs;
+    g.res_co = d.res_co;
+    g.act = d.act;
+    g.round_out = d.round_out;
+    const int pad = d.dilation * (d.ksize - 1) / 2;
+    for (int t = 0; t < g.taps; ++t) {
+        const int kh = t / d.ksize, kw = t - kh * d.ksize;
+        if (d.stride == 1) {
+            g.tap_map[t] = 0;
+            g.tap_ox[t] = (short)(kw * d.dilation - pad);
+            g.tap_oy[t] = (short)(kh * d.dilation - pad);
+        } else {
+            // input coordinate 2*o + k - pad: parity plane (k-pad)&1, plane coordinate o + floor((k-pad)/2)
+            const int dy = kh - pad, dx = kw - pad;
+            const int py = dy & 1, px = dx & 1;
+            g.tap_map[t] = (signed char)(py * 2 + px);
+            g.tap_oy[t] = (short)((dy - py) / 2);
+            g.tap_ox[t] = (short)((dx - px) / 2);
+        }
+    }
+    p->kc = kc;
+    const int swz = kc * 4;
+    // A: NHWC input (or its four parity planes for stride 2)
+    const int nplanes = d.stride == 2 ? 4 : 1;
+    for (int pl = 0; pl < nplanes; ++pl) {
+        const int py = pl >> 1, px = pl & 1;
+        const float *base = d.in + d.in_co + ((size_t)py * d.W + px) * d.in_cs;
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)(d.W / d.stride), (cuuint64_t)(d.H / d.stride),
+                              (cuuint64_t)d.b};
+        cuuint64_t strides[3] = {(cuuint64_t)d.stride * d.in_cs * 4, (cuuint64_t)d.stride * d.W * d.in_cs * 4,
+                                 (cuuint64_t)d.H * d.W * d.in_cs * 4};
+        cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)g.TW, (cuuint32_t)g.TH, 1};
+        int rc = encode(&p->amaps.m[pl], base, 4, dims, strides, box, swz);
+        if (rc) return rc;
+    }
+    for (int pl = nplanes; pl < 4; ++pl) p->amaps.m[pl] = p->amaps.m[0];
+    // B: packed weights [Cout][taps*cin_pad]
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)g.taps * g.cin_pad, (cuuint64_t)d.Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)g.taps * g.cin_pad * 4};
+        cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)g.BN};
+        int rc = encode(&p->tmB, d.w, 2, dims, strides, box, swz);
+        if (rc) return rc;
+    }
+    p->grid = dim3((unsigned)(g.tiles_x * g.tiles_y * d.b), (unsigned)(d.Cout / g.BN));
+    p->smem = kc == 32 ? ConvCfg<32>::smem_bytes(g.BN) : ConvCfg<8>::smem_bytes(g.BN);
+    p->bias = d.bias;
+    p->res = d.res;
+    p->out = d.out;
+    return PVNET_OK;
+}
+
+int conv_launch(const ConvPlan &p, cudaStream_t s)
+{
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(k_conv_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)ConvCfg<32>::smem_bytes(256));
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(k_conv_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)ConvCfg<8>::smem_bytes(256));
+    });
+    PV_CUDA(attr_err);
+    if (p.kc == 32)
+        k_conv_tc<32><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.g, p.bias, p.res, p.out);
+    else
+        k_conv_tc<8><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.g, p.bias, p.res, p.out);
+    PV_LAUNCHED("k_conv_tc");
+    return PVNET_OK;
+}
+
+}  // namespace pvnet
+
+extern "C" {
+
+int pvnet_conv2d_nhwc(const float *in, int in_cs, int in_co, int Cin, const float *w_packed, const float *bias,
+                      const float *res, int res_cs, int res_co, float *out, int out_cs, int out_co, int Cout, int b,
+                      int H, int W, int ksize, int stride, int dilation, int act, int round_out,
+                      pvnet_stream_t stream)
+{
+    pvnet::ConvDesc d{in, in_cs, in_co, Cin, w_packed, bias, res, res_cs, res_co, out, out_cs, out_co, Cout,
+                      b, H, W, ksize, stride, dilation, act, round_out};
+    pvnet::ConvPlan plan;
+    int rc = pvnet::conv_plan(d, &plan);
+    if (rc) return rc;
+    return pvnet::conv_launch(plan, (cudaStream_t)stream);
+}
+
+}  // extern "C"

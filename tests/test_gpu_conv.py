@@ -1,0 +1,82 @@
+"""GPU: the tcgen05 convolution primitive against torch (fp64 reference computed from
+TF32-truncated operands: isolates indexing / layout / descriptor errors from TF32 rounding)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from pvnet_b200 import conv as pc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _trunc_tf32(t):
+    return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def _run_case(b, H, W, cin, cout, k, stride, dil, act, with_res, in_extra=0, out_extra=0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(b, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)
+    bias = torch.randn(cout, generator=g)
+    Ho, Wo = H // stride, W // stride
+    res = torch.randn(b, cout, Ho, Wo, generator=g) if with_res else None
+    # reference: fp64 conv of tf32-rounded weights and tf32-TRUNCATED activations (what the MMA sees)
+    wq = pc.round_tf32(w)
+    xq = _trunc_tf32(x)
+    ref = F.conv2d(xq.double(), wq.double(), bias.double(), stride=stride, padding=dil * (k - 1) // 2, dilation=dil)
+    if with_res:
+        ref = ref + res.double()
+    if act == 1:
+        ref = F.relu(ref)
+    elif act == 2:
+        ref = F.leaky_relu(ref, 0.1)
+    # device buffers, NHWC, with channel padding on both sides to exercise offsets
+    in_cs, in_co = cin + in_extra, in_extra // 2 // 4 * 4
+    out_cs, out_co = cout + out_extra, out_extra // 2 // 4 * 4
+    xin = torch.full((b, H, W, in_cs), 7.0, device=DEV)
+    xin[..., in_co:in_co + cin] = x.permute(0, 2, 3, 1).to(DEV)
+    out = torch.full((b, Ho, Wo, out_cs), -3.0, device=DEV)
+    resd = res.permute(0, 2, 3, 1).contiguous().to(DEV) if with_res else None
+    wp = pc.pack_weight(w.to(DEV))
+    pc.conv2d_nhwc(xin, in_co, cin, wp, bias.to(DEV), out, out_co, cout, k, stride, dil, act, resd, 0)
+    torch.cuda.synchronize()
+    got = out[..., out_co:out_co + cout].permute(0, 3, 1, 2).double().cpu()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-5 * max(scale, 1.0) + 1e-5, f"max err {err:.3e} (scale {scale:.2f})"
+    # untouched padding channels
+    if out_extra:
+        mask = torch.ones(out_cs, dtype=torch.bool)
+        mask[out_co:out_co + cout] = False
+        assert (out[..., mask.to(DEV)] == -3.0).all()
+
+
+@pytest.mark.parametrize("cfg", [
+    # b, H,  W,  cin, cout, k, s, d, act, res
+    (1, 16, 32, 32, 32, 1, 1, 1, 0, False),     # smallest: single K-block, exact tiles
+    (1, 16, 32, 32, 32, 3, 1, 1, 0, False),     # 9 taps, zero padding via TMA OOB fill
+    (2, 24, 40, 64, 64, 3, 1, 1, 1, True),      # partial tiles, residual + ReLU (BasicBlock)
+    (1, 24, 40, 128, 256, 3, 1, 2, 1, False),   # dilation 2 (layer3)
+    (1, 24, 40, 64, 512, 3, 1, 4, 1, True),     # dilation 4, two N tiles (layer4)
+    (2, 24, 40, 128, 256, 1, 1, 1, 0, False),   # 1x1 downsample, no stride
+    (2, 48, 80, 64, 128, 3, 2, 1, 1, False),    # stride-2 3x3 through parity planes (layer2.0.conv1)
+    (2, 48, 80, 64, 128, 1, 2, 1, 0, False),    # stride-2 1x1 downsample
+    (1, 40, 48, 40, 32, 3, 1, 1, 2, False),     # Cin=40 -> 8-channel K-blocks (convraw.0), LeakyReLU
+    (1, 60, 80, 384, 128, 3, 1, 1, 2, False),   # conv8s shape
+])
+def test_conv_vs_torch(cfg):
+    _run_case(*cfg)
+
+
+def test_conv_channel_offsets():
+    _run_case(1, 24, 40, 64, 64, 3, 1, 1, 2, False, in_extra=32, out_extra=64)
+
+
+def test_conv_round_out_is_tf32():
+    x = torch.randn(1, 16, 32, 32, device=DEV)
+    w = torch.randn(32, 32, 1, 1, device=DEV)
+    out = torch.empty(1, 16, 32, 32, device=DEV)
+    pc.conv2d_nhwc(x, 0, 32, pc.pack_weight(w), torch.zeros(32, device=DEV), out, 0, 32, 1, round_out=True)
+    assert ((out.view(torch.int32) & 0x1FFF) == 0).all()

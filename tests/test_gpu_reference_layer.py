@@ -60,11 +60,19 @@ def test_reference_kernels_pin_the_oracle_on_edge_values():
             assert np.array_equal(inl.cpu().numpy(), po.voting_for_hypothesis_kernel(direct, coords, hp, thresh))
 
 
-def _product_vs_reference_layer(mask_np, field_np, hn, thresh, max_num=30000):
+def _product_vs_reference_layer(mask_np, field_np, hn, thresh, max_num=30000, label=""):
+    """Runs the reference layer (its own kernels + its torch ops, fp32 refit), the same
+    with the refit ops in fp64, and the product, all from torch.manual_seed(0).
+    Asserts fixed-seed parity of samples / hypotheses / counts, and that the product is
+    within 1e-4 of the reference layer once the reference's fp32 refit rounding is taken
+    out (fp64 run).  Returns the gaps."""
     mask, vertex = _dev_inputs(mask_np, field_np)
     rec = []
     torch.manual_seed(0)
     ref_kp = ref_cuda.layer_v3(mask, vertex, hn, inlier_thresh=thresh, max_num=max_num, record=rec)
+    torch.manual_seed(0)
+    ref_kp64 = ref_cuda.layer_v3(mask, vertex, hn, inlier_thresh=thresh, max_num=max_num,
+                                 refit_dtype=torch.float64)
     torch.manual_seed(0)
     kp, dbg = rv.ransac_voting_layer_v3(mask, vertex, hn, inlier_thresh=thresh, max_num=max_num, return_debug=True)
     for bi, r in enumerate(rec):
@@ -75,33 +83,50 @@ def _product_vs_reference_layer(mask_np, field_np, hn, thresh, max_num=30000):
         assert int(dbg["tn"][bi]) == r["tn"]
         assert torch.equal(dbg["counts"][bi].long(), r["counts"]), "inlier counts differ from the reference layer"
         assert torch.equal(dbg["hyp"][bi], r["hyp"])
-    return kp.cpu().numpy(), ref_kp.cpu().numpy()
+    kp, ref_kp, ref_kp64 = kp.cpu().numpy(), ref_kp.cpu().numpy(), ref_kp64.cpu().numpy()
+    gap32 = np.abs(kp - ref_kp).max()
+    gap64 = np.abs(kp - ref_kp64).max()
+    noise = np.abs(ref_kp - ref_kp64).max()
+    print(f"\n[reference-layer gap] {label}: |ours - ref(fp32 refit)| = {gap32:.3e}; "
+          f"|ours - ref(fp64 refit)| = {gap64:.3e}; reference's own fp32 noise |ref32 - ref64| = {noise:.3e}")
+    assert gap64 <= 1e-4, "product differs from the reference layer beyond its fp32 refit rounding"
+    return gap32, gap64, noise
 
 
 def test_fixed_seed_parity_with_reference_layer_config1():
     mask, field, _ = cfg1_inputs("planted")
-    kp, ref_kp = _product_vs_reference_layer(np.stack([mask, mask]), np.stack([field, field]), 128, 0.99)
-    err = np.abs(kp - ref_kp).max()
-    print(f"\n[reference-layer gap] config1 planted, tn=10000: max |kp - ref| = {err:.3e}")
-    assert err <= 1e-4 + 2e-6 * 640   # 1e-4 abs + the reference's own fp32 refit noise
+    _product_vs_reference_layer(np.stack([mask, mask]), np.stack([field, field]), 128, 0.99,
+                                label="config1 planted, tn=10000, K=9 (odd keypoints 260 px outside the mask)")
 
 
 def test_fixed_seed_parity_with_reference_layer_demo():
+    """The reference's own demo fixture (well conditioned: keypoints inside the object)."""
     mask, field, pts = demo_fixture()
-    kp, ref_kp = _product_vs_reference_layer(mask[None], field[None], 512, 0.99)
-    err = np.abs(kp - ref_kp).max()
-    print(f"\n[reference-layer gap] demo fixture, tn=2289: max |kp - ref| = {err:.3e}; "
-          f"|ref - truth| = {np.abs(ref_kp[0] - pts).max():.3e}; |ours - truth| = {np.abs(kp[0] - pts).max():.3e}")
-    assert err <= 1e-4 + 2e-6 * 640
+    gap32, _, _ = _product_vs_reference_layer(mask[None], field[None], 512, 0.99, label="demo fixture, tn=2289")
+    assert gap32 <= 1e-3
+
+
+def test_fixed_seed_parity_near_keypoints():
+    """Keypoints inside the mask (R=20 px): the best-conditioned case."""
+    mask = syn.disc_mask(3000)
+    rng = np.random.default_rng(5)
+    kps = np.stack([320 + 20 * np.cos(np.arange(9)), 240 + 20 * np.sin(np.arange(9))], 1)
+    ys, xs = np.mgrid[0:480, 0:640].astype(np.float64)
+    field = np.zeros((18, 480, 640), np.float32)
+    for j in range(9):
+        dx, dy = kps[j, 0] - xs, kps[j, 1] - ys
+        n = np.sqrt(dx * dx + dy * dy) + 1e-3
+        eps = rng.normal(0, 0.03, size=dx.shape)
+        field[2 * j] = (np.cos(eps) * dx / n - np.sin(eps) * dy / n) * (mask != 0)
+        field[2 * j + 1] = (np.sin(eps) * dx / n + np.cos(eps) * dy / n) * (mask != 0)
+    gap32, _, _ = _product_vs_reference_layer(mask[None], field[None], 256, 0.99, label="near keypoints, tn=3000")
+    assert gap32 <= 1e-3
 
 
 def test_fixed_seed_parity_with_subsampling():
     masks = np.stack([syn.disc_mask(40000), syn.disc_mask(3), syn.disc_mask(9000)])
     fields = np.stack([syn.planted_field(masks[i], 9, 40 + i)[0] for i in range(3)])
-    kp, ref_kp = _product_vs_reference_layer(masks, fields, 256, 0.99, max_num=30000)
-    err = np.abs(kp - ref_kp).max()
-    print(f"\n[reference-layer gap] subsampled 40000->~30000: max |kp - ref| = {err:.3e}")
-    assert err <= 1e-4 + 2e-6 * 640
+    _product_vs_reference_layer(masks, fields, 256, 0.99, max_num=30000, label="subsampled 40000->~30000")
 
 
 def test_covariance_fixed_seed_parity():
