@@ -165,6 +165,44 @@ PVNET_API int pvnet_conv2d_nhwc(const float *in, int in_cs, int in_co, int Cin,
                                 int b, int H, int W, int ksize, int stride, int dilation,
                                 int act, int round_out, pvnet_stream_t stream);
 
+/* Resnet18_8s.forward (lib/networks/model_repository.py:64-80), eval mode, whole batch.
+ *
+ * The handle is a host-side table of per-convolution weight pointers plus cached tensor
+ * maps; it owns no device memory.  Weights are DEVICE pointers owned by the caller and
+ * must stay valid while the handle is used:
+ *   slot 0               stem conv1+bn1, packed [7*7][3][64] (tap, cin, cout), bias [64]
+ *   slots 1..24          the 3x3 / 1x1 convs in execution order (layer1.0.conv1, layer1.0.conv2,
+ *                        layer1.1.conv1, layer1.1.conv2, layer2.0.conv1, layer2.0.downsample,
+ *                        layer2.0.conv2, layer2.1.conv1, layer2.1.conv2, layer3.* and layer4.* in the
+ *                        same pattern, fc.0, conv8s.0, conv4s.0, conv2s.0, convraw.0), each packed
+ *                        [Cout][kh*kw][Cin] with its BatchNorm folded in, bias [Cout].  convraw.0's
+ *                        Cin is s2dim+8: s2dim upsampled channels, 3 image channels, 5 zeros.
+ *   slot 25              convraw.3 (1x1, with bias): [seg_dim+ver_dim][32], bias [seg_dim+ver_dim]
+ * pvnet_backbone_forward:
+ *   image_nchw  f32 [b,3,h,w] (h,w multiples of 8)
+ *   out_nchw    f32 [b,seg_dim+ver_dim,h,w]: seg logits are channels [0,seg_dim), the vertex
+ *               field the rest (model_repository.py:77-78)
+ *   mask_out    optional [b,h,w] argmax over the seg channels (first maximum), int64
+ *               (mask_elem_size 8, what torch.argmax returns) or uint8 (1); NULL to skip
+ */
+typedef struct pvnet_backbone pvnet_backbone_t;
+PVNET_API int pvnet_backbone_create(int ver_dim, int seg_dim, int fcdim, int s8dim, int s4dim, int s2dim,
+                                    int raw_dim, pvnet_backbone_t **out);
+PVNET_API void pvnet_backbone_destroy(pvnet_backbone_t *m);
+PVNET_API int pvnet_backbone_num_convs(void);
+PVNET_API int pvnet_backbone_set_conv(pvnet_backbone_t *m, int slot, const float *w_packed, const float *bias);
+PVNET_API int pvnet_backbone_workspace_bytes(const pvnet_backbone_t *m, int b, int h, int w, size_t *bytes);
+PVNET_API int pvnet_backbone_forward(pvnet_backbone_t *m, const float *image_nchw, int b, int h, int w,
+                                     float *out_nchw, void *mask_out, int mask_elem_size,
+                                     void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
+/* The forward pass is an ordered list of single-kernel stages; these run/describe one of
+ * them with the same arguments (per-layer timing in bench.py, layer-wise parity tests). */
+PVNET_API int pvnet_backbone_num_stages(void);
+PVNET_API const char *pvnet_backbone_stage_name(int stage);
+PVNET_API int pvnet_backbone_run_stage(pvnet_backbone_t *m, int stage, const float *image_nchw, int b, int h, int w,
+                                       float *out_nchw, void *mask_out, int mask_elem_size,
+                                       void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,264 @@
+// backbone_aux.cu -- the non-GEMM kernels of Resnet18_8s (lib/networks/resnet.py:200-220,
+// lib/networks/model_repository.py:64-80): stem conv 7x7/2 (Cin=3), max-pool 3x3/2,
+// bilinear x2 upsampling (align_corners=True), NCHW image -> NHWC slice packing, and the
+// final 1x1 conv + per-pixel argmax head that writes the reference's NCHW outputs.
+// All of them are HBM-bound streaming kernels except the stem (FP32 FMA bound).
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace pvnet {
+
+// ------------------------------------------------------------------ stem
+// conv1 (3->64, 7x7, stride 2, pad 3) + folded bn1 + ReLU (resnet.py:201-203).
+// in: NCHW [b,3,H,W]; out: NHWC [b,H/2,W/2,out_cs] at out_co (64 channels), tf32-rounded.
+// CTA: 8 x 32 output pixels x 64 channels.  Shared memory: the 21 x 69 x 3 input patch and
+// all 64*147 weights ([tap][ci][co] so a thread reads 4 consecutive co as one LDS.128
+// broadcast).  Thread = one output pixel, 64 accumulators.
+constexpr int STEM_TY = 8, STEM_TX = 32;
+constexpr int STEM_PH = STEM_TY * 2 + 5, STEM_PW = STEM_TX * 2 + 5;   // 21 x 69
+constexpr int STEM_PWP = STEM_PW + 1;
+
+__global__ void __launch_bounds__(256)
+    k_stem(const float *__restrict__ in, const float *__restrict__ w /*[49][3][64]*/,
+           const float *__restrict__ bias /*[64]*/, float *__restrict__ out, int H, int W, int out_cs, int out_co)
+{
+    extern __shared__ float sm[];
+    float *sw = sm;                               // 147*64
+    float *sp = sm + 147 * 64;                    // [3][21][70]
+    const int Ho = H / 2, Wo = W / 2;
+    const int n = blockIdx.z;
+    const int oy0 = blockIdx.y * STEM_TY, ox0 = blockIdx.x * STEM_TX;
+    for (int i = threadIdx.x; i < 147 * 64; i += 256) sw[i] = w[i];
+    const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+    for (int i = threadIdx.x; i < 3 * STEM_PH * STEM_PW; i += 256) {
+        const int c = i / (STEM_PH * STEM_PW);
+        const int r = i - c * (STEM_PH * STEM_PW);
+        const int py = r / STEM_PW, px = r - py * STEM_PW;
+        const int iy = iy0 + py, ix = ix0 + px;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = in[(((size_t)n * 3 + c) * H + iy) * W + ix];
+        sp[(c * STEM_PH + py) * STEM_PWP + px] = v;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / STEM_TX, tx = threadIdx.x % STEM_TX;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (int kh = 0; kh < 7; ++kh) {
+        for (int kw = 0; kw < 7; ++kw) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = sp[(c * STEM_PH + ty * 2 + kh) * STEM_PWP + tx * 2 + kw];
+                const float4 *wv = reinterpret_cast<const float4 *>(sw + ((kh * 7 + kw) * 3 + c) * 64);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4 ww = wv[j];
+                    acc[4 * j + 0] = fmaf(v, ww.x, acc[4 * j + 0]);
+                    acc[4 * j + 1] = fmaf(v, ww.y, acc[4 * j + 1]);
+                    acc[4 * j + 2] = fmaf(v, ww.z, acc[4 * j + 2]);
+                    acc[4 * j + 3] = fmaf(v, ww.w, acc[4 * j + 3]);
+                }
+            }
+        }
+    }
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    if (oy < Ho && ox < Wo) {
+        float *o = out + (((size_t)n * Ho + oy) * Wo + ox) * out_cs + out_co;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float4 v;
+            v.x = ptx::round_tf32(fmaxf(acc[4 * j + 0] + bias[4 * j + 0], 0.f));
+            v.y = ptx::round_tf32(fmaxf(acc[4 * j + 1] + bias[4 * j + 1], 0.f));
+            v.z = ptx::round_tf32(fmaxf(acc[4 * j + 2] + bias[4 * j + 2], 0.f));
+            v.w = ptx::round_tf32(fmaxf(acc[4 * j + 3] + bias[4 * j + 3], 0.f));
+            reinterpret_cast<float4 *>(o)[j] = v;
+        }
+    }
+}
+
+int launch_stem(const float *in, const float *w, const float *bias, float *out, int b, int H, int W, int out_cs,
+                int out_co, cudaStream_t s)
+{
+    const size_t smem = (147 * 64 + 3 * STEM_PH * STEM_PWP) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        PV_CUDA(cudaFuncSetAttribute(k_stem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid((W / 2 + STEM_TX - 1) / STEM_TX, (H / 2 + STEM_TY - 1) / STEM_TY, b);
+    k_stem<<<grid, 256, smem, s>>>(in, w, bias, out, H, W, out_cs, out_co);
+    PV_LAUNCHED("k_stem");
+    return PVNET_OK;
+}
+
+// ------------------------------------------------------------------ image packing
+// NCHW [b,3,H,W] -> NHWC slice [.., co..co+8): 3 image channels (tf32-rounded) + 5 zeros
+__global__ void k_pack_image(const float *__restrict__ in, float *__restrict__ out, int npix_per_img, long long total,
+                             int out_cs, int out_co)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long n = i / npix_per_img;
+    const long long p = i - n * npix_per_img;
+    const float *src = in + n * 3 * (long long)npix_per_img + p;
+    float4 a = make_float4(ptx::round_tf32(src[0]), ptx::round_tf32(src[npix_per_img]),
+                           ptx::round_tf32(src[2 * (long long)npix_per_img]), 0.f);
+    float4 *o = reinterpret_cast<float4 *>(out + i * out_cs + out_co);
+    o[0] = a;
+    o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+int launch_pack_image(const float *in, float *out, int b, int H, int W, int out_cs, int out_co, cudaStream_t s)
+{
+    const long long total = (long long)b * H * W;
+    k_pack_image<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, H * W, total, out_cs, out_co);
+    PV_LAUNCHED("k_pack_image");
+    return PVNET_OK;
+}
+
+// ------------------------------------------------------------------ max-pool 3x3/2 pad 1
+// (resnet.py:142,204).  in NHWC [b,H,W,in_cs] at in_co (C channels) -> out [b,H/2,W/2,C]
+__global__ void k_maxpool(const float *__restrict__ in, float *__restrict__ out, int H, int W, int C, int in_cs,
+                          int in_co, long long total /* b*Ho*Wo*C/4 */)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c4 = C / 4, Ho = H / 2, Wo = W / 2;
+    const int cg = (int)(i % c4);
+    long long r = i / c4;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int iy = oy * 2 + dy;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int ix = ox * 2 + dx;
+            if (ix < 0 || ix >= W) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(in + (((size_t)n * H + iy) * W + ix) * in_cs + in_co) + cg);
+            m.x = fmaxf(m.x, v.x);
+            m.y = fmaxf(m.y, v.y);
+            m.z = fmaxf(m.z, v.z);
+            m.w = fmaxf(m.w, v.w);
+        }
+    }
+    reinterpret_cast<float4 *>(out)[i] = m;
+}
+
+int launch_maxpool(const float *in, float *out, int b, int H, int W, int C, int in_cs, int in_co, cudaStream_t s)
+{
+    const long long total = (long long)b * (H / 2) * (W / 2) * (C / 4);
+    k_maxpool<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, H, W, C, in_cs, in_co, total);
+    PV_LAUNCHED("k_maxpool");
+    return PVNET_OK;
+}
+
+// ------------------------------------------------------------------ bilinear x2, align_corners=True
+// nn.UpsamplingBilinear2d(scale_factor=2) (model_repository.py:35,43,51).  Same arithmetic
+// as ATen's upsample_bilinear2d: scale=(in-1)/(out-1) in fp32, src=scale*dst, i0=(int)src,
+// l1=src-i0, l0=1-l1, out = h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11).
+// in NHWC [b,h,w,C] dense -> out NHWC [b,2h,2w,out_cs] at out_co; values rounded to tf32.
+__global__ void k_upsample2x(const float *__restrict__ in, float *__restrict__ out, int h, int w, int C, int out_cs,
+                             int out_co, float sy, float sx, long long total /* b*2h*2w*C/4 */)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c4 = C / 4, Ho = 2 * h, Wo = 2 * w;
+    const int cg = (int)(i % c4);
+    long long r = i / c4;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    const float fy = sy * (float)oy, fx = sx * (float)ox;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float h1 = fy - (float)y0, h0 = 1.f - h1, w1 = fx - (float)x0, w0 = 1.f - w1;
+    const float4 *base = reinterpret_cast<const float4 *>(in) + (size_t)n * h * w * c4 + cg;
+    const float4 v00 = __ldg(base + ((size_t)y0 * w + x0) * c4), v01 = __ldg(base + ((size_t)y0 * w + x1) * c4);
+    const float4 v10 = __ldg(base + ((size_t)y1 * w + x0) * c4), v11 = __ldg(base + ((size_t)y1 * w + x1) * c4);
+    float4 o;
+    o.x = ptx::round_tf32(h0 * (w0 * v00.x + w1 * v01.x) + h1 * (w0 * v10.x + w1 * v11.x));
+    o.y = ptx::round_tf32(h0 * (w0 * v00.y + w1 * v01.y) + h1 * (w0 * v10.y + w1 * v11.y));
+    o.z = ptx::round_tf32(h0 * (w0 * v00.z + w1 * v01.z) + h1 * (w0 * v10.z + w1 * v11.z));
+    o.w = ptx::round_tf32(h0 * (w0 * v00.w + w1 * v01.w) + h1 * (w0 * v10.w + w1 * v11.w));
+    *reinterpret_cast<float4 *>(out + (((size_t)n * Ho + oy) * Wo + ox) * out_cs + out_co + cg * 4) = o;
+}
+
+int launch_upsample2x(const float *in, float *out, int b, int h, int w, int C, int out_cs, int out_co, cudaStream_t s)
+{
+    const long long total = (long long)b * (2 * h) * (2 * w) * (C / 4);
+    const float sy = (float)(h - 1) / (float)(2 * h - 1), sx = (float)(w - 1) / (float)(2 * w - 1);
+    k_upsample2x<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, h, w, C, out_cs, out_co, sy, sx, total);
+    PV_LAUNCHED("k_upsample2x");
+    return PVNET_OK;
+}
+
+// ------------------------------------------------------------------ head
+// convraw.3: 1x1 conv raw_dim(=32) -> seg_dim+ver_dim with bias (model_repository.py:57), in
+// exact fp32, fused with torch.argmax(seg_pred,1) (tools/demo.py:52; first maximum wins).
+// in NHWC [b,H,W,32] -> out NCHW [b,Cout,H,W]; mask int64 [b,H,W] (or u8) optional.
+constexpr int HEAD_MAX_COUT = 64;
+__global__ void __launch_bounds__(256)
+    k_head(const float *__restrict__ in, const float *__restrict__ w /*[Cout][32]*/, const float *__restrict__ bias,
+           float *__restrict__ out, void *__restrict__ mask, int mask_esz, int seg_dim, int Cout, int npix,
+           long long total)
+{
+    __shared__ float sw[HEAD_MAX_COUT * 32];
+    __shared__ float sb[HEAD_MAX_COUT];
+    for (int i = threadIdx.x; i < Cout * 32; i += 256) sw[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += 256) sb[i] = bias[i];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long n = i / npix;
+    const long long p = i - n * npix;
+    float v[32];
+    const float4 *src = reinterpret_cast<const float4 *>(in + i * 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(src + j);
+        v[4 * j] = t.x;
+        v[4 * j + 1] = t.y;
+        v[4 * j + 2] = t.z;
+        v[4 * j + 3] = t.w;
+    }
+    float best = -INFINITY;
+    int best_c = 0;
+    float *o = out + n * Cout * (long long)npix + p;
+    for (int co = 0; co < Cout; ++co) {
+        float acc = sb[co];
+        const float *wr = sw + co * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc = fmaf(v[j], wr[j], acc);
+        o[(long long)co * npix] = acc;
+        if (co < seg_dim && acc > best) {
+            best = acc;
+            best_c = co;
+        }
+    }
+    if (mask) {
+        if (mask_esz == 8)
+            reinterpret_cast<long long *>(mask)[i] = best_c;
+        else
+            reinterpret_cast<unsigned char *>(mask)[i] = (unsigned char)best_c;
+    }
+}
+
+int launch_head(const float *in, const float *w, const float *bias, float *out, void *mask, int mask_esz, int seg_dim,
+                int Cout, int b, int H, int W, cudaStream_t s)
+{
+    PV_CHECK_ARG(Cout >= 1 && Cout <= HEAD_MAX_COUT, "head: %d output channels unsupported (max %d)", Cout,
+                 HEAD_MAX_COUT);
+    const long long total = (long long)b * H * W;
+    k_head<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, w, bias, out, mask, mask_esz, seg_dim, Cout, H * W,
+                                                          total);
+    PV_LAUNCHED("k_head");
+    return PVNET_OK;
+}
+
+}  // namespace pvnet

@@ -21,10 +21,11 @@
 //
 // Stride-2 convolutions read the input through four "parity plane" tensor maps (even/odd
 // rows x even/odd columns); each tap then is a stride-1 box in one plane.
-#include "common.cuh"
+#include "conv_tc.cuh"
 #include "ptx.cuh"
 
 #include <mutex>
+#include <new>
 
 namespace pvnet {
 
@@ -255,20 +256,6 @@ struct ConvPlan {
     float *out;
 };
 
-struct ConvDesc {
-    const float *in;   // NHWC buffer [b,H,W,in_cs], channels [in_co, in_co+Cin) are the conv input
-    int in_cs, in_co, Cin;
-    const float *w;    // packed [Cout][taps][cin_pad]
-    const float *bias; // [Cout]
-    const float *res;  // NHWC [b,Ho,Wo,res_cs] at res_co, or null
-    int res_cs, res_co;
-    float *out;        // NHWC [b,Ho,Wo,out_cs], written at out_co
-    int out_cs, out_co, Cout;
-    int b, H, W;
-    int ksize, stride, dilation;
-    int act, round_out;
-};
-
 int conv_cin_pad(int Cin) { return Cin % 32 == 0 ? Cin : (Cin + 7) / 8 * 8; }
 int conv_kc(int Cin) { return Cin % 32 == 0 ? 32 : 8; }
 
@@ -375,6 +362,10 @@ int conv_launch(const ConvPlan &p, cudaStream_t s)
     PV_LAUNCHED("k_conv_tc");
     return PVNET_OK;
 }
+
+size_t conv_plan_size() { return sizeof(ConvPlan); }
+int conv_plan_at(const ConvDesc &d, void *storage) { return conv_plan(d, new (storage) ConvPlan()); }
+int conv_launch_at(const void *storage, cudaStream_t s) { return conv_launch(*static_cast<const ConvPlan *>(storage), s); }
 
 }  // namespace pvnet
 

@@ -1,0 +1,173 @@
+"""`Resnet18_8s` with the reference's constructor, forward signature and state-dict keys
+(zju3dv/pvnet lib/networks/model_repository.py:7-80), backed in eval mode by the native
+sm_100a backbone (tcgen05 implicit-GEMM convs behind include/pvnet_b200.h).
+
+    net = Resnet18_8s(ver_dim=18, seg_dim=2)
+    net.load_state_dict(ckpt['net'])          # reference checkpoints load unchanged
+    net.cuda().eval()
+    seg_pred, ver_pred = net(x)               # [b,2,H,W], [b,18,H,W] views of one tensor
+
+* eval mode on CUDA -> `pvnet_backbone_forward`: BatchNorm folded into TF32 conv weights
+  (the reference's cuDNN path also runs TF32 on this hardware: torch's
+  `cudnn.allow_tf32` default), fp32 accumulation, fp32 stem and 1x1 head, fused argmax.
+  There is no PyTorch fallback in this mode: if the library is missing it raises.
+* train mode (BatchNorm batch statistics, autograd; also what tools/demo.py runs because it
+  never calls .eval()) -> the plain PyTorch graph below, as SURVEY.md §7
+  prescribes; training is out of scope for the native path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch import nn
+
+from . import _native
+from . import conv as pc
+from .resnet import resnet18
+
+# execution-order conv slots of include/pvnet_b200.h (pvnet_backbone_set_conv)
+_SLOTS = [
+    ("resnet18_8s.conv1", "resnet18_8s.bn1"),
+    ("resnet18_8s.layer1.0.conv1", "resnet18_8s.layer1.0.bn1"), ("resnet18_8s.layer1.0.conv2", "resnet18_8s.layer1.0.bn2"),
+    ("resnet18_8s.layer1.1.conv1", "resnet18_8s.layer1.1.bn1"), ("resnet18_8s.layer1.1.conv2", "resnet18_8s.layer1.1.bn2"),
+    ("resnet18_8s.layer2.0.conv1", "resnet18_8s.layer2.0.bn1"), ("resnet18_8s.layer2.0.downsample.0", "resnet18_8s.layer2.0.downsample.1"),
+    ("resnet18_8s.layer2.0.conv2", "resnet18_8s.layer2.0.bn2"),
+    ("resnet18_8s.layer2.1.conv1", "resnet18_8s.layer2.1.bn1"), ("resnet18_8s.layer2.1.conv2", "resnet18_8s.layer2.1.bn2"),
+    ("resnet18_8s.layer3.0.conv1", "resnet18_8s.layer3.0.bn1"), ("resnet18_8s.layer3.0.downsample.0", "resnet18_8s.layer3.0.downsample.1"),
+    ("resnet18_8s.layer3.0.conv2", "resnet18_8s.layer3.0.bn2"),
+    ("resnet18_8s.layer3.1.conv1", "resnet18_8s.layer3.1.bn1"), ("resnet18_8s.layer3.1.conv2", "resnet18_8s.layer3.1.bn2"),
+    ("resnet18_8s.layer4.0.conv1", "resnet18_8s.layer4.0.bn1"), ("resnet18_8s.layer4.0.downsample.0", "resnet18_8s.layer4.0.downsample.1"),
+    ("resnet18_8s.layer4.0.conv2", "resnet18_8s.layer4.0.bn2"),
+    ("resnet18_8s.layer4.1.conv1", "resnet18_8s.layer4.1.bn1"), ("resnet18_8s.layer4.1.conv2", "resnet18_8s.layer4.1.bn2"),
+    ("resnet18_8s.fc.0", "resnet18_8s.fc.1"),
+    ("conv8s.0", "conv8s.1"), ("conv4s.0", "conv4s.1"), ("conv2s.0", "conv2s.1"), ("convraw.0", "convraw.1"),
+    ("convraw.3", None),
+]
+
+
+class Resnet18_8s(nn.Module):
+    def __init__(self, ver_dim, seg_dim, fcdim=256, s8dim=128, s4dim=64, s2dim=32, raw_dim=32):
+        super().__init__()
+        trunk = resnet18(output_stride=8)
+        self.ver_dim = ver_dim
+        self.seg_dim = seg_dim
+        self._dims = (fcdim, s8dim, s4dim, s2dim, raw_dim)
+        trunk.fc = nn.Sequential(nn.Conv2d(trunk.inplanes, fcdim, 3, 1, 1, bias=False), nn.BatchNorm2d(fcdim),
+                                 nn.ReLU(True))
+        self.resnet18_8s = trunk
+        self.conv8s = nn.Sequential(nn.Conv2d(128 + fcdim, s8dim, 3, 1, 1, bias=False), nn.BatchNorm2d(s8dim),
+                                    nn.LeakyReLU(0.1, True))
+        self.up8sto4s = nn.UpsamplingBilinear2d(scale_factor=2)
+        self.conv4s = nn.Sequential(nn.Conv2d(64 + s8dim, s4dim, 3, 1, 1, bias=False), nn.BatchNorm2d(s4dim),
+                                    nn.LeakyReLU(0.1, True))
+        self.up4sto2s = nn.UpsamplingBilinear2d(scale_factor=2)
+        self.conv2s = nn.Sequential(nn.Conv2d(64 + s4dim, s2dim, 3, 1, 1, bias=False), nn.BatchNorm2d(s2dim),
+                                    nn.LeakyReLU(0.1, True))
+        self.up2storaw = nn.UpsamplingBilinear2d(scale_factor=2)
+        self.convraw = nn.Sequential(nn.Conv2d(3 + s2dim, raw_dim, 3, 1, 1, bias=False), nn.BatchNorm2d(raw_dim),
+                                     nn.LeakyReLU(0.1, True), nn.Conv2d(raw_dim, seg_dim + ver_dim, 1, 1))
+        self._native = None          # (handle, packed tensors kept alive, version key)
+
+    # ------------------------------------------------------------------ PyTorch graph
+    def _forward_torch(self, x):
+        x2s, x4s, x8s, _x16s, _x32s, xfc = self.resnet18_8s(x)
+        fm = self.up8sto4s(self.conv8s(torch.cat([xfc, x8s], 1)))
+        fm = self.up4sto2s(self.conv4s(torch.cat([fm, x4s], 1)))
+        fm = self.up2storaw(self.conv2s(torch.cat([fm, x2s], 1)))
+        out = self.convraw(torch.cat([fm, x], 1))
+        return out[:, :self.seg_dim], out[:, self.seg_dim:]
+
+    # ------------------------------------------------------------------ native path
+    def _weights_key(self, device):
+        return (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
+               tuple((b.data_ptr(), b._version) for b in self.buffers())
+
+    def _release_native(self):
+        if self._native is not None:
+            _native.lib().pvnet_backbone_destroy(self._native[0])
+            self._native = None
+
+    def __del__(self):
+        try:
+            self._release_native()
+        except Exception:
+            pass
+
+    def _prepare_native(self, device):
+        """Fold BatchNorm (eval statistics) into the conv weights, pack them K-major, round
+        to TF32, hand the pointers to the C handle.  Redone when any parameter changes."""
+        key = self._weights_key(device)
+        if self._native is not None and self._native[2] == key:
+            return self._native[0]
+        self._release_native()
+        L = _native.lib()
+        mods = dict(self.named_modules())
+        fcdim, s8dim, s4dim, s2dim, raw_dim = self._dims
+        handle = ctypes.c_void_p()
+        _native.check(L.pvnet_backbone_create(self.ver_dim, self.seg_dim, fcdim, s8dim, s4dim, s2dim, raw_dim,
+                                              ctypes.byref(handle)), "pvnet_backbone_create")
+        keep = []
+        with torch.no_grad():
+            for slot, (conv_name, bn_name) in enumerate(_SLOTS):
+                conv = mods[conv_name]
+                if bn_name is not None:
+                    bn = mods[bn_name]
+                    w, b = pc.fold_bn(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+                else:
+                    w, b = pc.fold_bn(conv.weight, conv_bias=conv.bias)
+                w, b = w.to(device), b.to(device).contiguous()
+                if slot == 0:                         # stem: fp32 [tap][cin][cout]
+                    packed = w.permute(2, 3, 1, 0).reshape(49, 3, 64).contiguous()
+                elif conv_name == "convraw.3":        # head: fp32 [cout][32]
+                    packed = w.reshape(w.shape[0], w.shape[1]).contiguous()
+                elif conv_name == "convraw.0":        # cat[fm(s2dim), image(3)] -> s2dim+8 input channels
+                    packed = pc.pack_weight(w, cin_pad=s2dim + 8)
+                else:
+                    packed = pc.pack_weight(w)
+                keep += [packed, b]
+                _native.check(L.pvnet_backbone_set_conv(handle, slot, packed.data_ptr(), b.data_ptr()),
+                              f"pvnet_backbone_set_conv({conv_name})")
+        self._native = (handle, keep, key)
+        return handle
+
+    def forward_native(self, x, with_mask=False, mask_dtype=torch.int64):
+        """x [b,3,H,W] float32 CUDA -> out [b,seg+ver,H,W] (and the fused argmax mask)."""
+        if not x.is_cuda:
+            raise RuntimeError("pvnet_b200: the native backbone needs a CUDA tensor (there is no CPU path)")
+        x = x.contiguous().float()
+        b, c, h, w = x.shape
+        if c != 3 or h % 8 or w % 8:
+            raise ValueError(f"input must be [b,3,H,W] with H,W multiples of 8, got {tuple(x.shape)}")
+        dev = x.device
+        with torch.cuda.device(dev):
+            handle = self._prepare_native(dev)
+            L = _native.lib()
+            n = ctypes.c_size_t()
+            _native.check(L.pvnet_backbone_workspace_bytes(handle, b, h, w, ctypes.byref(n)),
+                          "pvnet_backbone_workspace_bytes")
+            ws = self._workspace(n.value, dev)
+            out = torch.empty([b, self.seg_dim + self.ver_dim, h, w], dtype=torch.float32, device=dev)
+            mask = torch.empty([b, h, w], dtype=mask_dtype, device=dev) if with_mask else None
+            _native.check(L.pvnet_backbone_forward(
+                handle, x.data_ptr(), b, h, w, out.data_ptr(), None if mask is None else mask.data_ptr(),
+                0 if mask is None else mask.element_size(), ws.data_ptr(), ws.numel(),
+                ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "pvnet_backbone_forward")
+        return (out, mask) if with_mask else out
+
+    def _workspace(self, nbytes, dev):
+        # one persistent workspace per module (activations of the largest batch seen); reusing
+        # the same address also lets the C handle keep its encoded tensor maps
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < nbytes or ws.device != dev:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws = ws
+        return ws
+
+    def forward(self, x, feature_alignment=False):
+        if self.training or not x.is_cuda:
+            if not self.training and not x.is_cuda:
+                raise RuntimeError("pvnet_b200: eval-mode Resnet18_8s runs only on CUDA (no CPU fallback)")
+            return self._forward_torch(x)
+        out = self.forward_native(x)
+        return out[:, :self.seg_dim, :, :], out[:, self.seg_dim:, :, :]

@@ -34,3 +34,32 @@ def cfg1_inputs(kind):
     field = syn.random_field(mask, 9, 1000) if kind == "random" else syn.planted_field(mask, 9, 1000)[0]
     idxs = syn.draw_idxs(10000, 128, 9, seed=1000)
     return mask, field, idxs
+
+
+def seeded_state_dict(model, seed=0):
+    """Deterministic weights for a Resnet18_8s-shaped module, a pure function of
+    (parameter name, shape, seed) -- so the golden generator (which builds the REFERENCE
+    classes) and the tests (which build ours) get identical tensors without sharing a file.
+    Conv weights ~ N(0, sqrt(2/fan_out)); BN gamma ~ U(0.5,1.5), beta ~ N(0,0.1),
+    running_mean ~ N(0,0.1), running_var ~ U(0.5,1.5) so folding is exercised."""
+    import hashlib
+
+    import torch
+    out = {}
+    for name, t in model.state_dict().items():
+        h = int(hashlib.sha256(f"{seed}:{name}".encode()).hexdigest()[:8], 16)
+        g = torch.Generator().manual_seed(h)
+        if name.endswith("num_batches_tracked"):
+            out[name] = torch.zeros_like(t)
+        elif name.endswith("running_var"):
+            out[name] = torch.rand(t.shape, generator=g) + 0.5
+        elif name.endswith("running_mean"):
+            out[name] = torch.randn(t.shape, generator=g) * 0.1
+        elif t.dim() == 4:
+            fan = t.shape[0] * t.shape[2] * t.shape[3]
+            out[name] = torch.randn(t.shape, generator=g) * (2.0 / fan) ** 0.5
+        elif name.endswith(".weight"):          # BN gamma
+            out[name] = torch.rand(t.shape, generator=g) + 0.5
+        else:                                    # BN beta / conv bias
+            out[name] = torch.randn(t.shape, generator=g) * 0.1
+    return out
