@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- PVNet per-image inference hot path on B200: images/sec (480x640, K=9),
+backbone (Resnet18_8s) + RANSAC vote (ransac_voting_layer_v3).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (rank 0)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one batch of 16 synthetic 480x640 images per GPU (BASELINE config 2):
+Resnet18_8s(ver_dim=18, seg_dim=2).eval() forward -> per-pixel argmax (fused into the head)
+-> ransac_voting_layer_v3(mask, vertex, 256, inlier_thresh=0.99).  Weights are random-init
+(reference init scheme, seeded) with the segmentation bias calibrated so that about 20000
+pixels per image come out as foreground (config 2's mask size); inputs are N(0,1) images.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = the same step
+through the public API from pinned HOST buffers (H2D of the image batch and D2H of the
+keypoints inside the timed region).  Also: `roofline` of the dominant kernel (the tcgen05
+convolution, timed per layer with CUDA events inside this process), `cpu_baseline` (oracle
+port of the voting path on the host cores, bounded sample), `clocks`, `gpu_launches`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, K_KP, HYP, BATCH = 480, 640, 9, 256, 16
+THRESH = 0.99
+GFLOP_PER_IMAGE = 144.87          # SURVEY.md App. B (26 convs, 72.44 GMAC)
+GFLOP_STEM_HEAD = 2 * (0.723 + 0.197)   # stem + 1x1 head run on the FP32 pipe, not tcgen05
+TARGET_FG = 20000
+
+
+def _rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}",
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._reader, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _reader(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- model
+def build_model(torch, dev):
+    from pvnet_b200.model_repository import Resnet18_8s
+    torch.manual_seed(0)
+    net = Resnet18_8s(ver_dim=2 * K_KP, seg_dim=2)
+    g = torch.Generator().manual_seed(0)
+    for m in net.modules():                  # exercise BN folding
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+    return net.to(dev).eval()
+
+
+def calibrate_foreground(torch, net, x):
+    """Shift the class-1 logit bias so that ~TARGET_FG pixels per image are foreground."""
+    with torch.no_grad():
+        out = net.forward_native(x[:4])
+        margin = (out[:, 1] - out[:, 0]).flatten()
+        kth = margin.numel() - TARGET_FG * x[:4].shape[0]
+        cut = torch.kthvalue(margin.float().cpu(), max(1, kth)).values.item()
+        net.convraw[3].bias[1] -= cut
+        _, mask = net.forward_native(x, with_mask=True)
+        return float(mask.float().sum().item() / x.shape[0])
+
+
+def make_step(torch, net):
+    from pvnet_b200 import ransac_voting_gpu as rv
+
+    def step(x):
+        out, mask = net.forward_native(x, with_mask=True)
+        b, c, h, w = out.shape
+        vertex = out[:, 2:].permute(0, 2, 3, 1).view(b, h, w, K_KP, 2)      # tools/demo.py:48-50
+        return rv.ransac_voting_layer_v3(mask, vertex, HYP, inlier_thresh=THRESH, rng="batched")
+    return step
+
+
+# ----------------------------------------------------------------------------- roofline
+def conv_roofline(torch, net, x, peaks):
+    """Per-stage device time of one forward pass, CUDA events recorded on the launch stream
+    between the single-kernel stages; aggregates the tcgen05 convolution launches."""
+    import ctypes
+
+    from pvnet_b200 import _native
+    L = _native.lib()
+    dev = x.device
+    b = x.shape[0]
+    handle = net._prepare_native(dev)
+    n = ctypes.c_size_t()
+    L.pvnet_backbone_workspace_bytes(handle, b, H, W, ctypes.byref(n))
+    ws = net._workspace(n.value, dev)
+    out = torch.empty([b, 2 + 2 * K_KP, H, W], dtype=torch.float32, device=dev)
+    mask = torch.empty([b, H, W], dtype=torch.int64, device=dev)
+    ns = L.pvnet_backbone_num_stages()
+    names = [L.pvnet_backbone_stage_name(i).decode() for i in range(ns)]
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    reps = 5
+    acc = np.zeros(ns)
+    for rep in range(reps + 1):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(ns + 1)]
+        ev[0].record()
+        for i in range(ns):
+            _native.check(L.pvnet_backbone_run_stage(handle, i, x.data_ptr(), b, H, W, out.data_ptr(), mask.data_ptr(),
+                                                     8, ws.data_ptr(), ws.numel(), stream), "run_stage")
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        if rep:
+            acc += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(ns)])
+    ms = acc / reps
+    is_conv = np.array([("layer" in nm or nm.startswith("fc") or nm.startswith("conv")) and "head" not in nm
+                        for nm in names])
+    conv_ms = float(ms[is_conv].sum())
+    flops = (GFLOP_PER_IMAGE - GFLOP_STEM_HEAD) * 1e9 * b
+    achieved = flops / (conv_ms * 1e-3) / 1e12
+    bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
+    peak = bf16 / 2.0
+    stages = [{"stage": nm, "ms": round(float(t), 4)} for nm, t in zip(names, ms)]
+    return {
+        "bound": "tensor", "kernel": "k_conv_tc (tcgen05.mma kind::tf32, 25 launches/step)",
+        "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+        "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tcgen05 tf32 = half the bf16 rate)"
+                        if "bf16_tflops_sustained" in peaks else "fallback 1590/2"),
+        "algorithmic_gflop_per_launch_set": round(flops / 1e9, 1), "conv_ms_per_step": round(conv_ms, 3),
+        "backbone_ms_per_step": round(float(ms.sum()), 3), "traffic": None,
+    }, stages
+
+
+# ----------------------------------------------------------------------------- cpu side
+def cpu_vote_baseline(seconds_budget=15.0):
+    """Oracle port of the voting path (ransac_voting_layer_v3) on the host cores: bounded
+    sample = images of 20000 foreground px, K=9, 256 hypotheses."""
+    from oracle import pvnet_oracle as po
+    from pvnet_b200 import synthetic as syn
+    mask = syn.disc_mask(TARGET_FG)
+    field = syn.planted_field(mask, K_KP, 1)[0]
+    vertex = syn.as_reference_view(field[None])
+    idxs = [syn.draw_idxs(TARGET_FG, HYP, K_KP, seed=0)]
+    po.ransac_voting_layer_v3(mask[None], vertex, HYP, inlier_thresh=THRESH, idxs=idxs)   # warm
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds_budget and n < 64:
+        po.ransac_voting_layer_v3(mask[None], vertex, HYP, inlier_thresh=THRESH, idxs=idxs)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": round(n / dt, 3), "unit": "images/sec (voting path only)", "cores": po.num_threads(),
+            "kind": "port", "sample": f"{n} images x (20000 fg px, K=9, 256 hyp) of ransac_voting_layer_v3, "
+                                      f"oracle/pvnet_oracle.c with OpenMP"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's path on the HOST cores.  The reference has no CPU
+    voting code of its own (its extension is CUDA only), so this arm is: the reference
+    network graph (our nn.Module is bit-identical to the reference classes on the CPU, see
+    tests/test_backbone_cpu.py) in eval mode under torch CPU + the oracle port of the voting
+    kernels, all host threads.  Bounded sample: 1 image per step."""
+    rank, world, _ = _rank_world()
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import pvnet_oracle as po
+    from pvnet_b200 import synthetic as syn
+    from pvnet_b200.model_repository import Resnet18_8s
+    torch.manual_seed(0)
+    net = Resnet18_8s(2 * K_KP, 2).eval()
+    x = torch.from_numpy(syn.backbone_input(1, 0))
+    mask = syn.disc_mask(TARGET_FG)
+    idxs = [syn.draw_idxs(TARGET_FG, HYP, K_KP, seed=0)]
+
+    def step():
+        with torch.no_grad():
+            seg, ver = net._forward_torch(x)
+        vertex = ver.permute(0, 2, 3, 1).reshape(1, H, W, K_KP, 2).numpy()
+        # vote on a 20000-px disc (random-init logits have no object), same sizes as our arm
+        return po.ransac_voting_layer_v3(mask[None], vertex, HYP, inlier_thresh=THRESH, idxs=idxs)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = steps / dt
+    cores = po.num_threads()
+    line = {
+        "impl": "reference", "metric": "images/sec (480x640, K=9) backbone+vote", "value": round(val, 4),
+        "unit": "images/sec", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2 shape, 1 image/step on the host: Resnet18_8s(18,2) eval forward "
+                               "(torch CPU, reference graph) + ransac_voting_layer_v3(256 hyp, thresh 0.99, 20000 fg px)"},
+        "cpu_baseline": {"value": round(val, 4), "unit": "images/sec", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps x 1 image"},
+        "e2e": {"value": round(val, 4), "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from pvnet_b200 import _native
+    from pvnet_b200 import synthetic as syn
+
+    rank, world, local = _rank_world()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: pvnet_b200 has no CPU path")
+    _native.lib()                                    # fail loudly if the extension is missing
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    net = build_model(torch, dev)
+    step = make_step(torch, net)
+    # 3 rotating input batches (3 x 59 MB > 126 MB L2); different per rank
+    hosts = [torch.from_numpy(syn.backbone_input(BATCH, 1000 * 2 + 17 * rank + i)).pin_memory() for i in range(3)]
+    xs = [h.to(dev, non_blocking=True) for h in hosts]
+    torch.cuda.synchronize()
+    fg = calibrate_foreground(torch, net, xs[0])
+    gathered = [torch.empty([BATCH, K_KP, 2], device=dev) for _ in range(world)] if world > 1 else None
+
+    def full_step(x):
+        kp = step(x)
+        if world > 1:
+            dist.all_gather(gathered, kp)            # pose results to every rank
+        return kp
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing
+    with torch.no_grad():
+        for i in range(args.warmup):
+            full_step(xs[i % 3])
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        _native.launch_count_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            kp = full_step(xs[i % 3])
+        e1.record()
+        barrier()
+        launches = _native.launch_count()
+        ms_total = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---------------- end to end from pinned host buffers
+        kp_host = torch.empty([BATCH, K_KP, 2]).pin_memory()
+        xin = torch.empty_like(xs[0])
+
+        def e2e_step(i):
+            xin.copy_(hosts[i % 3], non_blocking=True)
+            kp = full_step(xin)
+            kp_host.copy_(kp, non_blocking=True)
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        with torch.no_grad():
+            roofline, stages = conv_roofline(torch, net, xs[0], peaks)
+        images = BATCH * world * args.steps
+        line = {
+            "metric": "images/sec (480x640, K=9) backbone+vote",
+            "value": round(images / (ms_total * 1e-3), 2), "unit": "images/sec",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate; vote fp32/fp64)", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: Resnet18_8s(18,2) forward + argmax + ransac_voting_layer_v3"
+                                   "(256 hyp, thresh 0.99), batch 16 per GPU, 480x640, K=9",
+                       "global_batch": BATCH * world, "parallelism": f"batch-sharded dp{world}",
+                       "fg_px_per_image": round(fg, 1), "rng": "batched", "weights": "random-init, BN stats randomised",
+                       "l2": "3 rotating input batches (177 MB) and a ~3.7 GB activation working set per step, both > 126 MB L2"},
+            "e2e": {"value": round(images / (ms_e2e * 1e-3), 2), "unit": "images/sec",
+                    "h2d_bytes_per_step": int(xs[0].numel() * 4), "d2h_bytes_per_step": int(BATCH * K_KP * 2 * 4)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "stages_ms": stages,
+        }
+        if not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_vote_baseline()
+            except Exception as e:          # the checker being unavailable must not hide the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "images/sec", "cores": 0, "kind": "port",
+                                        "sample": f"unavailable: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
