@@ -165,6 +165,12 @@ PVNET_API int pvnet_conv2d_nhwc(const float *in, int in_cs, int in_co, int Cin,
                                 int b, int H, int W, int ksize, int stride, int dilation,
                                 int act, int round_out, pvnet_stream_t stream);
 
+/* Test hook: which convolution kernel pvnet_conv2d_nhwc / the backbone use for layers both can
+ * run.  0 = automatic (persistent weights-resident column kernel for 3x3 stride-1 layers with
+ * Cout <= 64 whose weights fit in shared memory, per-tap kernel otherwise), 1 = per-tap kernel
+ * only, 2 = column kernel (error if the layer is not eligible). */
+PVNET_API int pvnet_conv_set_mode(int mode);
+
 /* Resnet18_8s.forward (lib/networks/model_repository.py:64-80), eval mode, whole batch.
  *
  * The handle is a host-side table of per-convolution weight pointers plus cached tensor

@@ -14,6 +14,12 @@ import torch
 from . import _native
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+MODE_AUTO, MODE_PER_TAP, MODE_COLUMN = 0, 1, 2
+
+
+def set_mode(mode: int):
+    """Test hook (pvnet_conv_set_mode): which kernel runs layers both kernels support."""
+    _native.check(_native.lib().pvnet_conv_set_mode(int(mode)), "pvnet_conv_set_mode")
 
 
 def round_tf32(t: torch.Tensor) -> torch.Tensor:

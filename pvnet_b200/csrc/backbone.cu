@@ -34,8 +34,16 @@ struct pvnet_backbone {
     // cached plan for one (b,h,w,workspace,in,out) combination
     int pb = 0, ph = 0, pw = 0;
     const void *p_ws = nullptr;
-    std::vector<unsigned char> plans;   // (CV_COUNT) * conv_plan_size()
+    std::vector<unsigned char> plans;   // CV_COUNT slots of plan_stride() bytes
+    bool use_col[CV_COUNT] = {};         // slot runs on the persistent column kernel (conv_col.cu)
+    bool head_fused = false;             // convraw.3 + argmax run inside convraw.0's epilogue
 };
+
+static size_t plan_stride()
+{
+    const size_t a = conv_plan_size(), b = conv_col_plan_size();
+    return ((a > b ? a : b) + 63) / 64 * 64;
+}
 
 namespace {
 
@@ -106,9 +114,23 @@ ConvDesc cd(const pvnet_backbone *m, int slot, const float *in, int in_cs, int i
 
 int build_plans(pvnet_backbone *m, const Buffers &B, int b, int h, int w)
 {
-    const size_t ps = conv_plan_size();
+    const size_t ps = plan_stride();
     m->plans.assign(ps * CV_COUNT, 0);
-    auto plan = [&](int slot, const ConvDesc &d) { return conv_plan_at(d, m->plans.data() + ps * slot); };
+    m->head_fused = false;
+    auto plan = [&](int slot, const ConvDesc &d) {
+        void *st = m->plans.data() + ps * slot;
+        const bool col = g_conv_mode != 1 && conv_col_eligible(d);
+        m->use_col[slot] = col;
+        if (!col) return conv_plan_at(d, st);
+        if (slot == CV_CONVRAW0 && m->raw == 32) {
+            // fuse convraw.3 + argmax into the epilogue; pointers are patched per forward call
+            HeadDesc hd{m->w[CV_HEAD], m->bias[CV_HEAD], reinterpret_cast<float *>(0x10), nullptr, 8, m->seg_dim,
+                        m->seg_dim + m->ver_dim};
+            m->head_fused = true;
+            return conv_col_plan_at(d, &hd, st);
+        }
+        return conv_col_plan_at(d, nullptr, st);
+    };
     const int h2 = h / 2, w2 = w / 2, h4 = h / 4, w4 = w / 4, h8 = h / 8, w8 = w / 8;
     const int c4s = m->s8 + 64, c8s = m->fc + 128, c2s = m->s4 + 64, c1s = m->s2 + 8;
     int rc = 0;
@@ -264,11 +286,17 @@ int run_stage(pvnet_backbone *m, const Stage &st, const Buffers &B, const float 
     case ST_STEM: return launch_stem(image_nchw, m->w[CV_STEM], m->bias[CV_STEM], B.C2, b, h, w, c2s, m->s4, s);
     case ST_PACK: return launch_pack_image(image_nchw, B.C1, b, h, w, c1s, m->s2, s);
     case ST_POOL: return launch_maxpool(B.C2, B.P, b, h2, w2, 64, c2s, m->s4, s);
-    case ST_CONV: return conv_launch_at(m->plans.data() + conv_plan_size() * st.slot, s);
+    case ST_CONV: {
+        unsigned char *pl = m->plans.data() + plan_stride() * st.slot;
+        if (!m->use_col[st.slot]) return conv_launch_at(pl, s);
+        if (st.slot == CV_CONVRAW0 && m->head_fused) conv_col_set_head_ptrs(pl, out_nchw, mask_out, mask_elem_size);
+        return conv_col_launch_at(pl, s);
+    }
     case ST_UP8: return launch_upsample2x(B.U8, B.C4, b, h8, w8, m->s8, c4s, 0, s);
     case ST_UP4: return launch_upsample2x(B.U4, B.C2, b, h4, w4, m->s4, c2s, 0, s);
     case ST_UP2: return launch_upsample2x(B.U2, B.C1, b, h2, w2, m->s2, c1s, 0, s);
     case ST_HEAD:
+        if (m->head_fused) return PVNET_OK;    // already written by convraw.0's epilogue
         return launch_head(B.R0, m->w[CV_HEAD], m->bias[CV_HEAD], out_nchw, mask_out, mask_elem_size, m->seg_dim,
                            m->seg_dim + m->ver_dim, b, h, w, s);
     }

@@ -1,0 +1,402 @@
+// conv_col.cu -- persistent, weights-resident 3x3 convolution for the narrow layers
+// (Cout <= 64: layer1.*, conv2s.0, convraw.0 of lib/networks/model_repository.py:22-58).
+//
+// Why a second kernel: with N <= 64 output channels a 128-pixel tile does too little math
+// per byte for the per-tap kernel (conv_tc.cu) -- ncu showed those launches L2-throughput
+// bound (62-71 %) with the tensor pipe 7-20 % active, because each of the 9 taps re-reads the
+// 128-pixel A tile and every CTA re-reads all weights.  Here:
+//   * ALL weights of the layer (<= 147 KB) are loaded into shared memory once per CTA, and the
+//     CTA is persistent over output tiles (grid = resident CTAs, static round-robin);
+//   * "column mode": for each kernel column kw and channel chunk, ONE TMA box of (TH+2d) rows is
+//     loaded, and the three vertical taps kh are descriptor offsets into it (kh*d*TW rows is a
+//     multiple of the 8-row swizzle atom), so A traffic drops from 9x to 3*(TH+2)/TH = 3.75x;
+//   * two TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * optional fused head (convraw.3 1x1 + bias + argmax, exact fp32) in the epilogue, writing
+//     the reference's NCHW output directly -- the [b,H,W,32] intermediate never exists.
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+#include <mutex>
+#include <new>
+
+namespace pvnet {
+
+int g_conv_mode = 0;
+
+namespace {
+
+constexpr int COL_THREADS = 192;
+constexpr int COL_TH = 8, COL_TW = 16;
+constexpr int HEAD_MAX = 64;
+
+struct ColGeom {
+    int Ho, Wo, tiles_x, tiles_y, total_tiles;
+    int dil, cin_chunks, cin_pad;
+    int BN;                 // == Cout (<= 64)
+    int stages;
+    int out_cs, out_co, res_cs, res_co;
+    int act, round_out;
+    // fused head
+    int head_cout, head_seg, mask_esz;
+};
+
+template <int KC>
+__host__ __device__ constexpr int col_a_bytes(int dil) { return (COL_TH + 2 * dil) * COL_TW * KC * 4; }
+
+template <int KC, bool HEAD>
+__global__ void __launch_bounds__(COL_THREADS, 1)
+    k_conv_col(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ColGeom g,
+               const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out,
+               const float *__restrict__ head_w, const float *__restrict__ head_b, float *__restrict__ head_out,
+               void *__restrict__ mask)
+{
+    constexpr int ROWB = KC * 4;                       // bytes per K-major row
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_tile = g.BN * ROWB;                    // one [BN][KC] weight tile
+    const int n_btiles = 9 * g.cin_chunks;
+    const int a_bytes = (COL_TH + 2 * g.dil) * COL_TW * ROWB;
+    uint8_t *sB = smem;
+    uint8_t *sA = smem + (size_t)n_btiles * b_tile;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + (size_t)g.stages * a_bytes);
+    uint64_t *wfull = bars;
+    uint64_t *full = bars + 1;
+    uint64_t *empty = full + g.stages;
+    uint64_t *tfull = empty + g.stages;               // [2]
+    uint64_t *tempty = tfull + 2;                     // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    float *s_head = reinterpret_cast<float *>(tmem_slot + 4);     // [head_cout*32 + head_cout]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(2 * g.BN)) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+        ptx::mbar_init(wfull, 1);
+        for (int s = 0; s < g.stages; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull[s], 1);
+            ptx::mbar_init(&tempty[s], 4);             // one arrive per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    if (HEAD) {
+        for (int i = threadIdx.x; i < g.head_cout * 32; i += COL_THREADS) s_head[i] = head_w[i];
+        for (int i = threadIdx.x; i < g.head_cout; i += COL_THREADS) s_head[g.head_cout * 32 + i] = head_b[i];
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_img = g.tiles_x * g.tiles_y;
+    const int kb_per_tile = 3 * g.cin_chunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // all weights, once: tile t = ((kw*cin_chunks + cc)*3 + kh) <- packed [Cout][kh][kw][cin]
+            ptx::mbar_arrive_expect_tx(wfull, (uint32_t)(n_btiles * b_tile));
+            for (int kw = 0; kw < 3; ++kw)
+                for (int cc = 0; cc < g.cin_chunks; ++cc)
+                    for (int kh = 0; kh < 3; ++kh)
+                        ptx::tma_load_2d(sB + (size_t)((kw * g.cin_chunks + cc) * 3 + kh) * b_tile, &tmB, wfull,
+                                         (kh * 3 + kw) * g.cin_pad + cc * KC, 0);
+            uint32_t cnt = 0;
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+                const int img = tile / tiles_per_img;
+                const int trem = tile - img * tiles_per_img;
+                const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
+                const int y0 = tyi * COL_TH, x0 = txi * COL_TW;
+                for (int kw = 0; kw < 3; ++kw)
+                    for (int cc = 0; cc < g.cin_chunks; ++cc, ++cnt) {
+                        const int s = cnt % g.stages;
+                        const uint32_t ph = (cnt / g.stages) & 1u;
+                        ptx::mbar_wait(&empty[s], ph ^ 1u);
+                        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)a_bytes);
+                        ptx::tma_load_4d(sA + (size_t)s * a_bytes, &tmA, &full[s], cc * KC, x0 + (kw - 1) * g.dil,
+                                         y0 - g.dil, img);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::make_idesc_tf32(128, g.BN);
+            ptx::mbar_wait(wfull, 0);
+            uint32_t cnt = 0, it = 0;
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t as = it & 1u;
+                ptx::mbar_wait(&tempty[as], ((it >> 1) & 1u) ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t tacc = tmem_base + as * (uint32_t)g.BN;
+                uint32_t first = 1;
+                for (int kb = 0; kb < kb_per_tile; ++kb, ++cnt) {
+                    const int s = cnt % g.stages;
+                    const uint32_t ph = (cnt / g.stages) & 1u;
+                    ptx::mbar_wait(&full[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t a0 = ptx::smem_u32(sA + (size_t)s * a_bytes);
+                    const uint32_t b0 = ptx::smem_u32(sB + (size_t)(kb * 3) * b_tile);
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const uint64_t adesc = ptx::make_kmajor_desc(a0 + kh * g.dil * COL_TW * ROWB, ROWB);
+                        const uint64_t bdesc = ptx::make_kmajor_desc(b0 + kh * b_tile, ROWB);
+#pragma unroll
+                        for (int k = 0; k < KC / 8; ++k) {
+                            ptx::mma_tf32_ss(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                             first ? 0u : 1u);
+                            first = 0;
+                        }
+                    }
+                    ptx::mma_commit(&empty[s]);
+                }
+                ptx::mma_commit(&tfull[as]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int ty = m / COL_TW, tx = m - ty * COL_TW;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t as = it & 1u;
+            const int img = tile / tiles_per_img;
+            const int trem = tile - img * tiles_per_img;
+            const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
+            const int y = tyi * COL_TH + ty, x = txi * COL_TW + tx;
+            const bool valid = (y < g.Ho) && (x < g.Wo);
+            const size_t pix = ((size_t)img * g.Ho + y) * g.Wo + x;
+            ptx::mbar_wait(&tfull[as], (it >> 1) & 1u);
+            ptx::tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)g.BN;
+            for (int c0 = 0; c0 < g.BN; c0 += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(tacc + (uint32_t)c0, r);
+                ptx::tmem_ld_wait();
+                if (c0 + 32 >= g.BN) {
+                    // accumulators are in registers: hand the TMEM stage back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+                }
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(bias + c0 + j);
+                if (res != nullptr && valid) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(res + pix * g.res_cs + g.res_co + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 rv = __ldg(rp + j);
+                        v[4 * j] += rv.x;
+                        v[4 * j + 1] += rv.y;
+                        v[4 * j + 2] += rv.z;
+                        v[4 * j + 3] += rv.w;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (g.act == 1) v[j] = fmaxf(v[j], 0.f);
+                    else if (g.act == 2) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
+                    if (g.round_out) v[j] = ptx::round_tf32(v[j]);
+                }
+                if (HEAD) {
+                    // convraw.3 (model_repository.py:57) + torch.argmax over the seg channels
+                    if (valid) {
+                        const size_t npix = (size_t)g.Ho * g.Wo;
+                        float *o = head_out + (size_t)img * g.head_cout * npix + (size_t)y * g.Wo + x;
+                        float best = -INFINITY;
+                        int best_c = 0;
+                        for (int co = 0; co < g.head_cout; ++co) {
+                            const float4 *wr = reinterpret_cast<const float4 *>(s_head + co * 32);
+                            float acc = s_head[g.head_cout * 32 + co];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 w4 = wr[j];
+                                acc = fmaf(v[4 * j], w4.x, acc);
+                                acc = fmaf(v[4 * j + 1], w4.y, acc);
+                                acc = fmaf(v[4 * j + 2], w4.z, acc);
+                                acc = fmaf(v[4 * j + 3], w4.w, acc);
+                            }
+                            o[(size_t)co * npix] = acc;
+                            if (co < g.head_seg && acc > best) {
+                                best = acc;
+                                best_c = co;
+                            }
+                        }
+                        if (mask) {
+                            if (g.mask_esz == 8) reinterpret_cast<long long *>(mask)[pix] = best_c;
+                            else reinterpret_cast<unsigned char *>(mask)[pix] = (unsigned char)best_c;
+                        }
+                    }
+                } else if (valid) {
+                    float4 *op = reinterpret_cast<float4 *>(out + pix * g.out_cs + g.out_co + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+struct ColPlan {
+    CUtensorMap tmA, tmB;
+    ColGeom g;
+    int kc, head;
+    unsigned grid;
+    size_t smem;
+    const float *bias, *res;
+    float *out;
+    HeadDesc hd;
+};
+
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+size_t col_smem(int kc, int cin_chunks, int bn, int dil, int stages, int head_cout)
+{
+    const size_t rowb = (size_t)kc * 4;
+    return 1024 + (size_t)9 * cin_chunks * bn * rowb + (size_t)stages * (COL_TH + 2 * dil) * COL_TW * rowb +
+           (size_t)(1 + 2 * stages + 4) * 8 + 16 + (size_t)(head_cout * 33) * 4 + 64;
+}
+
+template <int KC, bool HEAD>
+cudaError_t set_attr()
+{
+    return cudaFuncSetAttribute(k_conv_col<KC, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+}
+
+}  // namespace
+
+bool conv_col_eligible(const ConvDesc &d)
+{
+    if (d.ksize != 3 || d.stride != 1 || d.Cout > 64 || d.Cout % 32 != 0) return false;
+    const int kc = d.Cin % 32 == 0 ? 32 : 8;
+    if (d.Cin % kc != 0) return false;
+    // weights + at least 2 A stages must fit
+    return col_smem(kc, d.Cin / kc, d.Cout, d.dilation, 2, HEAD_MAX) <= SMEM_LIMIT;
+}
+
+size_t conv_col_plan_size() { return sizeof(ColPlan); }
+
+int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
+{
+    ColPlan *p = new (storage) ColPlan();
+    PV_CHECK_ARG(conv_col_eligible(d), "conv(col): layer not eligible for the column kernel");
+    PV_CHECK_ARG(d.in && d.w && d.bias && (d.out || head), "conv(col): null pointer");
+    PV_CHECK_ARG(d.in_cs % 4 == 0 && d.in_co % 4 == 0 && d.out_cs % 4 == 0 && d.out_co % 4 == 0,
+                 "conv(col): channel strides/offsets must be multiples of 4 floats");
+    PV_CHECK_ARG(!d.res || (d.res_cs % 4 == 0 && d.res_co % 4 == 0), "conv(col): residual stride/offset alignment");
+    PV_CHECK_ARG(!head || (d.Cout == 32 && head->cout >= 1 && head->cout <= HEAD_MAX && head->w && head->bias &&
+                           head->out_nchw && (!head->mask || head->mask_esz == 1 || head->mask_esz == 8)),
+                 "conv(col): bad fused-head description");
+    const int kc = d.Cin % 32 == 0 ? 32 : 8;
+    ColGeom &g = p->g;
+    g.Ho = d.H;
+    g.Wo = d.W;
+    g.tiles_x = (d.W + COL_TW - 1) / COL_TW;
+    g.tiles_y = (d.H + COL_TH - 1) / COL_TH;
+    g.total_tiles = g.tiles_x * g.tiles_y * d.b;
+    g.dil = d.dilation;
+    g.cin_chunks = d.Cin / kc;
+    g.cin_pad = d.Cin;
+    g.BN = d.Cout;
+    g.out_cs = d.out_cs;
+    g.out_co = d.out_co;
+    g.res_cs = d.res_cs;
+    g.res_co = d.res_co;
+    g.act = d.act;
+    g.round_out = d.round_out;
+    g.head_cout = head ? head->cout : 0;
+    g.head_seg = head ? head->seg_dim : 0;
+    g.mask_esz = head ? head->mask_esz : 0;
+    int stages = 8;
+    while (stages > 2 && col_smem(kc, g.cin_chunks, g.BN, g.dil, stages, g.head_cout) > SMEM_LIMIT) --stages;
+    g.stages = stages;
+    p->smem = col_smem(kc, g.cin_chunks, g.BN, g.dil, stages, g.head_cout);
+    p->kc = kc;
+    p->head = head ? 1 : 0;
+    if (head) p->hd = *head;
+    {
+        const float *base = d.in + d.in_co;
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.b};
+        cuuint64_t strides[3] = {(cuuint64_t)d.in_cs * 4, (cuuint64_t)d.W * d.in_cs * 4,
+                                 (cuuint64_t)d.H * d.W * d.in_cs * 4};
+        cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)COL_TW, (cuuint32_t)(COL_TH + 2 * d.dilation), 1};
+        int rc = tma_encode(&p->tmA, base, 4, dims, strides, box, kc * 4);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)9 * d.Cin, (cuuint64_t)d.Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)9 * d.Cin * 4};
+        cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)d.Cout};
+        int rc = tma_encode(&p->tmB, d.w, 2, dims, strides, box, kc * 4);
+        if (rc) return rc;
+    }
+    const int per_sm = (int)(SMEM_LIMIT / p->smem) >= 2 ? 2 : 1;
+    long long grid = (long long)sm_count() * per_sm;
+    if (grid > g.total_tiles) grid = g.total_tiles;
+    p->grid = (unsigned)grid;
+    p->bias = d.bias;
+    p->res = d.res;
+    p->out = d.out;
+    return PVNET_OK;
+}
+
+void conv_col_set_head_ptrs(void *storage, float *out_nchw, void *mask, int mask_esz)
+{
+    ColPlan *p = static_cast<ColPlan *>(storage);
+    p->hd.out_nchw = out_nchw;
+    p->hd.mask = mask;
+    p->hd.mask_esz = mask_esz;
+    p->g.mask_esz = mask_esz;
+}
+
+int conv_col_launch_at(const void *storage, cudaStream_t s)
+{
+    const ColPlan &p = *static_cast<const ColPlan *>(storage);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = set_attr<32, false>();
+        if (attr_err == cudaSuccess) attr_err = set_attr<8, false>();
+        if (attr_err == cudaSuccess) attr_err = set_attr<32, true>();
+        if (attr_err == cudaSuccess) attr_err = set_attr<8, true>();
+    });
+    PV_CUDA(attr_err);
+    const HeadDesc &h = p.hd;
+#define COL_LAUNCH(KC_, HEAD_)                                                                                    \
+    k_conv_col<KC_, HEAD_><<<p.grid, COL_THREADS, p.smem, s>>>(p.tmA, p.tmB, p.g, p.bias, p.res, p.out,           \
+                                                                p.head ? h.w : nullptr, p.head ? h.bias : nullptr, \
+                                                                p.head ? h.out_nchw : nullptr, p.head ? h.mask : nullptr)
+    if (p.kc == 32 && !p.head) COL_LAUNCH(32, false);
+    else if (p.kc == 8 && !p.head) COL_LAUNCH(8, false);
+    else if (p.kc == 32) COL_LAUNCH(32, true);
+    else COL_LAUNCH(8, true);
+#undef COL_LAUNCH
+    PV_LAUNCHED("k_conv_col");
+    return PVNET_OK;
+}
+
+}  // namespace pvnet
+
+extern "C" {
+// test hook: 0 auto, 1 force the per-tap kernel, 2 force the column kernel
+int pvnet_conv_set_mode(int mode)
+{
+    PV_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+    pvnet::g_conv_mode = mode;
+    return PVNET_OK;
+}
+}

@@ -219,8 +219,8 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
-static int encode(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
-                  const cuuint32_t *box, int swizzle_bytes)
+int tma_encode(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
+               const cuuint32_t *box, int swizzle_bytes)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
@@ -323,7 +323,7 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
         cuuint64_t strides[3] = {(cuuint64_t)d.stride * d.in_cs * 4, (cuuint64_t)d.stride * d.W * d.in_cs * 4,
                                  (cuuint64_t)d.H * d.W * d.in_cs * 4};
         cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)g.TW, (cuuint32_t)g.TH, 1};
-        int rc = encode(&p->amaps.m[pl], base, 4, dims, strides, box, swz);
+        int rc = tma_encode(&p->amaps.m[pl], base, 4, dims, strides, box, swz);
         if (rc) return rc;
     }
     for (int pl = nplanes; pl < 4; ++pl) p->amaps.m[pl] = p->amaps.m[0];
@@ -332,7 +332,7 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
         cuuint64_t dims[2] = {(cuuint64_t)g.taps * g.cin_pad, (cuuint64_t)d.Cout};
         cuuint64_t strides[1] = {(cuuint64_t)g.taps * g.cin_pad * 4};
         cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)g.BN};
-        int rc = encode(&p->tmB, d.w, 2, dims, strides, box, swz);
+        int rc = tma_encode(&p->tmB, d.w, 2, dims, strides, box, swz);
         if (rc) return rc;
     }
     p->grid = dim3((unsigned)(g.tiles_x * g.tiles_y * d.b), (unsigned)(d.Cout / g.BN));
@@ -378,6 +378,18 @@ int pvnet_conv2d_nhwc(const float *in, int in_cs, int in_co, int Cin, const floa
 {
     pvnet::ConvDesc d{in, in_cs, in_co, Cin, w_packed, bias, res, res_cs, res_co, out, out_cs, out_co, Cout,
                       b, H, W, ksize, stride, dilation, act, round_out};
+    const bool col = pvnet::g_conv_mode == 2 || (pvnet::g_conv_mode == 0 && pvnet::conv_col_eligible(d));
+    if (col) {
+        alignas(64) unsigned char storage[2048];
+        static_assert(sizeof(storage) >= 1024, "plan storage");
+        if (pvnet::conv_col_plan_size() > sizeof(storage)) {
+            pvnet::set_error("column plan larger than its stack storage");
+            return PVNET_E_STATE;
+        }
+        int rc = pvnet::conv_col_plan_at(d, nullptr, storage);
+        if (rc) return rc;
+        return pvnet::conv_col_launch_at(storage, (cudaStream_t)stream);
+    }
     pvnet::ConvPlan plan;
     int rc = pvnet::conv_plan(d, &plan);
     if (rc) return rc;

@@ -3,6 +3,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <cuda.h>
+
 namespace pvnet {
 
 struct ConvDesc {
@@ -18,6 +20,27 @@ struct ConvDesc {
     int ksize, stride, dilation;
     int act, round_out;
 };
+
+// Optional fused 1x1 head (convraw.3 + argmax) for the column kernel's epilogue.
+struct HeadDesc {
+    const float *w;      // [cout][32] fp32
+    const float *bias;   // [cout]
+    float *out_nchw;     // [b,cout,H,W]
+    void *mask;          // [b,H,W] int64 / u8, or null
+    int mask_esz, seg_dim, cout;
+};
+
+// cuTensorMapEncodeTiled wrapper (fp32 elements); swizzle_bytes in {128,64,32}
+int tma_encode(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
+               const cuuint32_t *box, int swizzle_bytes);
+
+// conv mode override for tests: 0 auto, 1 force per-tap kernel, 2 force column kernel
+extern int g_conv_mode;
+bool conv_col_eligible(const ConvDesc &d);
+size_t conv_col_plan_size();
+int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *plan_storage);
+int conv_col_launch_at(const void *plan_storage, cudaStream_t s);
+void conv_col_set_head_ptrs(void *plan_storage, float *out_nchw, void *mask, int mask_esz);
 
 // A plan = encoded tensor maps + launch geometry; opaque bytes so callers can cache it.
 size_t conv_plan_size();

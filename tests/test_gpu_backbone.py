@@ -24,13 +24,19 @@ def _net(ver, seed=1):
     return net.to(DEV).eval()
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["auto(column+fused head)", "per-tap only"])
 @pytest.mark.parametrize("tag,ver", [("k9", 18), ("k17", 34)])
-def test_native_vs_reference_golden(tag, ver):
+def test_native_vs_reference_golden(tag, ver, mode):
+    from pvnet_b200 import conv as pc
     z = np.load(os.path.join(GOLDEN, "resnet18_8s_ref.npz"))
-    net = _net(ver)
-    with torch.no_grad():
-        seg, v = net(torch.from_numpy(z[tag + "_x"]).to(DEV))
-    torch.cuda.synchronize()
+    pc.set_mode(mode)
+    try:
+        net = _net(ver)
+        with torch.no_grad():
+            seg, v = net(torch.from_numpy(z[tag + "_x"]).to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        pc.set_mode(0)
     for name, got, ref in (("seg", seg, z[tag + "_seg"]), ("ver", v, z[tag + "_ver"])):
         got = got.cpu().numpy()
         err = np.abs(got - ref).max()

@@ -67,7 +67,37 @@ def _run_case(b, H, W, cin, cout, k, stride, dil, act, with_res, in_extra=0, out
     (1, 60, 80, 384, 128, 3, 1, 1, 2, False),   # conv8s shape
 ])
 def test_conv_vs_torch(cfg):
-    _run_case(*cfg)
+    pc.set_mode(pc.MODE_PER_TAP)
+    try:
+        _run_case(*cfg)
+    finally:
+        pc.set_mode(pc.MODE_AUTO)
+
+
+@pytest.mark.parametrize("cfg", [
+    # the persistent weights-resident column kernel (3x3, stride 1, Cout <= 64)
+    (1, 16, 32, 32, 32, 3, 1, 1, 0, False),     # one tile, one chunk
+    (2, 24, 40, 64, 64, 3, 1, 1, 1, True),      # layer1 BasicBlock conv2: residual + ReLU, partial tiles, N=64
+    (1, 40, 48, 40, 32, 3, 1, 1, 2, False),     # convraw.0: Cin=40 -> 8-channel chunks, LeakyReLU
+    (1, 48, 80, 128, 32, 3, 1, 1, 2, False),    # conv2s.0 shape (weights 147 KB resident)
+    (3, 64, 96, 64, 64, 3, 1, 1, 1, False),     # many tiles per CTA: exercises the persistent loop / TMEM ping-pong
+    (1, 24, 40, 32, 32, 3, 1, 2, 0, False),     # dilation 2 in column mode
+])
+def test_conv_column_kernel_vs_torch(cfg):
+    pc.set_mode(pc.MODE_COLUMN)
+    try:
+        _run_case(*cfg)
+    finally:
+        pc.set_mode(pc.MODE_AUTO)
+
+
+def test_conv_column_kernel_large_persistent():
+    """More tiles than resident CTAs (148 SMs x 2): every CTA loops several times."""
+    pc.set_mode(pc.MODE_COLUMN)
+    try:
+        _run_case(2, 240, 320, 40, 32, 3, 1, 1, 2, False, seed=3)
+    finally:
+        pc.set_mode(pc.MODE_AUTO)
 
 
 def test_conv_channel_offsets():
