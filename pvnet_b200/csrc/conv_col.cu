@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(COL_THREADS, 1)
     uint64_t *tfull = empty + g.stages;               // [2]
     uint64_t *tempty = tfull + 2;                     // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
-    float *s_head = reinterpret_cast<float *>(tmem_slot + 4);     // [head_cout*32 + head_cout]
+    float *s_head = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // [head_cout*33]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t tmem_cols = 32;
