@@ -150,13 +150,14 @@ PVNET_API void pvnet_launch_count_reset(void);
  *                               + sum_{kh,kw,ci} w[co][kh][kw][ci] * in[n, y*stride+(kh-c)*dil, x*stride+(kw-c)*dil, in_co+ci] )
  *
  *   in        NHWC buffer [b,H,W,in_cs]; the conv reads channels [in_co, in_co+Cin)
- *   w_packed  [Cout][ksize*ksize][Cin] fp32 (BatchNorm already folded in), bias [Cout]
+ *   w_packed  [Cout][ksize*ksize][cin_pad] fp32 (BatchNorm already folded in; cin_pad = Cin rounded up
+ *             to a multiple of 32, zero padded; 16 stays 16), bias [Cout]
  *   res       NHWC [b,H/stride,W/stride,res_cs] read at res_co, or NULL
  *   out       NHWC [b,H/stride,W/stride,out_cs] written at channel offset out_co
  *             (writing into a slice of a wider buffer replaces torch.cat)
  *   ksize 1|3, stride 1|2 (2 needs even H,W, dilation 1), padding = dilation*(ksize-1)/2
  *   act 0 none, 1 ReLU, 2 LeakyReLU(0.1); round_out != 0 rounds the stored values to TF32
- *   Cin multiple of 8, Cout multiple of 32; strides/offsets multiples of 4 floats.
+ *   Cin multiple of 4, Cout multiple of 32; strides/offsets multiples of 4 floats.
  */
 PVNET_API int pvnet_conv2d_nhwc(const float *in, int in_cs, int in_co, int Cin,
                                 const float *w_packed, const float *bias,
@@ -181,9 +182,12 @@ PVNET_API int pvnet_conv_set_mode(int mode);
  *                        layer1.1.conv1, layer1.1.conv2, layer2.0.conv1, layer2.0.downsample,
  *                        layer2.0.conv2, layer2.1.conv1, layer2.1.conv2, layer3.* and layer4.* in the
  *                        same pattern, fc.0, conv8s.0, conv4s.0, conv2s.0, convraw.0), each packed
- *                        [Cout][kh*kw][Cin] with its BatchNorm folded in, bias [Cout].  convraw.0's
- *                        Cin is s2dim+8: s2dim upsampled channels, 3 image channels, 5 zeros.
+ *                        [Cout][kh*kw][cin_pad] with its BatchNorm folded in, bias [Cout].  convraw.0 reads
+ *                        s2dim+8 buffer channels (s2dim upsampled, 3 image, 5 zeros); cin_pad rounds up to 32.
  *   slot 25              convraw.3 (1x1, with bias): [seg_dim+ver_dim][32], bias [seg_dim+ver_dim]
+ *   slot 26              the stem once more for the tensor-core path: the 7x7 stride-2 conv written as
+ *                        a 4x4 stride-1 conv over the 2x2 space-to-depth image, packed [64][4][4][16]
+ *                        (tap (ty,tx), channel (py*2+px)*3+c holds w[c][2ty+py-1][2tx+px-1]; rest 0)
  * pvnet_backbone_forward:
  *   image_nchw  f32 [b,3,h,w] (h,w multiples of 8)
  *   out_nchw    f32 [b,seg_dim+ver_dim,h,w]: seg logits are channels [0,seg_dim), the vertex

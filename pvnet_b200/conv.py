@@ -40,14 +40,41 @@ def fold_bn(weight, bn_weight=None, bn_bias=None, bn_mean=None, bn_var=None, eps
     return w.float(), b.float()
 
 
+def cin_padded(cin: int) -> int:
+    """Channels per tap in the packed weights: 16 stays 16, everything else rounds up to 32."""
+    return 16 if cin == 16 else (cin + 31) // 32 * 32
+
+
 def pack_weight(w: torch.Tensor, cin_pad: int | None = None, cout_pad: int | None = None, tf32: bool = True):
-    """[Cout,Cin,kh,kw] -> [Cout_pad][kh*kw][Cin_pad] contiguous (zero padded)."""
+    """[Cout,Cin,kh,kw] -> [Cout_pad][kh*kw][cin_pad] contiguous (zero padded; cin_pad defaults to
+    cin_padded(Cin), what the kernels expect)."""
     cout, cin, kh, kw = w.shape
-    cin_pad = cin if cin_pad is None else cin_pad
+    cin_pad = cin_padded(cin) if cin_pad is None else cin_pad
     cout_pad = cout if cout_pad is None else cout_pad
     p = torch.zeros(cout_pad, kh * kw, cin_pad, dtype=torch.float32, device=w.device)
     p[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
     return round_tf32(p) if tf32 else p.contiguous()
+
+
+def pack_stem_s2d(w: torch.Tensor) -> torch.Tensor:
+    """conv1 [64,3,7,7] (stride 2, pad 3) -> [64][4][4][16], the equivalent 4x4 stride-1 conv on
+    the 2x2 space-to-depth image: out(o) = sum_k w[k] in(2o+k-3); with in(2j+p) = S[j][p] the tap
+    t = j-o+2 in {0..3} and parity p carry k = 2t+p-1 (zero weight when k is outside 0..6)."""
+    cout = w.shape[0]
+    out = torch.zeros(cout, 4, 4, 16, dtype=torch.float32, device=w.device)
+    for ty in range(4):
+        for py in range(2):
+            kh = 2 * ty + py - 1
+            if not 0 <= kh <= 6:
+                continue
+            for tx in range(4):
+                for px in range(2):
+                    kw = 2 * tx + px - 1
+                    if not 0 <= kw <= 6:
+                        continue
+                    ch = (py * 2 + px) * 3
+                    out[:, ty, tx, ch:ch + 3] = w[:, :, kh, kw]
+    return round_tf32(out)
 
 
 def _p(t):

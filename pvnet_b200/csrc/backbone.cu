@@ -24,6 +24,7 @@ enum {
     CV_L3_0_C1, CV_L3_0_DS, CV_L3_0_C2, CV_L3_1_C1, CV_L3_1_C2,
     CV_L4_0_C1, CV_L4_0_DS, CV_L4_0_C2, CV_L4_1_C1, CV_L4_1_C2,
     CV_FC, CV_CONV8S, CV_CONV4S, CV_CONV2S, CV_CONVRAW0, CV_HEAD,
+    CV_STEM_TC,   // the stem again, packed [64][4][4][16] for the space-to-depth tensor-core form
     CV_COUNT
 };
 
@@ -37,6 +38,7 @@ struct pvnet_backbone {
     std::vector<unsigned char> plans;   // CV_COUNT slots of plan_stride() bytes
     bool use_col[CV_COUNT] = {};         // slot runs on the persistent column kernel (conv_col.cu)
     bool head_fused = false;             // convraw.3 + argmax run inside convraw.0's epilogue
+    bool stem_tc = false;                // stem runs as a 4x4 conv on the space-to-depth image
 };
 
 static size_t plan_stride()
@@ -48,7 +50,7 @@ static size_t plan_stride()
 namespace {
 
 struct Buffers {
-    float *C1, *R0, *C2, *U2, *P, *A1, *B1, *C4, *U4, *A2, *D2, *B2, *C8, *U8, *A3, *D3, *B3, *E3, *A4, *D4, *B4, *E4;
+    float *S2D, *C1, *R0, *C2, *U2, *P, *A1, *B1, *C4, *U4, *A2, *D2, *B2, *C8, *U8, *A3, *D3, *B3, *E3, *A4, *D4, *B4, *E4;
     size_t bytes;
 };
 
@@ -57,6 +59,7 @@ Buffers carve_buffers(const pvnet_backbone *m, void *ws, int b, int h, int w)
     Carver c(ws);
     Buffers B;
     const size_t p1 = (size_t)b * h * w, p2 = p1 / 4, p4 = p1 / 16, p8 = p1 / 64;
+    B.S2D = c.take<float>(p2 * 16);
     B.C1 = c.take<float>(p1 * (m->s2 + 8));
     B.R0 = c.take<float>(p1 * m->raw);
     B.C2 = c.take<float>(p2 * (m->s4 + 64));
@@ -134,6 +137,13 @@ int build_plans(pvnet_backbone *m, const Buffers &B, int b, int h, int w)
     const int h2 = h / 2, w2 = w / 2, h4 = h / 4, w4 = w / 4, h8 = h / 8, w8 = w / 8;
     const int c4s = m->s8 + 64, c8s = m->fc + 128, c2s = m->s4 + 64, c1s = m->s2 + 8;
     int rc = 0;
+    // stem (resnet.py:201-203) as a 4x4 stride-1 conv on the 2x2 space-to-depth image
+    m->stem_tc = g_conv_mode != 1;
+    if (m->stem_tc) {
+        ConvDesc d = cd(m, CV_STEM_TC, B.S2D, 16, 0, 16, B.C2, c2s, m->s4, 64, b, h2, w2, 4, 1, 1, 1);
+        m->use_col[CV_STEM_TC] = true;
+        if ((rc = conv_col_plan_at(d, nullptr, m->plans.data() + ps * CV_STEM_TC))) return rc;
+    }
     // layer1 (resnet.py:206): two BasicBlocks at 1/4 resolution
     if ((rc = plan(CV_L1_0_C1, cd(m, CV_L1_0_C1, B.P, 64, 0, 64, B.A1, 64, 0, 64, b, h4, w4, 3, 1, 1, 1)))) return rc;
     if ((rc = plan(CV_L1_0_C2, cd(m, CV_L1_0_C2, B.A1, 64, 0, 64, B.B1, 64, 0, 64, b, h4, w4, 3, 1, 1, 1, B.P, 64, 0)))) return rc;
@@ -227,8 +237,8 @@ struct Stage {
     const char *name;
 };
 const Stage kStages[] = {
-    {ST_STEM, CV_STEM, "stem conv1+bn1+relu (fp32 direct)"},
-    {ST_PACK, -1, "pack image NCHW->NHWC slice"},
+    {ST_PACK, -1, "image: space-to-depth + NHWC slice packing"},
+    {ST_STEM, CV_STEM, "stem conv1+bn1+relu"},
     {ST_POOL, -1, "maxpool 3x3/2"},
     {ST_CONV, CV_L1_0_C1, "layer1.0.conv1"}, {ST_CONV, CV_L1_0_C2, "layer1.0.conv2"},
     {ST_CONV, CV_L1_1_C1, "layer1.1.conv1"}, {ST_CONV, CV_L1_1_C2, "layer1.1.conv2"},
@@ -283,8 +293,12 @@ int run_stage(pvnet_backbone *m, const Stage &st, const Buffers &B, const float 
     const int h2 = h / 2, w2 = w / 2, h4 = h / 4, w4 = w / 4, h8 = h / 8, w8 = w / 8;
     const int c4s = m->s8 + 64, c2s = m->s4 + 64, c1s = m->s2 + 8;
     switch (st.kind) {
-    case ST_STEM: return launch_stem(image_nchw, m->w[CV_STEM], m->bias[CV_STEM], B.C2, b, h, w, c2s, m->s4, s);
-    case ST_PACK: return launch_pack_image(image_nchw, B.C1, b, h, w, c1s, m->s2, s);
+    case ST_STEM:
+        if (m->stem_tc) return conv_col_launch_at(m->plans.data() + plan_stride() * CV_STEM_TC, s);
+        return launch_stem(image_nchw, m->w[CV_STEM], m->bias[CV_STEM], B.C2, b, h, w, c2s, m->s4, s);
+    case ST_PACK:
+        if (m->stem_tc) return launch_s2d_pack(image_nchw, B.S2D, B.C1, b, h, w, c1s, m->s2, s);
+        return launch_pack_image(image_nchw, B.C1, b, h, w, c1s, m->s2, s);
     case ST_POOL: return launch_maxpool(B.C2, B.P, b, h2, w2, 64, c2s, m->s4, s);
     case ST_CONV: {
         unsigned char *pl = m->plans.data() + plan_stride() * st.slot;

@@ -116,6 +116,55 @@ int launch_pack_image(const float *in, float *out, int b, int H, int W, int out_
     return PVNET_OK;
 }
 
+// ------------------------------------------------------------------ space-to-depth + image packing
+// One pass over the NCHW image that writes (a) S [b,H/2,W/2,16]: the 2x2 space-to-depth image,
+// channel (py*2+px)*3+c, 4 zero channels, for the tensor-core stem (a 7x7 stride-2 conv is a
+// 4x4 stride-1 conv on S), and (b) the image slice of the convraw.0 input buffer (3 channels +
+// 5 zeros at out_co).  Values rounded to tf32.
+__global__ void k_s2d_pack(const float *__restrict__ in, float *__restrict__ s2d, float *__restrict__ out, int H, int W,
+                           long long total /* b*H/2*W/2 */, int out_cs, int out_co)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int W2 = W / 2, H2 = H / 2;
+    const int x2 = (int)(i % W2);
+    long long r = i / W2;
+    const int y2 = (int)(r % H2);
+    const long long n = r / H2;
+    const long long plane = (long long)H * W;
+    const float *src = in + n * 3 * plane + (long long)(2 * y2) * W + 2 * x2;
+    float v[16];
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[(py * 2 + px) * 3 + c] = ptx::round_tf32(src[c * plane + py * W + px]);
+    v[12] = v[13] = v[14] = v[15] = 0.f;
+    float4 *so = reinterpret_cast<float4 *>(s2d + i * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) so[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+        for (int px = 0; px < 2; ++px) {
+            const long long pix = n * plane + (long long)(2 * y2 + py) * W + (2 * x2 + px);
+            float4 *o = reinterpret_cast<float4 *>(out + pix * out_cs + out_co);
+            const int b = (py * 2 + px) * 3;
+            o[0] = make_float4(v[b], v[b + 1], v[b + 2], 0.f);
+            o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+}
+
+int launch_s2d_pack(const float *in, float *s2d, float *out, int b, int H, int W, int out_cs, int out_co,
+                    cudaStream_t s)
+{
+    const long long total = (long long)b * (H / 2) * (W / 2);
+    k_s2d_pack<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, s2d, out, H, W, total, out_cs, out_co);
+    PV_LAUNCHED("k_s2d_pack");
+    return PVNET_OK;
+}
+
 // ------------------------------------------------------------------ max-pool 3x3/2 pad 1
 // (resnet.py:142,204).  in NHWC [b,H,W,in_cs] at in_co (C channels) -> out [b,H/2,W/2,C]
 __global__ void k_maxpool(const float *__restrict__ in, float *__restrict__ out, int H, int W, int C, int in_cs,

@@ -32,8 +32,10 @@ constexpr int HEAD_MAX = 64;
 struct ColGeom {
     int Ho, Wo, tiles_x, tiles_y, total_tiles;
     int dil, cin_chunks, cin_pad;
+    int KW, KH, pad_l, pad_t;   // taps and how many of them lie left of / above the output pixel
     int BN;                 // == Cout (<= 64)
     int stages;
+    int resident;           // 1: all weights loaded once per CTA; 0: the KH weight tiles ride in each stage
     int out_cs, out_co, res_cs, res_co;
     int act, round_out;
     // fused head
@@ -54,11 +56,12 @@ __global__ void __launch_bounds__(COL_THREADS, 1)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_tile = g.BN * ROWB;                    // one [BN][KC] weight tile
-    const int n_btiles = 9 * g.cin_chunks;
-    const int a_bytes = (COL_TH + 2 * g.dil) * COL_TW * ROWB;
+    const int n_btiles = g.KW * g.KH * g.cin_chunks;
+    const int a_bytes = (COL_TH + (g.KH - 1) * g.dil) * COL_TW * ROWB;
+    const int stage_bytes = a_bytes + (g.resident ? 0 : g.KH * b_tile);
     uint8_t *sB = smem;
-    uint8_t *sA = smem + (size_t)n_btiles * b_tile;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + (size_t)g.stages * a_bytes);
+    uint8_t *sA = smem + (g.resident ? (size_t)n_btiles * b_tile : 0);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + (size_t)g.stages * stage_bytes);
     uint64_t *wfull = bars;
     uint64_t *full = bars + 1;
     uint64_t *empty = full + g.stages;
@@ -98,38 +101,45 @@ __global__ void __launch_bounds__(COL_THREADS, 1)
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int tiles_per_img = g.tiles_x * g.tiles_y;
-    const int kb_per_tile = 3 * g.cin_chunks;
+    const int kb_per_tile = g.KW * g.cin_chunks;
 
     if (warp == 0) {
         if (lane == 0) {
-            // all weights, once: tile t = ((kw*cin_chunks + cc)*3 + kh) <- packed [Cout][kh][kw][cin]
-            ptx::mbar_arrive_expect_tx(wfull, (uint32_t)(n_btiles * b_tile));
-            for (int kw = 0; kw < 3; ++kw)
-                for (int cc = 0; cc < g.cin_chunks; ++cc)
-                    for (int kh = 0; kh < 3; ++kh)
-                        ptx::tma_load_2d(sB + (size_t)((kw * g.cin_chunks + cc) * 3 + kh) * b_tile, &tmB, wfull,
-                                         (kh * 3 + kw) * g.cin_pad + cc * KC, 0);
+            // all weights, once: tile t = ((kw*cin_chunks + cc)*KH + kh) <- packed [Cout][kh][kw][cin]
+            if (g.resident) {
+                ptx::mbar_arrive_expect_tx(wfull, (uint32_t)(n_btiles * b_tile));
+                for (int kw = 0; kw < g.KW; ++kw)
+                    for (int cc = 0; cc < g.cin_chunks; ++cc)
+                        for (int kh = 0; kh < g.KH; ++kh)
+                            ptx::tma_load_2d(sB + (size_t)((kw * g.cin_chunks + cc) * g.KH + kh) * b_tile, &tmB,
+                                             wfull, (kh * g.KW + kw) * g.cin_pad + cc * KC, 0);
+            }
             uint32_t cnt = 0;
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
                 const int img = tile / tiles_per_img;
                 const int trem = tile - img * tiles_per_img;
                 const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
                 const int y0 = tyi * COL_TH, x0 = txi * COL_TW;
-                for (int kw = 0; kw < 3; ++kw)
+                for (int kw = 0; kw < g.KW; ++kw)
                     for (int cc = 0; cc < g.cin_chunks; ++cc, ++cnt) {
                         const int s = cnt % g.stages;
                         const uint32_t ph = (cnt / g.stages) & 1u;
                         ptx::mbar_wait(&empty[s], ph ^ 1u);
-                        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)a_bytes);
-                        ptx::tma_load_4d(sA + (size_t)s * a_bytes, &tmA, &full[s], cc * KC, x0 + (kw - 1) * g.dil,
-                                         y0 - g.dil, img);
+                        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+                        uint8_t *st = sA + (size_t)s * stage_bytes;
+                        ptx::tma_load_4d(st, &tmA, &full[s], cc * KC, x0 + (kw - g.pad_l) * g.dil,
+                                         y0 - g.pad_t * g.dil, img);
+                        if (!g.resident)
+                            for (int kh = 0; kh < g.KH; ++kh)
+                                ptx::tma_load_2d(st + a_bytes + (size_t)kh * b_tile, &tmB, &full[s],
+                                                 (kh * g.KW + kw) * g.cin_pad + cc * KC, 0);
                     }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = ptx::make_idesc_tf32(128, g.BN);
-            ptx::mbar_wait(wfull, 0);
+            if (g.resident) ptx::mbar_wait(wfull, 0);
             uint32_t cnt = 0, it = 0;
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
                 const uint32_t as = it & 1u;
@@ -142,10 +152,9 @@ __global__ void __launch_bounds__(COL_THREADS, 1)
                     const uint32_t ph = (cnt / g.stages) & 1u;
                     ptx::mbar_wait(&full[s], ph);
                     ptx::tc_fence_after();
-                    const uint32_t a0 = ptx::smem_u32(sA + (size_t)s * a_bytes);
-                    const uint32_t b0 = ptx::smem_u32(sB + (size_t)(kb * 3) * b_tile);
-#pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) {
+                    const uint32_t a0 = ptx::smem_u32(sA + (size_t)s * stage_bytes);
+                    const uint32_t b0 = g.resident ? ptx::smem_u32(sB + (size_t)(kb * g.KH) * b_tile) : a0 + a_bytes;
+                    for (int kh = 0; kh < g.KH; ++kh) {
                         const uint64_t adesc = ptx::make_kmajor_desc(a0 + kh * g.dil * COL_TW * ROWB, ROWB);
                         const uint64_t bdesc = ptx::make_kmajor_desc(b0 + kh * b_tile, ROWB);
 #pragma unroll
@@ -264,10 +273,14 @@ struct ColPlan {
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
-size_t col_smem(int kc, int cin_chunks, int bn, int dil, int stages, int head_cout)
+int col_kc(int Cin) { return Cin == 16 ? 16 : 32; }   // ragged last chunk: TMA zero-fills, weights are zero-padded
+
+size_t col_smem(int kc, int ksize, int cin_chunks, int bn, int dil, int stages, int head_cout, bool resident = true)
 {
     const size_t rowb = (size_t)kc * 4;
-    return 1024 + (size_t)9 * cin_chunks * bn * rowb + (size_t)stages * (COL_TH + 2 * dil) * COL_TW * rowb +
+    const size_t a = (size_t)(COL_TH + (ksize - 1) * dil) * COL_TW * rowb, bt = (size_t)bn * rowb;
+    return 1024 + (resident ? (size_t)ksize * ksize * cin_chunks * bt : 0) +
+           (size_t)stages * (a + (resident ? 0 : (size_t)ksize * bt)) +
            (size_t)(1 + 2 * stages + 4) * 8 + 16 + (size_t)(head_cout * 33) * 4 + 64;
 }
 
@@ -281,11 +294,11 @@ cudaError_t set_attr()
 
 bool conv_col_eligible(const ConvDesc &d)
 {
-    if (d.ksize != 3 || d.stride != 1 || d.Cout > 64 || d.Cout % 32 != 0) return false;
-    const int kc = d.Cin % 32 == 0 ? 32 : 8;
-    if (d.Cin % kc != 0) return false;
-    // weights + at least 2 A stages must fit
-    return col_smem(kc, d.Cin / kc, d.Cout, d.dilation, 2, HEAD_MAX) <= SMEM_LIMIT;
+    // ksize 4 = the space-to-depth form of the 7x7/2 stem: taps at offsets {-2,-1,0,1}
+    if ((d.ksize != 3 && d.ksize != 4) || d.stride != 1 || d.Cout > 64 || d.Cout % 32 != 0) return false;
+    const int kc = col_kc(d.Cin);
+    if (d.Cin % 4 != 0) return false;
+    return col_smem(kc, d.ksize, (d.Cin + kc - 1) / kc, d.Cout, d.dilation, 3, HEAD_MAX, false) <= SMEM_LIMIT;
 }
 
 size_t conv_col_plan_size() { return sizeof(ColPlan); }
@@ -298,19 +311,21 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     PV_CHECK_ARG(d.in_cs % 4 == 0 && d.in_co % 4 == 0 && d.out_cs % 4 == 0 && d.out_co % 4 == 0,
                  "conv(col): channel strides/offsets must be multiples of 4 floats");
     PV_CHECK_ARG(!d.res || (d.res_cs % 4 == 0 && d.res_co % 4 == 0), "conv(col): residual stride/offset alignment");
-    PV_CHECK_ARG(!head || (d.Cout == 32 && head->cout >= 1 && head->cout <= HEAD_MAX && head->w && head->bias &&
+    PV_CHECK_ARG(!head || (d.Cout == 32 && col_kc(d.Cin) != 16 && head->cout >= 1 && head->cout <= HEAD_MAX && head->w && head->bias &&
                            head->out_nchw && (!head->mask || head->mask_esz == 1 || head->mask_esz == 8)),
                  "conv(col): bad fused-head description");
-    const int kc = d.Cin % 32 == 0 ? 32 : 8;
+    const int kc = col_kc(d.Cin);
     ColGeom &g = p->g;
+    g.KW = g.KH = d.ksize;
+    g.pad_l = g.pad_t = d.ksize == 4 ? 2 : 1;
     g.Ho = d.H;
     g.Wo = d.W;
     g.tiles_x = (d.W + COL_TW - 1) / COL_TW;
     g.tiles_y = (d.H + COL_TH - 1) / COL_TH;
     g.total_tiles = g.tiles_x * g.tiles_y * d.b;
     g.dil = d.dilation;
-    g.cin_chunks = d.Cin / kc;
-    g.cin_pad = d.Cin;
+    g.cin_chunks = (d.Cin + kc - 1) / kc;
+    g.cin_pad = g.cin_chunks * kc;          // weights are packed [Cout][KH][KW][cin_pad], zero padded
     g.BN = d.Cout;
     g.out_cs = d.out_cs;
     g.out_co = d.out_co;
@@ -321,10 +336,23 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     g.head_cout = head ? head->cout : 0;
     g.head_seg = head ? head->seg_dim : 0;
     g.mask_esz = head ? head->mask_esz : 0;
+    // Resident weights only if at least 6 A stages still fit next to them (the narrow layers are
+    // bound by bytes in flight, not by L2 bandwidth); otherwise the KH weight tiles of a K-block
+    // travel with its A box.  Two CTAs per SM when the footprint allows.
     int stages = 8;
-    while (stages > 2 && col_smem(kc, g.cin_chunks, g.BN, g.dil, stages, g.head_cout) > SMEM_LIMIT) --stages;
+    bool resident = true;
+    while (stages > 2 && col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, true) > SMEM_LIMIT)
+        --stages;
+    if (stages < 6 || col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, true) > SMEM_LIMIT) {
+        resident = false;
+        stages = 8;
+        while (stages > 2 &&
+               col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, false) > SMEM_LIMIT)
+            --stages;
+    }
     g.stages = stages;
-    p->smem = col_smem(kc, g.cin_chunks, g.BN, g.dil, stages, g.head_cout);
+    g.resident = resident ? 1 : 0;
+    p->smem = col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, resident);
     p->kc = kc;
     p->head = head ? 1 : 0;
     if (head) p->hd = *head;
@@ -333,13 +361,13 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
         cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.b};
         cuuint64_t strides[3] = {(cuuint64_t)d.in_cs * 4, (cuuint64_t)d.W * d.in_cs * 4,
                                  (cuuint64_t)d.H * d.W * d.in_cs * 4};
-        cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)COL_TW, (cuuint32_t)(COL_TH + 2 * d.dilation), 1};
+        cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)COL_TW, (cuuint32_t)(COL_TH + (d.ksize - 1) * d.dilation), 1};
         int rc = tma_encode(&p->tmA, base, 4, dims, strides, box, kc * 4);
         if (rc) return rc;
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)9 * d.Cin, (cuuint64_t)d.Cout};
-        cuuint64_t strides[1] = {(cuuint64_t)9 * d.Cin * 4};
+        cuuint64_t dims[2] = {(cuuint64_t)d.ksize * d.ksize * g.cin_pad, (cuuint64_t)d.Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)d.ksize * d.ksize * g.cin_pad * 4};
         cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)d.Cout};
         int rc = tma_encode(&p->tmB, d.w, 2, dims, strides, box, kc * 4);
         if (rc) return rc;
@@ -370,6 +398,7 @@ int conv_col_launch_at(const void *storage, cudaStream_t s)
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
         attr_err = set_attr<32, false>();
+        if (attr_err == cudaSuccess) attr_err = set_attr<16, false>();
         if (attr_err == cudaSuccess) attr_err = set_attr<8, false>();
         if (attr_err == cudaSuccess) attr_err = set_attr<32, true>();
         if (attr_err == cudaSuccess) attr_err = set_attr<8, true>();
@@ -381,6 +410,7 @@ int conv_col_launch_at(const void *storage, cudaStream_t s)
                                                                 p.head ? h.w : nullptr, p.head ? h.bias : nullptr, \
                                                                 p.head ? h.out_nchw : nullptr, p.head ? h.mask : nullptr)
     if (p.kc == 32 && !p.head) COL_LAUNCH(32, false);
+    else if (p.kc == 16 && !p.head) COL_LAUNCH(16, false);
     else if (p.kc == 8 && !p.head) COL_LAUNCH(8, false);
     else if (p.kc == 32) COL_LAUNCH(32, true);
     else COL_LAUNCH(8, true);

@@ -256,8 +256,7 @@ struct ConvPlan {
     float *out;
 };
 
-int conv_cin_pad(int Cin) { return Cin % 32 == 0 ? Cin : (Cin + 7) / 8 * 8; }
-int conv_kc(int Cin) { return Cin % 32 == 0 ? 32 : 8; }
+int conv_kc(int) { return 32; }   // ragged last channel chunk: TMA zero-fills, weights are zero-padded
 
 int conv_plan(const ConvDesc &d, ConvPlan *p)
 {
@@ -274,7 +273,7 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
                      ((uintptr_t)d.bias % 16 == 0),
                  "conv: pointers must be 16-byte aligned");
     const int kc = conv_kc(d.Cin);
-    PV_CHECK_ARG(d.Cin % kc == 0, "conv: Cin %d must be a multiple of 8", d.Cin);
+    PV_CHECK_ARG(d.Cin % 4 == 0, "conv: Cin %d must be a multiple of 4", d.Cin);
     ConvGeom &g = p->g;
     g.Ho = d.H / d.stride;
     g.Wo = d.W / d.stride;
@@ -284,8 +283,8 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
     g.tiles_x = (g.Wo + g.TW - 1) / g.TW;
     g.tiles_y = (g.Ho + g.TH - 1) / g.TH;
     g.taps = d.ksize * d.ksize;
-    g.cin_pad = d.Cin;
-    g.cin_chunks = d.Cin / kc;
+    g.cin_chunks = (d.Cin + kc - 1) / kc;
+    g.cin_pad = g.cin_chunks * kc;
     g.Cout = d.Cout;
     g.BN = d.Cout > 256 ? 256 : d.Cout;
     PV_CHECK_ARG(d.Cout % g.BN == 0, "conv: Cout %d not a multiple of the N tile %d", d.Cout, g.BN);

@@ -122,12 +122,21 @@ class Resnet18_8s(nn.Module):
                 elif conv_name == "convraw.3":        # head: fp32 [cout][32]
                     packed = w.reshape(w.shape[0], w.shape[1]).contiguous()
                 elif conv_name == "convraw.0":        # cat[fm(s2dim), image(3)] -> s2dim+8 input channels
-                    packed = pc.pack_weight(w, cin_pad=s2dim + 8)
+                    packed = pc.pack_weight(w, cin_pad=pc.cin_padded(s2dim + 8))
                 else:
                     packed = pc.pack_weight(w)
                 keep += [packed, b]
                 _native.check(L.pvnet_backbone_set_conv(handle, slot, packed.data_ptr(), b.data_ptr()),
                               f"pvnet_backbone_set_conv({conv_name})")
+            # slot 26: the stem as a 4x4 conv over the 2x2 space-to-depth image (tensor-core path)
+            bn = mods["resnet18_8s.bn1"]
+            w, b = pc.fold_bn(mods["resnet18_8s.conv1"].weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                              bn.eps)
+            w4 = pc.pack_stem_s2d(w.to(device))
+            b = b.to(device).contiguous()
+            keep += [w4, b]
+            _native.check(L.pvnet_backbone_set_conv(handle, len(_SLOTS), w4.data_ptr(), b.data_ptr()),
+                          "pvnet_backbone_set_conv(stem s2d)")
         self._native = (handle, keep, key)
         return handle
 

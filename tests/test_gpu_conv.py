@@ -110,3 +110,20 @@ def test_conv_round_out_is_tf32():
     out = torch.empty(1, 16, 32, 32, device=DEV)
     pc.conv2d_nhwc(x, 0, 32, pc.pack_weight(w), torch.zeros(32, device=DEV), out, 0, 32, 1, round_out=True)
     assert ((out.view(torch.int32) & 0x1FFF) == 0).all()
+
+
+def test_conv_column_kernel_4x4_s2d_stem_shape():
+    """ksize 4 = taps at offsets {-2,-1,0,1} (the space-to-depth form of the 7x7/2 stem),
+    Cin=16 -> 64-byte swizzled rows, weights [64][4][4][16] resident."""
+    g = torch.Generator().manual_seed(4)
+    b, H, W = 2, 40, 56
+    x = torch.randn(b, 16, H, W, generator=g)
+    w = torch.randn(64, 16, 4, 4, generator=g) / 16.0
+    bias = torch.randn(64, generator=g)
+    ref = F.relu(F.conv2d(F.pad(_trunc_tf32(x), (2, 1, 2, 1)).double(), pc.round_tf32(w).double(), bias.double()))
+    xin = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.empty(b, H, W, 64, device=DEV)
+    pc.conv2d_nhwc(xin, 0, 16, pc.pack_weight(w.to(DEV)), bias.to(DEV), out, 0, 64, 4, 1, 1, pc.ACT_RELU)
+    torch.cuda.synchronize()
+    err = (out.permute(0, 3, 1, 2).double().cpu() - ref).abs().max().item()
+    assert err <= 2e-5 * max(ref.abs().max().item(), 1.0) + 1e-5, err
