@@ -22,6 +22,11 @@ def set_mode(mode: int):
     _native.check(_native.lib().pvnet_conv_set_mode(int(mode)), "pvnet_conv_set_mode")
 
 
+def set_multicast(on: bool):
+    """Test hook (pvnet_conv_set_multicast): 2-CTA weight multicast in the per-tap kernel."""
+    _native.check(_native.lib().pvnet_conv_set_multicast(int(bool(on))), "pvnet_conv_set_multicast")
+
+
 def round_tf32(t: torch.Tensor) -> torch.Tensor:
     """Round fp32 to the nearest TF32 value (10 explicit mantissa bits), kept in fp32."""
     i = t.contiguous().view(torch.int32)

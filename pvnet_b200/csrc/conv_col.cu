@@ -273,7 +273,10 @@ struct ColPlan {
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
-int col_kc(int Cin) { return Cin == 16 ? 16 : 32; }   // ragged last chunk: TMA zero-fills, weights are zero-padded
+// K-chunk: 128-byte rows when Cin is a multiple of 32, 64-byte rows for the 16-channel stem, else
+// 32-byte rows (Cin=40: measured 0.73 ms vs 1.12 ms with zero-padded 128-byte rows).
+int col_kc(int Cin) { return Cin % 32 == 0 ? 32 : (Cin == 16 ? 16 : 8); }
+int col_cin_pad(int Cin) { return Cin == 16 ? 16 : (Cin + 31) / 32 * 32; }   // packing of the weights
 
 size_t col_smem(int kc, int ksize, int cin_chunks, int bn, int dil, int stages, int head_cout, bool resident = true)
 {
@@ -297,7 +300,7 @@ bool conv_col_eligible(const ConvDesc &d)
     // ksize 4 = the space-to-depth form of the 7x7/2 stem: taps at offsets {-2,-1,0,1}
     if ((d.ksize != 3 && d.ksize != 4) || d.stride != 1 || d.Cout > 64 || d.Cout % 32 != 0) return false;
     const int kc = col_kc(d.Cin);
-    if (d.Cin % 4 != 0) return false;
+    if (d.Cin % kc != 0) return false;
     return col_smem(kc, d.ksize, (d.Cin + kc - 1) / kc, d.Cout, d.dilation, 3, HEAD_MAX, false) <= SMEM_LIMIT;
 }
 
@@ -324,8 +327,8 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     g.tiles_y = (d.H + COL_TH - 1) / COL_TH;
     g.total_tiles = g.tiles_x * g.tiles_y * d.b;
     g.dil = d.dilation;
-    g.cin_chunks = (d.Cin + kc - 1) / kc;
-    g.cin_pad = g.cin_chunks * kc;          // weights are packed [Cout][KH][KW][cin_pad], zero padded
+    g.cin_chunks = d.Cin / kc;
+    g.cin_pad = col_cin_pad(d.Cin);         // weights are packed [Cout][KH][KW][cin_pad], zero padded
     g.BN = d.Cout;
     g.out_cs = d.out_cs;
     g.out_co = d.out_co;
@@ -336,14 +339,14 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     g.head_cout = head ? head->cout : 0;
     g.head_seg = head ? head->seg_dim : 0;
     g.mask_esz = head ? head->mask_esz : 0;
-    // Resident weights only if at least 6 A stages still fit next to them (the narrow layers are
-    // bound by bytes in flight, not by L2 bandwidth); otherwise the KH weight tiles of a K-block
-    // travel with its A box.  Two CTAs per SM when the footprint allows.
+    // Resident weights whenever at least 3 A stages still fit next to them (measured on conv2s.0:
+    // 0.43 ms resident with 3 stages vs 0.49 ms streaming with 6); otherwise the KH weight tiles
+    // of a K-block travel with its A box.  Two CTAs per SM when the footprint allows.
     int stages = 8;
     bool resident = true;
     while (stages > 2 && col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, true) > SMEM_LIMIT)
         --stages;
-    if (stages < 6 || col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, true) > SMEM_LIMIT) {
+    if (stages < 3 || col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, true) > SMEM_LIMIT) {
         resident = false;
         stages = 8;
         while (stages > 2 &&

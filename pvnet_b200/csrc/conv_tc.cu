@@ -31,7 +31,7 @@ namespace pvnet {
 
 struct ConvGeom {
     int Ho, Wo;
-    int tiles_x, tiles_y;
+    int tiles_x, tiles_y, total_m_tiles;
     int TH, TW;
     int taps, cin_chunks, cin_pad;
     int Cout, BN;
@@ -61,7 +61,12 @@ struct ConvCfg {
     }
 };
 
-template <int KC>
+// MC = 1: launched as clusters of 2 CTAs (adjacent M tiles, same N tile).  Each CTA loads its own
+// A box and HALF of the {KC, BN} weight tile, multicast into both CTAs' shared memory: the weight
+// tile, 2/3 of the bytes of a K-block at BN=256, crosses L2->SM once per pair instead of twice.
+// (ncu/bench: the 60x80 layers were bound at ~49 B/clk/SM of L2->SM traffic, 245 cycles per MMA
+// against the 128-cycle floor measured in benchmarks/micro/mma_rate.cu.)
+template <int KC, int MC>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
     k_conv_tc(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap tmB, const ConvGeom g,
               const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out)
@@ -79,8 +84,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = g.tiles_x * g.tiles_y;
-    const int img = blockIdx.x / tiles_per_img;
-    const int trem = blockIdx.x - img * tiles_per_img;
+    const uint32_t crank = MC ? ptx::cluster_ctarank() : 0u;
+    // an odd tile count leaves the last cluster one tile short: its second CTA recomputes the last
+    // tile (identical values) so that it still takes part in the multicast protocol
+    const int tile_lin = min((int)blockIdx.x, g.total_m_tiles - 1);
+    const int img = tile_lin / tiles_per_img;
+    const int trem = tile_lin - img * tiles_per_img;
     const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
     const int y0 = tyi * g.TH, x0 = txi * g.TW;
     const int n0 = blockIdx.y * g.BN;
@@ -94,7 +103,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         ptx::prefetch_tensormap(&amaps.m[0]);
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full[s], 1);
-            ptx::mbar_init(&empty[s], 1);
+            ptx::mbar_init(&empty[s], MC ? 2 : 1);     // both CTAs of the pair must have consumed the stage
         }
         ptx::mbar_init(tmem_full, 1);
         ptx::fence_barrier_init();
@@ -105,6 +114,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (MC) ptx::cluster_sync();                       // peer barriers are initialised before any remote arrive
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -119,7 +129,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                 uint8_t *sa = smem + (size_t)s * stage_bytes;
                 ptx::tma_load_4d(sa, &amaps.m[g.tap_map[tap]], &full[s], cc * KC, x0 + g.tap_ox[tap],
                                  y0 + g.tap_oy[tap], img);
-                ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], tap * g.cin_pad + cc * KC, n0);
+                if (MC) {
+                    const int half = b_bytes / 2;      // rows [crank*BN/2, +BN/2) of the weight tile
+                    ptx::tma_load_2d_mc(sa + Cfg::A_BYTES + crank * half, &tmB, &full[s], tap * g.cin_pad + cc * KC,
+                                        n0 + (int)crank * (g.BN / 2), (uint16_t)0x3);
+                } else {
+                    ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], tap * g.cin_pad + cc * KC, n0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -137,7 +153,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                 for (int k = 0; k < KC / 8; ++k)   // 8 tf32 = 32 B per MMA along K: +2 in 16-byte units
                     ptx::mma_tf32_ss(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                      (kb | k) != 0 ? 1u : 0u);
-                ptx::mma_commit(&empty[s]);
+                if (MC) ptx::mma_commit_mc(&empty[s], (uint16_t)0x3);
+                else ptx::mma_commit(&empty[s]);
             }
             ptx::mma_commit(tmem_full);
         }
@@ -194,6 +211,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (MC) ptx::cluster_sync();                       // no CTA exits while its peer may still write into it
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, tmem_cols);
@@ -249,13 +267,14 @@ struct ConvPlan {
     AMaps amaps;
     CUtensorMap tmB;
     ConvGeom g;
-    int kc;
+    int kc, mc;
     dim3 grid;
     size_t smem;
     const float *bias, *res;
     float *out;
 };
 
+int g_conv_mc = 1;   // pairs of CTAs multicast 256-row weight tiles (pvnet_conv_set_multicast)
 int conv_kc(int) { return 32; }   // ragged last channel chunk: TMA zero-fills, weights are zero-padded
 
 int conv_plan(const ConvDesc &d, ConvPlan *p)
@@ -282,6 +301,7 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
     g.TW = 16;
     g.tiles_x = (g.Wo + g.TW - 1) / g.TW;
     g.tiles_y = (g.Ho + g.TH - 1) / g.TH;
+    g.total_m_tiles = g.tiles_x * g.tiles_y * d.b;
     g.taps = d.ksize * d.ksize;
     g.cin_chunks = (d.Cin + kc - 1) / kc;
     g.cin_pad = g.cin_chunks * kc;
@@ -330,12 +350,15 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
     {
         cuuint64_t dims[2] = {(cuuint64_t)g.taps * g.cin_pad, (cuuint64_t)d.Cout};
         cuuint64_t strides[1] = {(cuuint64_t)g.taps * g.cin_pad * 4};
-        cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)g.BN};
+        // pairs of CTAs multicast the weight tile when it is the 256-row one (g_conv_mc: test hook)
+        p->mc = (g.BN == 256 && g_conv_mc) ? 1 : 0;
+        cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(p->mc ? g.BN / 2 : g.BN)};
         int rc = tma_encode(&p->tmB, d.w, 2, dims, strides, box, swz);
         if (rc) return rc;
     }
-    p->grid = dim3((unsigned)(g.tiles_x * g.tiles_y * d.b), (unsigned)(d.Cout / g.BN));
-    p->smem = kc == 32 ? ConvCfg<32>::smem_bytes(g.BN) : ConvCfg<8>::smem_bytes(g.BN);
+    const int m_ctas = p->mc ? (g.total_m_tiles + 1) / 2 * 2 : g.total_m_tiles;
+    p->grid = dim3((unsigned)m_ctas, (unsigned)(d.Cout / g.BN));
+    p->smem = ConvCfg<32>::smem_bytes(g.BN);
     p->bias = d.bias;
     p->res = d.res;
     p->out = d.out;
@@ -347,17 +370,30 @@ int conv_launch(const ConvPlan &p, cudaStream_t s)
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(k_conv_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        attr_err = cudaFuncSetAttribute(k_conv_tc<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)ConvCfg<32>::smem_bytes(256));
         if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(k_conv_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)ConvCfg<8>::smem_bytes(256));
+            attr_err = cudaFuncSetAttribute(k_conv_tc<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)ConvCfg<32>::smem_bytes(256));
     });
     PV_CUDA(attr_err);
-    if (p.kc == 32)
-        k_conv_tc<32><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.g, p.bias, p.res, p.out);
-    else
-        k_conv_tc<8><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.g, p.bias, p.res, p.out);
+    if (p.mc) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = p.grid;
+        cfg.blockDim = dim3(CONV_THREADS);
+        cfg.dynamicSmemBytes = p.smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PV_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<32, 1>, p.amaps, p.tmB, p.g, p.bias, p.res, p.out));
+    } else {
+        k_conv_tc<32, 0><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.g, p.bias, p.res, p.out);
+    }
     PV_LAUNCHED("k_conv_tc");
     return PVNET_OK;
 }
@@ -369,6 +405,12 @@ int conv_launch_at(const void *storage, cudaStream_t s) { return conv_launch(*st
 }  // namespace pvnet
 
 extern "C" {
+
+int pvnet_conv_set_multicast(int on)
+{
+    pvnet::g_conv_mc = on ? 1 : 0;
+    return PVNET_OK;
+}
 
 int pvnet_conv2d_nhwc(const float *in, int in_cs, int in_co, int Cin, const float *w_packed, const float *bias,
                       const float *res, int res_cs, int res_co, float *out, int out_cs, int out_co, int Cout, int b,

@@ -127,3 +127,20 @@ def test_conv_column_kernel_4x4_s2d_stem_shape():
     torch.cuda.synchronize()
     err = (out.permute(0, 3, 1, 2).double().cpu() - ref).abs().max().item()
     assert err <= 2e-5 * max(ref.abs().max().item(), 1.0) + 1e-5, err
+
+
+@pytest.mark.parametrize("mc", [True, False], ids=["multicast", "no-multicast"])
+@pytest.mark.parametrize("cfg", [
+    (1, 24, 40, 128, 256, 3, 1, 2, 1, False),   # 9 M tiles: odd -> the last cluster's 2nd CTA duplicates a tile
+    (2, 24, 40, 64, 512, 3, 1, 4, 1, True),     # two N tiles, residual
+    (2, 60, 80, 256, 256, 1, 1, 1, 0, False),   # 1x1, 80 M tiles
+])
+def test_conv_cluster_multicast(cfg, mc):
+    """256-row weight tiles: 2-CTA clusters with TMA multicast vs the plain launch."""
+    pc.set_mode(pc.MODE_PER_TAP)
+    pc.set_multicast(mc)
+    try:
+        _run_case(*cfg)
+    finally:
+        pc.set_multicast(True)
+        pc.set_mode(pc.MODE_AUTO)
