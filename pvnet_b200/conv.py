@@ -22,9 +22,9 @@ def set_mode(mode: int):
     _native.check(_native.lib().pvnet_conv_set_mode(int(mode)), "pvnet_conv_set_mode")
 
 
-def set_multicast(on: bool):
-    """Test hook (pvnet_conv_set_multicast): 2-CTA weight multicast in the per-tap kernel."""
-    _native.check(_native.lib().pvnet_conv_set_multicast(int(bool(on))), "pvnet_conv_set_multicast")
+def set_multicast(mode: int):
+    """Test hook (pvnet_conv_set_multicast): 0 plain, 1 2-CTA weight multicast, 2 cta_group::2 (default)."""
+    _native.check(_native.lib().pvnet_conv_set_multicast(int(mode)), "pvnet_conv_set_multicast")
 
 
 def round_tf32(t: torch.Tensor) -> torch.Tensor:

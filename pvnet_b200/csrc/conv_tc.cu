@@ -72,10 +72,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
               const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out)
 {
     using Cfg = ConvCfg<KC>;
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int STAGES = MC == 2 ? 6 : Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_bytes = g.BN * KC * 4;
+    // MC == 2: this CTA holds only its half (BN/2 rows) of the weight tile
+    const int b_bytes = (MC == 2 ? g.BN / 2 : g.BN) * KC * 4;
     const int stage_bytes = Cfg::A_BYTES + b_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * stage_bytes);
     uint64_t *empty = full + STAGES;
@@ -103,14 +104,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         ptx::prefetch_tensormap(&amaps.m[0]);
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full[s], 1);
-            ptx::mbar_init(&empty[s], MC ? 2 : 1);     // both CTAs of the pair must have consumed the stage
+            ptx::mbar_init(&empty[s], MC == 1 ? 2 : 1);   // MC 1: both CTAs of the pair must have consumed the stage
         }
         ptx::mbar_init(tmem_full, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, tmem_cols);
-        ptx::tmem_relinquish();
+        if (MC == 2) {
+            ptx::tmem_alloc_2sm(tmem_slot, tmem_cols);
+            ptx::tmem_relinquish_2sm();
+        } else {
+            ptx::tmem_alloc(tmem_slot, tmem_cols);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -124,9 +130,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                 const int s = kb % STAGES;
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
                 ptx::mbar_wait(&empty[s], ph ^ 1u);
-                ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
                 const int tap = kb / g.cin_chunks, cc = kb - tap * g.cin_chunks;
                 uint8_t *sa = smem + (size_t)s * stage_bytes;
+                if (MC == 2) {
+                    // both CTAs load their A rows and their half of B; all bytes are counted on the
+                    // leader's barrier, which alone feeds the 2-SM MMA
+                    if (crank == 0) ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * stage_bytes));
+                    ptx::tma_load_4d_2sm(sa, &amaps.m[g.tap_map[tap]], &full[s], cc * KC, x0 + g.tap_ox[tap],
+                                         y0 + g.tap_oy[tap], img);
+                    ptx::tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, &full[s], tap * g.cin_pad + cc * KC,
+                                         n0 + (int)crank * (g.BN / 2));
+                    continue;
+                }
+                ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
                 ptx::tma_load_4d(sa, &amaps.m[g.tap_map[tap]], &full[s], cc * KC, x0 + g.tap_ox[tap],
                                  y0 + g.tap_oy[tap], img);
                 if (MC) {
@@ -139,7 +155,27 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (MC == 2) {
+            if (lane == 0 && crank == 0) {
+                // one 256 x BN x 8 MMA per k-step across the CTA pair
+                const uint32_t idesc = ptx::make_idesc_tf32(256, g.BN);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int s = kb % STAGES;
+                    const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                    ptx::mbar_wait(&full[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t adesc = ptx::make_kmajor_desc(sa, Cfg::SWIZZLE);
+                    const uint64_t bdesc = ptx::make_kmajor_desc(sa + Cfg::A_BYTES, Cfg::SWIZZLE);
+#pragma unroll
+                    for (int k = 0; k < KC / 8; ++k)
+                        ptx::mma_tf32_ss_2sm(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                             (kb | k) != 0 ? 1u : 0u);
+                    ptx::mma_commit_2sm_mc(&empty[s], (uint16_t)0x3);
+                }
+                ptx::mma_commit_2sm_mc(tmem_full, (uint16_t)0x3);
+            }
+        } else if (lane == 0) {
             const uint32_t idesc = ptx::make_idesc_tf32(128, g.BN);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
@@ -214,7 +250,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     if (MC) ptx::cluster_sync();                       // no CTA exits while its peer may still write into it
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, tmem_cols);
+        if (MC == 2) ptx::tmem_dealloc_2sm(tmem_base, tmem_cols);
+        else ptx::tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 
@@ -274,7 +311,9 @@ struct ConvPlan {
     float *out;
 };
 
-int g_conv_mc = 1;   // pairs of CTAs multicast 256-row weight tiles (pvnet_conv_set_multicast)
+// how 256-row weight tiles run: 0 one CTA per tile; 1 CTA pairs, weight tile multicast into both;
+// 2 CTA pairs, one cta_group::2 MMA per k-step, each CTA holds half of the weight tile
+int g_conv_mc = 2;
 int conv_kc(int) { return 32; }   // ragged last channel chunk: TMA zero-fills, weights are zero-padded
 
 int conv_plan(const ConvDesc &d, ConvPlan *p)
@@ -351,14 +390,15 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
         cuuint64_t dims[2] = {(cuuint64_t)g.taps * g.cin_pad, (cuuint64_t)d.Cout};
         cuuint64_t strides[1] = {(cuuint64_t)g.taps * g.cin_pad * 4};
         // pairs of CTAs multicast the weight tile when it is the 256-row one (g_conv_mc: test hook)
-        p->mc = (g.BN == 256 && g_conv_mc) ? 1 : 0;
+        p->mc = g.BN == 256 ? g_conv_mc : 0;
         cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(p->mc ? g.BN / 2 : g.BN)};
         int rc = tma_encode(&p->tmB, d.w, 2, dims, strides, box, swz);
         if (rc) return rc;
     }
     const int m_ctas = p->mc ? (g.total_m_tiles + 1) / 2 * 2 : g.total_m_tiles;
     p->grid = dim3((unsigned)m_ctas, (unsigned)(d.Cout / g.BN));
-    p->smem = ConvCfg<32>::smem_bytes(g.BN);
+    p->smem = p->mc == 2 ? (size_t)(1024 + 6 * (ConvCfg<32>::A_BYTES + 128 * 32 * 4) + 256)
+                         : ConvCfg<32>::smem_bytes(g.BN);
     p->bias = d.bias;
     p->res = d.res;
     p->out = d.out;
@@ -375,6 +415,9 @@ int conv_launch(const ConvPlan &p, cudaStream_t s)
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(k_conv_tc<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)ConvCfg<32>::smem_bytes(256));
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(k_conv_tc<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)ConvCfg<32>::smem_bytes(256));
     });
     PV_CUDA(attr_err);
     if (p.mc) {
@@ -390,7 +433,10 @@ int conv_launch(const ConvPlan &p, cudaStream_t s)
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        PV_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<32, 1>, p.amaps, p.tmB, p.g, p.bias, p.res, p.out));
+        if (p.mc == 2)
+            PV_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<32, 2>, p.amaps, p.tmB, p.g, p.bias, p.res, p.out));
+        else
+            PV_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<32, 1>, p.amaps, p.tmB, p.g, p.bias, p.res, p.out));
     } else {
         k_conv_tc<32, 0><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.g, p.bias, p.res, p.out);
     }
@@ -408,7 +454,7 @@ extern "C" {
 
 int pvnet_conv_set_multicast(int on)
 {
-    pvnet::g_conv_mc = on ? 1 : 0;
+    pvnet::g_conv_mc = on < 0 ? 0 : (on > 2 ? 2 : on);
     return PVNET_OK;
 }
 

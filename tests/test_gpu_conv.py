@@ -129,7 +129,7 @@ def test_conv_column_kernel_4x4_s2d_stem_shape():
     assert err <= 2e-5 * max(ref.abs().max().item(), 1.0) + 1e-5, err
 
 
-@pytest.mark.parametrize("mc", [True, False], ids=["multicast", "no-multicast"])
+@pytest.mark.parametrize("mc", [2, 1, 0], ids=["cta_group2", "multicast", "single-cta"])
 @pytest.mark.parametrize("cfg", [
     (1, 24, 40, 128, 256, 3, 1, 2, 1, False),   # 9 M tiles: odd -> the last cluster's 2nd CTA duplicates a tile
     (2, 24, 40, 64, 512, 3, 1, 4, 1, True),     # two N tiles, residual
@@ -142,5 +142,5 @@ def test_conv_cluster_multicast(cfg, mc):
     try:
         _run_case(*cfg)
     finally:
-        pc.set_multicast(True)
+        pc.set_multicast(2)
         pc.set_mode(pc.MODE_AUTO)
