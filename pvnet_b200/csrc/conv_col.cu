@@ -45,7 +45,7 @@ struct ColGeom {
 template <int KC>
 __host__ __device__ constexpr int col_a_bytes(int dil) { return (COL_TH + 2 * dil) * COL_TW * KC * 4; }
 
-template <int KC, bool HEAD>
+template <int KC, bool HEAD, int KH>
 __global__ void __launch_bounds__(COL_THREADS, 1)
     k_conv_col(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ColGeom g,
                const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out,
@@ -56,9 +56,9 @@ __global__ void __launch_bounds__(COL_THREADS, 1)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_tile = g.BN * ROWB;                    // one [BN][KC] weight tile
-    const int n_btiles = g.KW * g.KH * g.cin_chunks;
-    const int a_bytes = (COL_TH + (g.KH - 1) * g.dil) * COL_TW * ROWB;
-    const int stage_bytes = a_bytes + (g.resident ? 0 : g.KH * b_tile);
+    const int n_btiles = g.KW * KH * g.cin_chunks;
+    const int a_bytes = (COL_TH + (KH - 1) * g.dil) * COL_TW * ROWB;
+    const int stage_bytes = a_bytes + (g.resident ? 0 : KH * b_tile);
     uint8_t *sB = smem;
     uint8_t *sA = smem + (g.resident ? (size_t)n_btiles * b_tile : 0);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sA + (size_t)g.stages * stage_bytes);
@@ -110,63 +110,82 @@ __global__ void __launch_bounds__(COL_THREADS, 1)
                 ptx::mbar_arrive_expect_tx(wfull, (uint32_t)(n_btiles * b_tile));
                 for (int kw = 0; kw < g.KW; ++kw)
                     for (int cc = 0; cc < g.cin_chunks; ++cc)
-                        for (int kh = 0; kh < g.KH; ++kh)
-                            ptx::tma_load_2d(sB + (size_t)((kw * g.cin_chunks + cc) * g.KH + kh) * b_tile, &tmB,
+                        for (int kh = 0; kh < KH; ++kh)
+                            ptx::tma_load_2d(sB + (size_t)((kw * g.cin_chunks + cc) * KH + kh) * b_tile, &tmB,
                                              wfull, (kh * g.KW + kw) * g.cin_pad + cc * KC, 0);
             }
-            uint32_t cnt = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
                 const int img = tile / tiles_per_img;
                 const int trem = tile - img * tiles_per_img;
                 const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
                 const int y0 = tyi * COL_TH, x0 = txi * COL_TW;
                 for (int kw = 0; kw < g.KW; ++kw)
-                    for (int cc = 0; cc < g.cin_chunks; ++cc, ++cnt) {
-                        const int s = cnt % g.stages;
-                        const uint32_t ph = (cnt / g.stages) & 1u;
+                    for (int cc = 0; cc < g.cin_chunks; ++cc) {
                         ptx::mbar_wait(&empty[s], ph ^ 1u);
                         ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
                         uint8_t *st = sA + (size_t)s * stage_bytes;
                         ptx::tma_load_4d(st, &tmA, &full[s], cc * KC, x0 + (kw - g.pad_l) * g.dil,
                                          y0 - g.pad_t * g.dil, img);
                         if (!g.resident)
-                            for (int kh = 0; kh < g.KH; ++kh)
+                            for (int kh = 0; kh < KH; ++kh)
                                 ptx::tma_load_2d(st + a_bytes + (size_t)kh * b_tile, &tmB, &full[s],
                                                  (kh * g.KW + kw) * g.cin_pad + cc * KC, 0);
+                        if (++s == g.stages) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
                     }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // the whole warp runs the loop converged (warp-uniform values stay in uniform registers,
+            // no R2UR per MMA); one elected lane issues
             const uint32_t idesc = ptx::make_idesc_tf32(128, g.BN);
             if (g.resident) ptx::mbar_wait(wfull, 0);
-            uint32_t cnt = 0, it = 0;
+            // The issuing thread is the bottleneck of narrow tiles (hardware floor 40-48 cycles per
+            // N<=64 MMA, benchmarks/micro/mma_rate.cu), so the loop is kept to a handful of
+            // instructions per MMA: descriptors are a constant plus a 16-byte-unit offset, the
+            // (kh, k) nest is fully unrolled, stage/phase are running counters.
+            const uint64_t dbase = ptx::make_kmajor_desc(0, ROWB);
+            const uint32_t a_kh = (uint32_t)(g.dil * COL_TW * ROWB) >> 4;
+            const uint32_t b_kh = (uint32_t)b_tile >> 4;
+            const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB);
+            int s = 0;
+            uint32_t ph = 0, it = 0;
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
                 const uint32_t as = it & 1u;
                 ptx::mbar_wait(&tempty[as], ((it >> 1) & 1u) ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t tacc = tmem_base + as * (uint32_t)g.BN;
-                uint32_t first = 1;
-                for (int kb = 0; kb < kb_per_tile; ++kb, ++cnt) {
-                    const int s = cnt % g.stages;
-                    const uint32_t ph = (cnt / g.stages) & 1u;
+                uint32_t bres = sB_u;
+                for (int kb = 0; kb < kb_per_tile; ++kb) {
                     ptx::mbar_wait(&full[s], ph);
                     ptx::tc_fence_after();
-                    const uint32_t a0 = ptx::smem_u32(sA + (size_t)s * stage_bytes);
-                    const uint32_t b0 = g.resident ? ptx::smem_u32(sB + (size_t)(kb * g.KH) * b_tile) : a0 + a_bytes;
-                    for (int kh = 0; kh < g.KH; ++kh) {
-                        const uint64_t adesc = ptx::make_kmajor_desc(a0 + kh * g.dil * COL_TW * ROWB, ROWB);
-                        const uint64_t bdesc = ptx::make_kmajor_desc(b0 + kh * b_tile, ROWB);
+                    const uint32_t a0 = sA_u + (uint32_t)s * (uint32_t)stage_bytes;
+                    const uint32_t b0 = g.resident ? bres : a0 + (uint32_t)a_bytes;
+                    const uint64_t ad = dbase + (uint64_t)(a0 >> 4);
+                    const uint64_t bd = dbase + (uint64_t)(b0 >> 4);
+                    if (ptx::elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < KC / 8; ++k) {
-                            ptx::mma_tf32_ss(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                             first ? 0u : 1u);
-                            first = 0;
+                        for (int kh = 0; kh < KH; ++kh) {
+#pragma unroll
+                            for (int k = 0; k < KC / 8; ++k)
+                                ptx::mma_tf32_ss(tacc, ad + (uint64_t)(kh * a_kh + 2 * k),
+                                                 bd + (uint64_t)(kh * b_kh + 2 * k), idesc, (kb | kh | k) != 0 ? 1u : 0u);
                         }
+                        ptx::mma_commit(&empty[s]);
                     }
-                    ptx::mma_commit(&empty[s]);
+                    __syncwarp();
+                    bres += (uint32_t)(KH * b_tile);
+                    if (++s == g.stages) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
                 }
-                ptx::mma_commit(&tfull[as]);
+                if (ptx::elect_one()) ptx::mma_commit(&tfull[as]);
+                __syncwarp();
             }
         }
     } else {
@@ -287,10 +306,10 @@ size_t col_smem(int kc, int ksize, int cin_chunks, int bn, int dil, int stages, 
            (size_t)(1 + 2 * stages + 4) * 8 + 16 + (size_t)(head_cout * 33) * 4 + 64;
 }
 
-template <int KC, bool HEAD>
+template <int KC, bool HEAD, int KH>
 cudaError_t set_attr()
 {
-    return cudaFuncSetAttribute(k_conv_col<KC, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    return cudaFuncSetAttribute(k_conv_col<KC, HEAD, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
 }
 
 }  // namespace
@@ -301,6 +320,7 @@ bool conv_col_eligible(const ConvDesc &d)
     if ((d.ksize != 3 && d.ksize != 4) || d.stride != 1 || d.Cout > 64 || d.Cout % 32 != 0) return false;
     const int kc = col_kc(d.Cin);
     if (d.Cin % kc != 0) return false;
+    if ((d.ksize == 4) != (kc == 16)) return false;   // instantiated: 4x4 taps with 16 channels, 3x3 otherwise
     return col_smem(kc, d.ksize, (d.Cin + kc - 1) / kc, d.Cout, d.dilation, 3, HEAD_MAX, false) <= SMEM_LIMIT;
 }
 
@@ -400,23 +420,23 @@ int conv_col_launch_at(const void *storage, cudaStream_t s)
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = set_attr<32, false>();
-        if (attr_err == cudaSuccess) attr_err = set_attr<16, false>();
-        if (attr_err == cudaSuccess) attr_err = set_attr<8, false>();
-        if (attr_err == cudaSuccess) attr_err = set_attr<32, true>();
-        if (attr_err == cudaSuccess) attr_err = set_attr<8, true>();
+        attr_err = set_attr<32, false, 3>();
+        if (attr_err == cudaSuccess) attr_err = set_attr<16, false, 4>();
+        if (attr_err == cudaSuccess) attr_err = set_attr<8, false, 3>();
+        if (attr_err == cudaSuccess) attr_err = set_attr<32, true, 3>();
+        if (attr_err == cudaSuccess) attr_err = set_attr<8, true, 3>();
     });
     PV_CUDA(attr_err);
     const HeadDesc &h = p.hd;
-#define COL_LAUNCH(KC_, HEAD_)                                                                                    \
-    k_conv_col<KC_, HEAD_><<<p.grid, COL_THREADS, p.smem, s>>>(p.tmA, p.tmB, p.g, p.bias, p.res, p.out,           \
+#define COL_LAUNCH(KC_, HEAD_, KH_)                                                                               \
+    k_conv_col<KC_, HEAD_, KH_><<<p.grid, COL_THREADS, p.smem, s>>>(p.tmA, p.tmB, p.g, p.bias, p.res, p.out,           \
                                                                 p.head ? h.w : nullptr, p.head ? h.bias : nullptr, \
                                                                 p.head ? h.out_nchw : nullptr, p.head ? h.mask : nullptr)
-    if (p.kc == 32 && !p.head) COL_LAUNCH(32, false);
-    else if (p.kc == 16 && !p.head) COL_LAUNCH(16, false);
-    else if (p.kc == 8 && !p.head) COL_LAUNCH(8, false);
-    else if (p.kc == 32) COL_LAUNCH(32, true);
-    else COL_LAUNCH(8, true);
+    if (p.kc == 32 && !p.head) COL_LAUNCH(32, false, 3);
+    else if (p.kc == 16 && !p.head) COL_LAUNCH(16, false, 4);
+    else if (p.kc == 8 && !p.head) COL_LAUNCH(8, false, 3);
+    else if (p.kc == 32) COL_LAUNCH(32, true, 3);
+    else COL_LAUNCH(8, true, 3);
 #undef COL_LAUNCH
     PV_LAUNCHED("k_conv_col");
     return PVNET_OK;

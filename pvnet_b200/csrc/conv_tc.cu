@@ -126,11 +126,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 
     if (warp == 0) {
         if (lane == 0) {
+            int s = 0, tap = 0, cc = 0;
+            uint32_t ph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
                 ptx::mbar_wait(&empty[s], ph ^ 1u);
-                const int tap = kb / g.cin_chunks, cc = kb - tap * g.cin_chunks;
                 uint8_t *sa = smem + (size_t)s * stage_bytes;
                 if (MC == 2) {
                     // both CTAs load their A rows and their half of B; all bytes are counted on the
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                                          y0 + g.tap_oy[tap], img);
                     ptx::tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, &full[s], tap * g.cin_pad + cc * KC,
                                          n0 + (int)crank * (g.BN / 2));
-                    continue;
+                    goto advance;
                 }
                 ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
                 ptx::tma_load_4d(sa, &amaps.m[g.tap_map[tap]], &full[s], cc * KC, x0 + g.tap_ox[tap],
@@ -152,47 +151,57 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                 } else {
                     ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], tap * g.cin_pad + cc * KC, n0);
                 }
+            advance:
+                if (++cc == g.cin_chunks) {
+                    cc = 0;
+                    ++tap;
+                }
+                if (++s == STAGES) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
         }
     } else if (warp == 1) {
-        if (MC == 2) {
-            if (lane == 0 && crank == 0) {
-                // one 256 x BN x 8 MMA per k-step across the CTA pair
-                const uint32_t idesc = ptx::make_idesc_tf32(256, g.BN);
-                for (int kb = 0; kb < nkb; ++kb) {
-                    const int s = kb % STAGES;
-                    const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                    ptx::mbar_wait(&full[s], ph);
-                    ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint64_t adesc = ptx::make_kmajor_desc(sa, Cfg::SWIZZLE);
-                    const uint64_t bdesc = ptx::make_kmajor_desc(sa + Cfg::A_BYTES, Cfg::SWIZZLE);
-#pragma unroll
-                    for (int k = 0; k < KC / 8; ++k)
-                        ptx::mma_tf32_ss_2sm(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                             (kb | k) != 0 ? 1u : 0u);
-                    ptx::mma_commit_2sm_mc(&empty[s], (uint16_t)0x3);
-                }
-                ptx::mma_commit_2sm_mc(tmem_full, (uint16_t)0x3);
-            }
-        } else if (lane == 0) {
-            const uint32_t idesc = ptx::make_idesc_tf32(128, g.BN);
+        // The whole warp runs the loop converged (warp-uniform values stay in uniform registers);
+        // one elected lane issues the MMAs and commits.
+        if (MC != 2 || crank == 0) {
+            const uint32_t idesc = ptx::make_idesc_tf32(MC == 2 ? 256 : 128, g.BN);
+            const uint64_t dbase = ptx::make_kmajor_desc(0, Cfg::SWIZZLE);
+            const uint32_t smem_u = ptx::smem_u32(smem);
+            int s = 0;
+            uint32_t ph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
-                const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t adesc = ptx::make_kmajor_desc(sa, Cfg::SWIZZLE);
-                const uint64_t bdesc = ptx::make_kmajor_desc(sa + Cfg::A_BYTES, Cfg::SWIZZLE);
+                const uint32_t sa = smem_u + (uint32_t)s * (uint32_t)stage_bytes;
+                const uint64_t adesc = dbase + (uint64_t)(sa >> 4);
+                const uint64_t bdesc = dbase + (uint64_t)((sa + Cfg::A_BYTES) >> 4);
+                if (ptx::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < KC / 8; ++k)   // 8 tf32 = 32 B per MMA along K: +2 in 16-byte units
-                    ptx::mma_tf32_ss(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                     (kb | k) != 0 ? 1u : 0u);
-                if (MC) ptx::mma_commit_mc(&empty[s], (uint16_t)0x3);
-                else ptx::mma_commit(&empty[s]);
+                    for (int k = 0; k < KC / 8; ++k) {   // 8 tf32 = 32 B per MMA along K: +2 in 16-byte units
+                        if (MC == 2)
+                            ptx::mma_tf32_ss_2sm(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                                 (kb | k) != 0 ? 1u : 0u);
+                        else
+                            ptx::mma_tf32_ss(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                             (kb | k) != 0 ? 1u : 0u);
+                    }
+                    if (MC == 2) ptx::mma_commit_2sm_mc(&empty[s], (uint16_t)0x3);
+                    else if (MC == 1) ptx::mma_commit_mc(&empty[s], (uint16_t)0x3);
+                    else ptx::mma_commit(&empty[s]);
+                }
+                __syncwarp();
+                if (++s == STAGES) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
-            ptx::mma_commit(tmem_full);
+            if (ptx::elect_one()) {
+                if (MC == 2) ptx::mma_commit_2sm_mc(tmem_full, (uint16_t)0x3);
+                else ptx::mma_commit(tmem_full);
+            }
+            __syncwarp();
         }
     } else {
         // TMEM lane quarter a warp may touch is (warp id % 4)
