@@ -121,34 +121,35 @@ int launch_pack_image(const float *in, float *out, int b, int H, int W, int out_
 // channel (py*2+px)*3+c, 4 zero channels, for the tensor-core stem (a 7x7 stride-2 conv is a
 // 4x4 stride-1 conv on S), and (b) the image slice of the convraw.0 input buffer (3 channels +
 // 5 zeros at out_co).  Values rounded to tf32.
-__global__ void k_s2d_pack(const float *__restrict__ in, float *__restrict__ s2d, float *__restrict__ out, int H, int W,
-                           long long total /* b*H/2*W/2 */, int out_cs, int out_co)
+__global__ void __launch_bounds__(128)
+    k_s2d_pack(const float *__restrict__ in, float *__restrict__ s2d, float *__restrict__ out, int H, int W, int out_cs,
+               int out_co)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int W2 = W / 2, H2 = H / 2;
-    const int x2 = (int)(i % W2);
-    long long r = i / W2;
-    const int y2 = (int)(r % H2);
-    const long long n = r / H2;
-    const long long plane = (long long)H * W;
-    const float *src = in + n * 3 * plane + (long long)(2 * y2) * W + 2 * x2;
+    // grid.y = image * H/2 + half-resolution row; threads over half-resolution columns
+    const int W2 = W >> 1, H2 = H >> 1;
+    const int x2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x2 >= W2) return;
+    const int n = blockIdx.y / H2, y2 = blockIdx.y - n * H2;
+    const size_t plane = (size_t)H * W;
+    const float *src = in + (size_t)n * 3 * plane + (size_t)(2 * y2) * W + 2 * x2;
     float v[16];
 #pragma unroll
-    for (int py = 0; py < 2; ++py)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int px = 0; px < 2; ++px)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) v[(py * 2 + px) * 3 + c] = ptx::round_tf32(src[c * plane + py * W + px]);
+        for (int py = 0; py < 2; ++py) {
+            const float2 t = __ldg(reinterpret_cast<const float2 *>(src + c * plane + py * W));
+            v[(py * 2 + 0) * 3 + c] = ptx::round_tf32(t.x);
+            v[(py * 2 + 1) * 3 + c] = ptx::round_tf32(t.y);
+        }
     v[12] = v[13] = v[14] = v[15] = 0.f;
-    float4 *so = reinterpret_cast<float4 *>(s2d + i * 16);
+    float4 *so = reinterpret_cast<float4 *>(s2d + ((size_t)blockIdx.y * W2 + x2) * 16);
 #pragma unroll
     for (int j = 0; j < 4; ++j) so[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 #pragma unroll
     for (int py = 0; py < 2; ++py)
 #pragma unroll
         for (int px = 0; px < 2; ++px) {
-            const long long pix = n * plane + (long long)(2 * y2 + py) * W + (2 * x2 + px);
+            const size_t pix = (size_t)n * plane + (size_t)(2 * y2 + py) * W + (2 * x2 + px);
             float4 *o = reinterpret_cast<float4 *>(out + pix * out_cs + out_co);
             const int b = (py * 2 + px) * 3;
             o[0] = make_float4(v[b], v[b + 1], v[b + 2], 0.f);
@@ -159,26 +160,23 @@ __global__ void k_s2d_pack(const float *__restrict__ in, float *__restrict__ s2d
 int launch_s2d_pack(const float *in, float *s2d, float *out, int b, int H, int W, int out_cs, int out_co,
                     cudaStream_t s)
 {
-    const long long total = (long long)b * (H / 2) * (W / 2);
-    k_s2d_pack<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, s2d, out, H, W, total, out_cs, out_co);
+    dim3 grid((unsigned)((W / 2 + 127) / 128), (unsigned)(b * (H / 2)));
+    k_s2d_pack<<<grid, 128, 0, s>>>(in, s2d, out, H, W, out_cs, out_co);
     PV_LAUNCHED("k_s2d_pack");
     return PVNET_OK;
 }
 
 // ------------------------------------------------------------------ max-pool 3x3/2 pad 1
 // (resnet.py:142,204).  in NHWC [b,H,W,in_cs] at in_co (C channels) -> out [b,H/2,W/2,C]
-__global__ void k_maxpool(const float *__restrict__ in, float *__restrict__ out, int H, int W, int C, int in_cs,
-                          int in_co, long long total /* b*Ho*Wo*C/4 */)
+__global__ void __launch_bounds__(256)
+    k_maxpool(const float *__restrict__ in, float *__restrict__ out, int H, int W, int C, int in_cs, int in_co)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int c4 = C / 4, Ho = H / 2, Wo = W / 2;
-    const int cg = (int)(i % c4);
-    long long r = i / c4;
-    const int ox = (int)(r % Wo);
-    r /= Wo;
-    const int oy = (int)(r % Ho);
-    const int n = (int)(r / Ho);
+    // grid.y = image * H/2 + output row
+    const int c4 = C >> 2, Ho = H >> 1, Wo = W >> 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Wo * c4) return;
+    const int ox = i / c4, cg = i - ox * c4;
+    const int n = blockIdx.y / Ho, oy = blockIdx.y - n * Ho;
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
@@ -195,13 +193,13 @@ __global__ void k_maxpool(const float *__restrict__ in, float *__restrict__ out,
             m.w = fmaxf(m.w, v.w);
         }
     }
-    reinterpret_cast<float4 *>(out)[i] = m;
+    reinterpret_cast<float4 *>(out)[((size_t)blockIdx.y * Wo + ox) * c4 + cg] = m;
 }
 
 int launch_maxpool(const float *in, float *out, int b, int H, int W, int C, int in_cs, int in_co, cudaStream_t s)
 {
-    const long long total = (long long)b * (H / 2) * (W / 2) * (C / 4);
-    k_maxpool<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, H, W, C, in_cs, in_co, total);
+    dim3 grid((unsigned)(((W / 2) * (C / 4) + 255) / 256), (unsigned)(b * (H / 2)));
+    k_maxpool<<<grid, 256, 0, s>>>(in, out, H, W, C, in_cs, in_co);
     PV_LAUNCHED("k_maxpool");
     return PVNET_OK;
 }
@@ -211,38 +209,36 @@ int launch_maxpool(const float *in, float *out, int b, int H, int W, int C, int 
 // as ATen's upsample_bilinear2d: scale=(in-1)/(out-1) in fp32, src=scale*dst, i0=(int)src,
 // l1=src-i0, l0=1-l1, out = h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11).
 // in NHWC [b,h,w,C] dense -> out NHWC [b,2h,2w,out_cs] at out_co; values rounded to tf32.
-__global__ void k_upsample2x(const float *__restrict__ in, float *__restrict__ out, int h, int w, int C, int out_cs,
-                             int out_co, float sy, float sx, long long total /* b*2h*2w*C/4 */)
+__global__ void __launch_bounds__(256)
+    k_upsample2x(const float *__restrict__ in, float *__restrict__ out, int h, int w, int C, int out_cs, int out_co,
+                 float sy, float sx)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int c4 = C / 4, Ho = 2 * h, Wo = 2 * w;
-    const int cg = (int)(i % c4);
-    long long r = i / c4;
-    const int ox = (int)(r % Wo);
-    r /= Wo;
-    const int oy = (int)(r % Ho);
-    const int n = (int)(r / Ho);
+    // grid.y = image * 2h + output row; threads cover (output column, 4-channel group) of that row
+    const int c4 = C >> 2, Ho = 2 * h, Wo = 2 * w;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Wo * c4) return;
+    const int ox = i / c4, cg = i - ox * c4;
+    const int n = blockIdx.y / Ho, oy = blockIdx.y - n * Ho;
     const float fy = sy * (float)oy, fx = sx * (float)ox;
     const int y0 = (int)fy, x0 = (int)fx;
     const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
     const float h1 = fy - (float)y0, h0 = 1.f - h1, w1 = fx - (float)x0, w0 = 1.f - w1;
     const float4 *base = reinterpret_cast<const float4 *>(in) + (size_t)n * h * w * c4 + cg;
-    const float4 v00 = __ldg(base + ((size_t)y0 * w + x0) * c4), v01 = __ldg(base + ((size_t)y0 * w + x1) * c4);
-    const float4 v10 = __ldg(base + ((size_t)y1 * w + x0) * c4), v11 = __ldg(base + ((size_t)y1 * w + x1) * c4);
+    const float4 v00 = __ldg(base + (y0 * w + x0) * c4), v01 = __ldg(base + (y0 * w + x1) * c4);
+    const float4 v10 = __ldg(base + (y1 * w + x0) * c4), v11 = __ldg(base + (y1 * w + x1) * c4);
     float4 o;
     o.x = ptx::round_tf32(h0 * (w0 * v00.x + w1 * v01.x) + h1 * (w0 * v10.x + w1 * v11.x));
     o.y = ptx::round_tf32(h0 * (w0 * v00.y + w1 * v01.y) + h1 * (w0 * v10.y + w1 * v11.y));
     o.z = ptx::round_tf32(h0 * (w0 * v00.z + w1 * v01.z) + h1 * (w0 * v10.z + w1 * v11.z));
     o.w = ptx::round_tf32(h0 * (w0 * v00.w + w1 * v01.w) + h1 * (w0 * v10.w + w1 * v11.w));
-    *reinterpret_cast<float4 *>(out + (((size_t)n * Ho + oy) * Wo + ox) * out_cs + out_co + cg * 4) = o;
+    *reinterpret_cast<float4 *>(out + ((size_t)blockIdx.y * Wo + ox) * out_cs + out_co + cg * 4) = o;
 }
 
 int launch_upsample2x(const float *in, float *out, int b, int h, int w, int C, int out_cs, int out_co, cudaStream_t s)
 {
-    const long long total = (long long)b * (2 * h) * (2 * w) * (C / 4);
     const float sy = (float)(h - 1) / (float)(2 * h - 1), sx = (float)(w - 1) / (float)(2 * w - 1);
-    k_upsample2x<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, h, w, C, out_cs, out_co, sy, sx, total);
+    dim3 grid((unsigned)((2 * w * (C / 4) + 255) / 256), (unsigned)(b * 2 * h));
+    k_upsample2x<<<grid, 256, 0, s>>>(in, out, h, w, C, out_cs, out_co, sy, sx);
     PV_LAUNCHED("k_upsample2x");
     return PVNET_OK;
 }

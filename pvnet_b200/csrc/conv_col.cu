@@ -16,6 +16,7 @@
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <new>
 
@@ -366,7 +367,11 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     bool resident = true;
     while (stages > 2 && col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, true) > SMEM_LIMIT)
         --stages;
-    if (stages < 3 || col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, true) > SMEM_LIMIT) {
+    static const int min_res_stages = [] {
+        const char *e = getenv("PVNET_COL_RESIDENT_MIN_STAGES");   // tuning knob, default 3
+        return e ? atoi(e) : 3;
+    }();
+    if (stages < min_res_stages || col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, true) > SMEM_LIMIT) {
         resident = false;
         stages = 8;
         while (stages > 2 &&
