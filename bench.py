@@ -319,21 +319,19 @@ def main():
         ms_total = e0.elapsed_time(e1)
         clocks = None
 
-        # ---------------- end to end from pinned host buffers
-        kp_host = torch.empty([BATCH, K_KP, 2]).pin_memory()
-        xin = torch.empty_like(xs[0])
+        # ---------------- end to end from pinned host buffers (public API: PoseKeypointPipeline)
+        from pvnet_b200.pipeline import PoseKeypointPipeline
+        pipe = PoseKeypointPipeline(net, round_hyp_num=HYP, inlier_thresh=THRESH, rng="batched")
+        kp_hosts = [torch.empty([BATCH, K_KP, 2]).pin_memory() for _ in range(args.steps)]
 
-        def e2e_step(i):
-            xin.copy_(hosts[i % 3], non_blocking=True)
-            kp = full_step(xin)
-            kp_host.copy_(kp, non_blocking=True)
-        for i in range(3):
-            e2e_step(i)
+        def gather_hook(i, kp):
+            if world > 1:
+                pd.gather_results(kp, BATCH * world)
+        pipe.run([hosts[i % 3] for i in range(3)], out_host=kp_hosts[:3], on_result=gather_hook)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for i in range(args.steps):
-            e2e_step(i)
+        pipe.run([hosts[i % 3] for i in range(args.steps)], out_host=kp_hosts, on_result=gather_hook)
         f1.record()
         barrier()
         ms_e2e = f0.elapsed_time(f1)

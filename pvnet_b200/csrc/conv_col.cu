@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(COL_THREADS, 1)
     uint64_t *tfull = empty + g.stages;               // [2]
     uint64_t *tempty = tfull + 2;                     // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
-    float *s_head = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // [head_cout*33]
+    float *s_bias = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // [64]
+    float *s_head = s_bias + 64;                                                                              // [head_cout*33]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t tmem_cols = 32;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(COL_THREADS, 1)
         ptx::tmem_alloc(tmem_slot, tmem_cols);
         ptx::tmem_relinquish();
     }
+    for (int i = threadIdx.x; i < g.BN; i += COL_THREADS) s_bias[i] = bias[i];
     if (HEAD) {
         for (int i = threadIdx.x; i < g.head_cout * 32; i += COL_THREADS) s_head[i] = head_w[i];
         for (int i = threadIdx.x; i < g.head_cout; i += COL_THREADS) s_head[g.head_cout * 32 + i] = head_b[i];
@@ -217,7 +219,13 @@ __global__ void __launch_bounds__(COL_THREADS, 1)
                 }
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(bias + c0 + j);
+                for (int j = 0; j < 8; ++j) {      // bias from shared memory: 8 broadcast LDS.128 instead of 32 LDG
+                    const float4 bv = reinterpret_cast<const float4 *>(s_bias + c0)[j];
+                    v[4 * j] = __uint_as_float(r[4 * j]) + bv.x;
+                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bv.y;
+                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bv.z;
+                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bv.w;
+                }
                 if (res != nullptr && valid) {
                     const float4 *rp = reinterpret_cast<const float4 *>(res + pix * g.res_cs + g.res_co + c0);
 #pragma unroll
@@ -242,21 +250,34 @@ __global__ void __launch_bounds__(COL_THREADS, 1)
                         float *o = head_out + (size_t)img * g.head_cout * npix + (size_t)y * g.Wo + x;
                         float best = -INFINITY;
                         int best_c = 0;
-                        for (int co = 0; co < g.head_cout; ++co) {
-                            const float4 *wr = reinterpret_cast<const float4 *>(s_head + co * 32);
-                            float acc = s_head[g.head_cout * 32 + co];
+                        // four output channels at a time: independent FMA chains (the 32-term dot
+                        // product is a dependent chain of 4-cycle FMAs)
+                        for (int co = 0; co < g.head_cout; co += 4) {
+                            float acc[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                acc[u] = (co + u < g.head_cout) ? s_head[g.head_cout * 32 + co + u] : 0.f;
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float4 w4 = wr[j];
-                                acc = fmaf(v[4 * j], w4.x, acc);
-                                acc = fmaf(v[4 * j + 1], w4.y, acc);
-                                acc = fmaf(v[4 * j + 2], w4.z, acc);
-                                acc = fmaf(v[4 * j + 3], w4.w, acc);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const int cu = (co + u < g.head_cout) ? co + u : co;
+                                    const float4 w4 = reinterpret_cast<const float4 *>(s_head + cu * 32)[j];
+                                    acc[u] = fmaf(v[4 * j], w4.x, acc[u]);
+                                    acc[u] = fmaf(v[4 * j + 1], w4.y, acc[u]);
+                                    acc[u] = fmaf(v[4 * j + 2], w4.z, acc[u]);
+                                    acc[u] = fmaf(v[4 * j + 3], w4.w, acc[u]);
+                                }
                             }
-                            o[(size_t)co * npix] = acc;
-                            if (co < g.head_seg && acc > best) {
-                                best = acc;
-                                best_c = co;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (co + u < g.head_cout) {
+                                    o[(size_t)(co + u) * npix] = acc[u];
+                                    if (co + u < g.head_seg && acc[u] > best) {
+                                        best = acc[u];
+                                        best_c = co + u;
+                                    }
+                                }
                             }
                         }
                         if (mask) {
@@ -304,7 +325,7 @@ size_t col_smem(int kc, int ksize, int cin_chunks, int bn, int dil, int stages, 
     const size_t a = (size_t)(COL_TH + (ksize - 1) * dil) * COL_TW * rowb, bt = (size_t)bn * rowb;
     return 1024 + (resident ? (size_t)ksize * ksize * cin_chunks * bt : 0) +
            (size_t)stages * (a + (resident ? 0 : (size_t)ksize * bt)) +
-           (size_t)(1 + 2 * stages + 4) * 8 + 16 + (size_t)(head_cout * 33) * 4 + 64;
+           (size_t)(1 + 2 * stages + 4) * 8 + 16 + (size_t)(64 + head_cout * 33) * 4 + 64;
 }
 
 template <int KC, bool HEAD, int KH>
