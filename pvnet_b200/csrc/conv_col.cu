@@ -47,7 +47,7 @@ template <int KC>
 __host__ __device__ constexpr int col_a_bytes(int dil) { return (COL_TH + 2 * dil) * COL_TW * KC * 4; }
 
 template <int KC, bool HEAD, int KH>
-__global__ void __launch_bounds__(COL_THREADS, 1)
+__global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTAs per SM when shared memory allows
     k_conv_col(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ColGeom g,
                const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out,
                const float *__restrict__ head_w, const float *__restrict__ head_b, float *__restrict__ head_out,
