@@ -184,6 +184,7 @@ def cpu_vote_baseline(seconds_budget=15.0):
     sample = images of 20000 foreground px, K=9, 256 hypotheses."""
     from oracle import pvnet_oracle as po
     from pvnet_b200 import synthetic as syn
+    po.set_num_threads(os.cpu_count() or 1)
     mask = syn.disc_mask(TARGET_FG)
     field = syn.planted_field(mask, K_KP, 1)[0]
     vertex = syn.as_reference_view(field[None])
@@ -213,6 +214,9 @@ def run_reference_arm(args):
     from oracle import pvnet_oracle as po
     from pvnet_b200 import synthetic as syn
     from pvnet_b200.model_repository import Resnet18_8s
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)          # torchrun exports OMP_NUM_THREADS=1; this arm may use every host core
+    po.set_num_threads(ncpu)
     torch.manual_seed(0)
     net = Resnet18_8s(2 * K_KP, 2).eval()
     x = torch.from_numpy(syn.backbone_input(1, 0))
