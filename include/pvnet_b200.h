@@ -175,6 +175,9 @@ PVNET_API int pvnet_conv_set_mode(int mode);
  * 1 = 2-CTA clusters with TMA multicast of the weight tile; 2 (default) = 2-CTA clusters issuing
  * tcgen05.mma.cta_group::2 (each CTA holds half of the weight tile). */
 PVNET_API int pvnet_conv_set_multicast(int on);
+/* Test hook: 1 (default) runs single-CTA tiles of the per-tap kernel on its persistent variant
+ * (continuous TMA ring, two TMEM accumulator stages); 0 = one tile per CTA. */
+PVNET_API int pvnet_conv_set_persistent(int on);
 
 /* Resnet18_8s.forward (lib/networks/model_repository.py:64-80), eval mode, whole batch.
  *

@@ -24,6 +24,7 @@
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <new>
 
@@ -277,6 +278,190 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     }
 }
 
+// ------------------------------------------------------------------ persistent per-tap kernel
+// Same tile math as k_conv_tc<KC,0>, but each CTA walks a static round-robin list of
+// (M tile, N tile) items with a continuous TMA ring and TWO TMEM accumulator stages, so the
+// prologue (barrier init, TMEM allocation, first TMA round trip) is paid once per CTA and the
+// epilogue of item i overlaps the MMAs of item i+1.  For the short-K layers (layer2, 1x1
+// downsamples, conv8s/conv4s) the per-tile prologue + epilogue of the one-tile-per-CTA kernel
+// cost as much as the MMAs themselves.
+template <int KC>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+    k_conv_tap_p(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap tmB, const ConvGeom g,
+                 const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out)
+{
+    using Cfg = ConvCfg<KC>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_bytes = g.BN * KC * 4;
+    const int stage_bytes = Cfg::A_BYTES + b_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * stage_bytes);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tfull = empty + STAGES;      // [2]
+    uint64_t *tempty = tfull + 2;          // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = g.tiles_x * g.tiles_y;
+    const int n_tiles_n = g.Cout / g.BN;
+    const int n_items = g.total_m_tiles * n_tiles_n;
+    const int nkb = g.taps * g.cin_chunks;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(2 * g.BN)) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmB);
+        ptx::prefetch_tensormap(&amaps.m[0]);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull[s], 1);
+            ptx::mbar_init(&tempty[s], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int n_tile = item % n_tiles_n, m_tile = item / n_tiles_n;   // N tile fastest
+                const int img = m_tile / tiles_per_img;
+                const int trem = m_tile - img * tiles_per_img;
+                const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
+                const int y0 = tyi * g.TH, x0 = txi * g.TW, n0 = n_tile * g.BN;
+                for (int tap = 0; tap < g.taps; ++tap)
+                    for (int cc = 0; cc < g.cin_chunks; ++cc) {
+                        ptx::mbar_wait(&empty[s], ph ^ 1u);
+                        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+                        uint8_t *sa = smem + (size_t)s * stage_bytes;
+                        ptx::tma_load_4d(sa, &amaps.m[g.tap_map[tap]], &full[s], cc * KC, x0 + g.tap_ox[tap],
+                                         y0 + g.tap_oy[tap], img);
+                        ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], tap * g.cin_pad + cc * KC, n0);
+                        if (++s == STAGES) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = ptx::make_idesc_tf32(128, g.BN);
+        const uint64_t dbase = ptx::make_kmajor_desc(0, Cfg::SWIZZLE);
+        const uint32_t smem_u = ptx::smem_u32(smem);
+        int s = 0;
+        uint32_t ph = 0, it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t as = it & 1u;
+            ptx::mbar_wait(&tempty[as], ((it >> 1) & 1u) ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t tacc = tmem_base + as * (uint32_t)g.BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+                ptx::mbar_wait(&full[s], ph);
+                ptx::tc_fence_after();
+                const uint32_t sa = smem_u + (uint32_t)s * (uint32_t)stage_bytes;
+                const uint64_t adesc = dbase + (uint64_t)(sa >> 4);
+                const uint64_t bdesc = dbase + (uint64_t)((sa + Cfg::A_BYTES) >> 4);
+                if (ptx::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < KC / 8; ++k)
+                        ptx::mma_tf32_ss(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                         (kb | k) != 0 ? 1u : 0u);
+                    ptx::mma_commit(&empty[s]);
+                }
+                __syncwarp();
+                if (++s == STAGES) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+            if (ptx::elect_one()) ptx::mma_commit(&tfull[as]);
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int ty = m / g.TW, tx = m - ty * g.TW;
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t as = it & 1u;
+            const int n_tile = item % n_tiles_n, m_tile = item / n_tiles_n;
+            const int img = m_tile / tiles_per_img;
+            const int trem = m_tile - img * tiles_per_img;
+            const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
+            const int y = tyi * g.TH + ty, x = txi * g.TW + tx, n0 = n_tile * g.BN;
+            const bool valid = (y < g.Ho) && (x < g.Wo);
+            const size_t pix = ((size_t)img * g.Ho + y) * g.Wo + x;
+            float *optr = out + pix * g.out_cs + g.out_co + n0;
+            const float *rptr = res ? res + pix * g.res_cs + g.res_co + n0 : nullptr;
+            ptx::mbar_wait(&tfull[as], (it >> 1) & 1u);
+            ptx::tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)g.BN;
+            for (int c0 = 0; c0 < g.BN; c0 += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(tacc + (uint32_t)c0, r);
+                ptx::tmem_ld_wait();
+                if (c0 + 32 >= g.BN) {      // everything is in registers: give the TMEM stage back
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n0 + c0 + j));
+                        float4 v = make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
+                                               __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w);
+                        if (rptr) {
+                            const float4 rv = __ldg(reinterpret_cast<const float4 *>(rptr + c0 + j));
+                            v.x += rv.x;
+                            v.y += rv.y;
+                            v.z += rv.z;
+                            v.w += rv.w;
+                        }
+                        if (g.act == 1) {
+                            v.x = fmaxf(v.x, 0.f);
+                            v.y = fmaxf(v.y, 0.f);
+                            v.z = fmaxf(v.z, 0.f);
+                            v.w = fmaxf(v.w, 0.f);
+                        } else if (g.act == 2) {
+                            v.x = v.x > 0.f ? v.x : 0.1f * v.x;
+                            v.y = v.y > 0.f ? v.y : 0.1f * v.y;
+                            v.z = v.z > 0.f ? v.z : 0.1f * v.z;
+                            v.w = v.w > 0.f ? v.w : 0.1f * v.w;
+                        }
+                        if (g.round_out) {
+                            v.x = ptx::round_tf32(v.x);
+                            v.y = ptx::round_tf32(v.y);
+                            v.z = ptx::round_tf32(v.z);
+                            v.w = ptx::round_tf32(v.w);
+                        }
+                        *reinterpret_cast<float4 *>(optr + c0 + j) = v;
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -326,7 +511,7 @@ struct ConvPlan {
     AMaps amaps;
     CUtensorMap tmB;
     ConvGeom g;
-    int kc, mc;
+    int kc, mc, persist;
     dim3 grid;
     size_t smem;
     const float *bias, *res;
@@ -336,6 +521,7 @@ struct ConvPlan {
 // how 256-row weight tiles run: 0 one CTA per tile; 1 CTA pairs, weight tile multicast into both;
 // 2 CTA pairs, one cta_group::2 MMA per k-step, each CTA holds half of the weight tile
 int g_conv_mc = 2;
+int g_conv_persist = 1;   // single-CTA tiles use the persistent kernel (pvnet_conv_set_persistent)
 int conv_kc(int) { return 32; }   // ragged last channel chunk: TMA zero-fills, weights are zero-padded
 
 int conv_plan(const ConvDesc &d, ConvPlan *p)
@@ -412,7 +598,11 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
         cuuint64_t dims[2] = {(cuuint64_t)g.taps * g.cin_pad, (cuuint64_t)d.Cout};
         cuuint64_t strides[1] = {(cuuint64_t)g.taps * g.cin_pad * 4};
         // pairs of CTAs multicast the weight tile when it is the 256-row one (g_conv_mc: test hook)
-        p->mc = g.BN == 256 ? g_conv_mc : 0;
+        static const int env_mc = [] {
+            const char *e = getenv("PVNET_CONV_MC");       // tuning knob: overrides the default cluster mode
+            return e ? atoi(e) : -1;
+        }();
+        p->mc = g.BN == 256 ? (env_mc >= 0 ? env_mc : g_conv_mc) : 0;
         cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(p->mc ? g.BN / 2 : g.BN)};
         int rc = tma_encode(&p->tmB, d.w, 2, dims, strides, box, swz);
         if (rc) return rc;
@@ -421,6 +611,18 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
     p->grid = dim3((unsigned)(m_ctas * (d.Cout / g.BN)));
     p->smem = p->mc == 2 ? (size_t)(1024 + 6 * (ConvCfg<32>::A_BYTES + 128 * 32 * 4) + 256)
                          : ConvCfg<32>::smem_bytes(g.BN);
+    // single-CTA tiles run on the persistent kernel: grid = resident CTAs
+    p->persist = (p->mc == 0 && g_conv_persist) ? 1 : 0;
+    if (p->persist) {
+        int per_sm = (int)((227 * 1024) / p->smem);
+        if (per_sm > 2) per_sm = 2;
+        if (per_sm * 2 * g.BN > 512) per_sm = 512 / (2 * g.BN);      // TMEM: two accumulator stages per CTA
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (long long)sm_count() * per_sm;
+        const long long items = (long long)g.total_m_tiles * (d.Cout / g.BN);
+        if (grid > items) grid = items;
+        p->grid = dim3((unsigned)grid);
+    }
     p->bias = d.bias;
     p->res = d.res;
     p->out = d.out;
@@ -439,6 +641,9 @@ int conv_launch(const ConvPlan &p, cudaStream_t s)
                                             (int)ConvCfg<32>::smem_bytes(256));
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(k_conv_tc<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)ConvCfg<32>::smem_bytes(256));
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(k_conv_tap_p<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)ConvCfg<32>::smem_bytes(256));
     });
     PV_CUDA(attr_err);
@@ -459,6 +664,8 @@ int conv_launch(const ConvPlan &p, cudaStream_t s)
             PV_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<32, 2>, p.amaps, p.tmB, p.g, p.bias, p.res, p.out));
         else
             PV_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<32, 1>, p.amaps, p.tmB, p.g, p.bias, p.res, p.out));
+    } else if (p.persist) {
+        k_conv_tap_p<32><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.g, p.bias, p.res, p.out);
     } else {
         k_conv_tc<32, 0><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.g, p.bias, p.res, p.out);
     }
@@ -473,6 +680,12 @@ int conv_launch_at(const void *storage, cudaStream_t s) { return conv_launch(*st
 }  // namespace pvnet
 
 extern "C" {
+
+int pvnet_conv_set_persistent(int on)
+{
+    pvnet::g_conv_persist = on ? 1 : 0;
+    return PVNET_OK;
+}
 
 int pvnet_conv_set_multicast(int on)
 {

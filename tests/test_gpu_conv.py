@@ -66,11 +66,26 @@ def _run_case(b, H, W, cin, cout, k, stride, dil, act, with_res, in_extra=0, out
     (1, 40, 48, 40, 32, 3, 1, 1, 2, False),     # Cin=40 -> 8-channel K-blocks (convraw.0), LeakyReLU
     (1, 60, 80, 384, 128, 3, 1, 1, 2, False),   # conv8s shape
 ])
-def test_conv_vs_torch(cfg):
+@pytest.mark.parametrize("persistent", [True, False], ids=["persistent", "tile-per-cta"])
+def test_conv_vs_torch(cfg, persistent):
     pc.set_mode(pc.MODE_PER_TAP)
+    pc.set_persistent(persistent)
     try:
         _run_case(*cfg)
     finally:
+        pc.set_persistent(True)
+        pc.set_mode(pc.MODE_AUTO)
+
+
+def test_conv_persistent_many_items_per_cta():
+    """More (M tile, N tile) items than resident CTAs: TMEM ping-pong and the continuous ring."""
+    pc.set_mode(pc.MODE_PER_TAP)
+    pc.set_multicast(0)
+    try:
+        _run_case(4, 120, 160, 64, 128, 3, 1, 1, 1, True, seed=11)     # 600 items, 1 CTA/SM
+        _run_case(2, 60, 80, 128, 512, 1, 1, 1, 0, False, seed=12)     # two N tiles per M tile, BN=256 (TMEM 512)
+    finally:
+        pc.set_multicast(2)
         pc.set_mode(pc.MODE_AUTO)
 
 
