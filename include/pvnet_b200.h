@@ -171,8 +171,8 @@ PVNET_API int pvnet_conv2d_nhwc(const float *in, int in_cs, int in_co, int Cin,
  * Cout <= 64 whose weights fit in shared memory, per-tap kernel otherwise), 1 = per-tap kernel
  * only, 2 = column kernel (error if the layer is not eligible). */
 PVNET_API int pvnet_conv_set_mode(int mode);
-/* Test hook: how the per-tap kernel runs 256-channel weight tiles.  0 = one CTA per tile;
- * 1 = 2-CTA clusters with TMA multicast of the weight tile; 2 (default) = 2-CTA clusters issuing
+/* Test hook: how the per-tap kernel runs 256-channel weight tiles.  0 (default) = single CTAs;
+ * 1 = 2-CTA clusters with TMA multicast of the weight tile; 2 = 2-CTA clusters issuing
  * tcgen05.mma.cta_group::2 (each CTA holds half of the weight tile). */
 PVNET_API int pvnet_conv_set_multicast(int on);
 /* Test hook: 1 (default) runs single-CTA tiles of the per-tap kernel on its persistent variant

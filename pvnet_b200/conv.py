@@ -23,7 +23,7 @@ def set_mode(mode: int):
 
 
 def set_multicast(mode: int):
-    """Test hook (pvnet_conv_set_multicast): 0 plain, 1 2-CTA weight multicast, 2 cta_group::2 (default)."""
+    """Test hook (pvnet_conv_set_multicast): 0 single CTA (default), 1 2-CTA weight multicast, 2 cta_group::2."""
     _native.check(_native.lib().pvnet_conv_set_multicast(int(mode)), "pvnet_conv_set_multicast")
 
 

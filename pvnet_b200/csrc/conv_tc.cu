@@ -518,9 +518,10 @@ struct ConvPlan {
     float *out;
 };
 
-// how 256-row weight tiles run: 0 one CTA per tile; 1 CTA pairs, weight tile multicast into both;
+// how 256-row weight tiles run: 0 single CTA (persistent kernel; default: measured 5.68 ms per
+// backbone step against 6.21 ms with mode 2); 1 CTA pairs, weight tile multicast into both;
 // 2 CTA pairs, one cta_group::2 MMA per k-step, each CTA holds half of the weight tile
-int g_conv_mc = 2;
+int g_conv_mc = 0;
 int g_conv_persist = 1;   // single-CTA tiles use the persistent kernel (pvnet_conv_set_persistent)
 int conv_kc(int) { return 32; }   // ragged last channel chunk: TMA zero-fills, weights are zero-padded
 

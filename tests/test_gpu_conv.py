@@ -85,7 +85,7 @@ def test_conv_persistent_many_items_per_cta():
         _run_case(4, 120, 160, 64, 128, 3, 1, 1, 1, True, seed=11)     # 600 items, 1 CTA/SM
         _run_case(2, 60, 80, 128, 512, 1, 1, 1, 0, False, seed=12)     # two N tiles per M tile, BN=256 (TMEM 512)
     finally:
-        pc.set_multicast(2)
+        pc.set_multicast(0)
         pc.set_mode(pc.MODE_AUTO)
 
 
@@ -157,5 +157,5 @@ def test_conv_cluster_multicast(cfg, mc):
     try:
         _run_case(*cfg)
     finally:
-        pc.set_multicast(2)
+        pc.set_multicast(0)
         pc.set_mode(pc.MODE_AUTO)
