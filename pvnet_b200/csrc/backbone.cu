@@ -125,7 +125,7 @@ int build_plans(pvnet_backbone *m, const Buffers &B, int b, int h, int w)
         const bool col = g_conv_mode != 1 && conv_col_eligible(d);
         m->use_col[slot] = col;
         if (!col) return conv_plan_at(d, st);
-        if (slot == CV_CONVRAW0 && m->raw == 32) {
+        if (slot == CV_CONVRAW0 && m->raw == 32 && m->seg_dim + m->ver_dim <= 32) {
             // fuse convraw.3 + argmax into the epilogue; pointers are patched per forward call
             HeadDesc hd{m->w[CV_HEAD], m->bias[CV_HEAD], reinterpret_cast<float *>(0x10), nullptr, 8, m->seg_dim,
                         m->seg_dim + m->ver_dim};

@@ -48,7 +48,8 @@ __host__ __device__ constexpr int col_a_bytes(int dil) { return (COL_TH + 2 * di
 
 template <int KC, bool HEAD, int KH>
 __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTAs per SM when shared memory allows
-    k_conv_col(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ColGeom g,
+    k_conv_col(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmH, const ColGeom g,
                const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out,
                const float *__restrict__ head_w, const float *__restrict__ head_b, float *__restrict__ head_out,
                void *__restrict__ mask)
@@ -62,19 +63,24 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
     const int stage_bytes = a_bytes + (g.resident ? 0 : KH * b_tile);
     uint8_t *sB = smem;
     uint8_t *sA = smem + (g.resident ? (size_t)n_btiles * b_tile : 0);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + (size_t)g.stages * stage_bytes);
+    uint8_t *sHB = sA + (size_t)g.stages * stage_bytes;            // head weights [32][32] (HEAD only), 4 KB
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sHB + (HEAD ? 4096 : 0));
     uint64_t *wfull = bars;
     uint64_t *full = bars + 1;
     uint64_t *empty = full + g.stages;
     uint64_t *tfull = empty + g.stages;               // [2]
     uint64_t *tempty = tfull + 2;                     // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint64_t *a2full = tempty + 2;                    // [2] HEAD: activated tile written back to TMEM
+    uint64_t *d2full = a2full + 2;                    // [2] HEAD: 1x1 head MMAs done
+    uint64_t *hfull = d2full + 2;                     // HEAD: head weights landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(hfull + 1);
     float *s_bias = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));  // [64]
     float *s_head = s_bias + 64;                                                                              // [head_cout*33]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(2 * g.BN)) tmem_cols <<= 1;
+    if (HEAD) tmem_cols = 256;      // acc[2] | A2[2] | D2[2], 32 columns each
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -87,7 +93,10 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tfull[s], 1);
             ptx::mbar_init(&tempty[s], 4);             // one arrive per epilogue warp
+            ptx::mbar_init(&a2full[s], 4);
+            ptx::mbar_init(&d2full[s], 1);
         }
+        ptx::mbar_init(hfull, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -95,10 +104,8 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
         ptx::tmem_relinquish();
     }
     for (int i = threadIdx.x; i < g.BN; i += COL_THREADS) s_bias[i] = bias[i];
-    if (HEAD) {
-        for (int i = threadIdx.x; i < g.head_cout * 32; i += COL_THREADS) s_head[i] = head_w[i];
-        for (int i = threadIdx.x; i < g.head_cout; i += COL_THREADS) s_head[g.head_cout * 32 + i] = head_b[i];
-    }
+    if (HEAD)
+        for (int i = threadIdx.x; i < g.head_cout; i += COL_THREADS) s_head[i] = head_b[i];
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -108,6 +115,10 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
 
     if (warp == 0) {
         if (lane == 0) {
+            if (HEAD) {      // convraw.3 weights [cout][32] -> K-major 32x32 tile (rows >= cout zero-filled)
+                ptx::mbar_arrive_expect_tx(hfull, 4096u);
+                ptx::tma_load_2d(sHB, &tmH, hfull, 0, 0);
+            }
             // all weights, once: tile t = ((kw*cin_chunks + cc)*KH + kh) <- packed [Cout][kh][kw][cin]
             if (g.resident) {
                 ptx::mbar_arrive_expect_tx(wfull, (uint32_t)(n_btiles * b_tile));
@@ -152,6 +163,7 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
             // instructions per MMA: descriptors are a constant plus a 16-byte-unit offset, the
             // (kh, k) nest is fully unrolled, stage/phase are running counters.
             const uint64_t dbase = ptx::make_kmajor_desc(0, ROWB);
+            const uint32_t hidesc = ptx::make_idesc_tf32(128, 32);
             const uint32_t a_kh = (uint32_t)(g.dil * COL_TW * ROWB) >> 4;
             const uint32_t b_kh = (uint32_t)b_tile >> 4;
             const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB);
@@ -188,6 +200,38 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
                     }
                 }
                 if (ptx::elect_one()) ptx::mma_commit(&tfull[as]);
+                __syncwarp();
+                if (HEAD && it > 0) {
+                    // 1x1 head of the PREVIOUS tile: D2 = leaky(acc) [TMEM, written back by the epilogue
+                    // warps] x Whead^T [smem]; issued after this tile's MMAs so the tensor pipe never waits
+                    const uint32_t hs = (it - 1) & 1u;
+                    if (it == 1) ptx::mbar_wait(hfull, 0);
+                    ptx::mbar_wait(&a2full[hs], ((it - 1) >> 1) & 1u);
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
+                        const uint64_t hd = dbase + (uint64_t)(ptx::smem_u32(sHB) >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ptx::mma_tf32_ts(tmem_base + 128u + hs * 32u, tmem_base + 64u + hs * 32u + 8u * k,
+                                             hd + (uint64_t)(2 * k), hidesc, k != 0 ? 1u : 0u);
+                        ptx::mma_commit(&d2full[hs]);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (HEAD && it > 0) {    // head of the last tile
+                const uint32_t hs = (it - 1) & 1u;
+                if (it == 1) ptx::mbar_wait(hfull, 0);
+                ptx::mbar_wait(&a2full[hs], ((it - 1) >> 1) & 1u);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint64_t hd = dbase + (uint64_t)(ptx::smem_u32(sHB) >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::mma_tf32_ts(tmem_base + 128u + hs * 32u, tmem_base + 64u + hs * 32u + 8u * k,
+                                         hd + (uint64_t)(2 * k), hidesc, k != 0 ? 1u : 0u);
+                    ptx::mma_commit(&d2full[hs]);
+                }
                 __syncwarp();
             }
         }
@@ -244,39 +288,35 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
                     if (g.round_out) v[j] = ptx::round_tf32(v[j]);
                 }
                 if (HEAD) {
-                    // convraw.3 (model_repository.py:57) + torch.argmax over the seg channels
+                    // convraw.3 (model_repository.py:57) on the tensor cores: the activated tile goes
+                    // back to TMEM as the A operand of a 128x32x32 MMA issued by the MMA warp, then
+                    // bias + torch.argmax over the seg channels + NCHW stores happen here.
+                    uint32_t a2[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) a2[j] = __float_as_uint(ptx::round_tf32(v[j]));
+                    ptx::tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + 64u + as * 32u, a2);
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&a2full[as]);
+                    ptx::mbar_wait(&d2full[as], (it >> 1) & 1u);
+                    ptx::tc_fence_after();
+                    uint32_t d2[32];
+                    ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + 128u + as * 32u, d2);
+                    ptx::tmem_ld_wait();
                     if (valid) {
                         const size_t npix = (size_t)g.Ho * g.Wo;
                         float *o = head_out + (size_t)img * g.head_cout * npix + (size_t)y * g.Wo + x;
                         float best = -INFINITY;
                         int best_c = 0;
-                        // four output channels at a time: independent FMA chains (the 32-term dot
-                        // product is a dependent chain of 4-cycle FMAs)
-                        for (int co = 0; co < g.head_cout; co += 4) {
-                            float acc[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                acc[u] = (co + u < g.head_cout) ? s_head[g.head_cout * 32 + co + u] : 0.f;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const int cu = (co + u < g.head_cout) ? co + u : co;
-                                    const float4 w4 = reinterpret_cast<const float4 *>(s_head + cu * 32)[j];
-                                    acc[u] = fmaf(v[4 * j], w4.x, acc[u]);
-                                    acc[u] = fmaf(v[4 * j + 1], w4.y, acc[u]);
-                                    acc[u] = fmaf(v[4 * j + 2], w4.z, acc[u]);
-                                    acc[u] = fmaf(v[4 * j + 3], w4.w, acc[u]);
-                                }
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                if (co + u < g.head_cout) {
-                                    o[(size_t)(co + u) * npix] = acc[u];
-                                    if (co + u < g.head_seg && acc[u] > best) {
-                                        best = acc[u];
-                                        best_c = co + u;
-                                    }
+                        for (int co = 0; co < 32; ++co) {
+                            if (co < g.head_cout) {
+                                const float val = __uint_as_float(d2[co]) + s_head[co];
+                                o[(size_t)co * npix] = val;
+                                if (co < g.head_seg && val > best) {
+                                    best = val;
+                                    best_c = co;
                                 }
                             }
                         }
@@ -302,7 +342,7 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
 }
 
 struct ColPlan {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmH;
     ColGeom g;
     int kc, head;
     unsigned grid;
@@ -325,7 +365,7 @@ size_t col_smem(int kc, int ksize, int cin_chunks, int bn, int dil, int stages, 
     const size_t a = (size_t)(COL_TH + (ksize - 1) * dil) * COL_TW * rowb, bt = (size_t)bn * rowb;
     return 1024 + (resident ? (size_t)ksize * ksize * cin_chunks * bt : 0) +
            (size_t)stages * (a + (resident ? 0 : (size_t)ksize * bt)) +
-           (size_t)(1 + 2 * stages + 4) * 8 + 16 + (size_t)(64 + head_cout * 33) * 4 + 64;
+           (size_t)(1 + 2 * stages + 4 + 5) * 8 + 16 + (size_t)(64 + 64) * 4 + 64 + (head_cout ? 4096 : 0);
 }
 
 template <int KC, bool HEAD, int KH>
@@ -356,7 +396,7 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     PV_CHECK_ARG(d.in_cs % 4 == 0 && d.in_co % 4 == 0 && d.out_cs % 4 == 0 && d.out_co % 4 == 0,
                  "conv(col): channel strides/offsets must be multiples of 4 floats");
     PV_CHECK_ARG(!d.res || (d.res_cs % 4 == 0 && d.res_co % 4 == 0), "conv(col): residual stride/offset alignment");
-    PV_CHECK_ARG(!head || (d.Cout == 32 && col_kc(d.Cin) != 16 && head->cout >= 1 && head->cout <= HEAD_MAX && head->w && head->bias &&
+    PV_CHECK_ARG(!head || (d.Cout == 32 && col_kc(d.Cin) != 16 && head->cout >= 1 && head->cout <= 32 && head->w && head->bias &&
                            head->out_nchw && (!head->mask || head->mask_esz == 1 || head->mask_esz == 8)),
                  "conv(col): bad fused-head description");
     const int kc = col_kc(d.Cin);
@@ -421,6 +461,16 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
         int rc = tma_encode(&p->tmB, d.w, 2, dims, strides, box, kc * 4);
         if (rc) return rc;
     }
+    if (head) {      // convraw.3 weights [cout][32] fp32, read as a 32x32 K-major tile (rows beyond cout: zero fill)
+        PV_CHECK_ARG((uintptr_t)head->w % 16 == 0, "conv(col): head weights must be 16-byte aligned");
+        cuuint64_t dims[2] = {32, (cuuint64_t)head->cout};
+        cuuint64_t strides[1] = {128};
+        cuuint32_t box[2] = {32, 32};
+        int rc = tma_encode(&p->tmH, head->w, 2, dims, strides, box, 128);
+        if (rc) return rc;
+    } else {
+        p->tmH = p->tmB;
+    }
     const int per_sm = (int)(SMEM_LIMIT / p->smem) >= 2 ? 2 : 1;
     long long grid = (long long)sm_count() * per_sm;
     if (grid > g.total_tiles) grid = g.total_tiles;
@@ -455,7 +505,7 @@ int conv_col_launch_at(const void *storage, cudaStream_t s)
     PV_CUDA(attr_err);
     const HeadDesc &h = p.hd;
 #define COL_LAUNCH(KC_, HEAD_, KH_)                                                                               \
-    k_conv_col<KC_, HEAD_, KH_><<<p.grid, COL_THREADS, p.smem, s>>>(p.tmA, p.tmB, p.g, p.bias, p.res, p.out,           \
+    k_conv_col<KC_, HEAD_, KH_><<<p.grid, COL_THREADS, p.smem, s>>>(p.tmA, p.tmB, p.tmH, p.g, p.bias, p.res, p.out,           \
                                                                 p.head ? h.w : nullptr, p.head ? h.bias : nullptr, \
                                                                 p.head ? h.out_nchw : nullptr, p.head ? h.mask : nullptr)
     if (p.kc == 32 && !p.head) COL_LAUNCH(32, false, 3);

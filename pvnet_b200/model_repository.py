@@ -120,7 +120,7 @@ class Resnet18_8s(nn.Module):
                 if slot == 0:                         # stem: fp32 [tap][cin][cout]
                     packed = w.permute(2, 3, 1, 0).reshape(49, 3, 64).contiguous()
                 elif conv_name == "convraw.3":        # head: fp32 [cout][32]
-                    packed = w.reshape(w.shape[0], w.shape[1]).contiguous()
+                    packed = pc.round_tf32(w.reshape(w.shape[0], w.shape[1]))   # fused path feeds it to a tf32 MMA
                 elif conv_name == "convraw.0":        # cat[fm(s2dim), image(3)] -> s2dim+8 input channels
                     packed = pc.pack_weight(w, cin_pad=pc.cin_padded(s2dim + 8))
                 else:
