@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
                     ptx::mbar_wait(&a2full[hs], ((it - 1) >> 1) & 1u);
                     ptx::tc_fence_after();
                     if (ptx::elect_one()) {
-                        const uint64_t hd = dbase + (uint64_t)(ptx::smem_u32(sHB) >> 4);
+                        const uint64_t hd = ptx::make_kmajor_desc(ptx::smem_u32(sHB), 128);   // head tile: 128-byte rows whatever KC is
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             ptx::mma_tf32_ts(tmem_base + 128u + hs * 32u, tmem_base + 64u + hs * 32u + 8u * k,
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
                 ptx::mbar_wait(&a2full[hs], ((it - 1) >> 1) & 1u);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
-                    const uint64_t hd = dbase + (uint64_t)(ptx::smem_u32(sHB) >> 4);
+                    const uint64_t hd = ptx::make_kmajor_desc(ptx::smem_u32(sHB), 128);   // head tile: 128-byte rows whatever KC is
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         ptx::mma_tf32_ts(tmem_base + 128u + hs * 32u, tmem_base + 64u + hs * 32u + 8u * k,
