@@ -33,6 +33,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -415,6 +416,170 @@ __global__ void __launch_bounds__(VT_THREADS, 3)
     }
 }
 
+// ------------------------------------------------------------------ the vote, packed FP32x2
+// Same decomposition and the same guard-band argument as k_vote, but the arithmetic of two
+// hypotheses rides in one FFMA2/FADD2/FMUL2 (sm_100 packed fp32): the scalar version is bound by
+// the FMA pipe (36 FP32 instructions per 4 tests).  Tiles store each pixel pre-duplicated,
+// {x,x,y,y} and {ux,ux,uy,uy}, so the packed operands come straight out of two LDS.128.
+// The sign of num is tested separately (e = num^2 - T^2 d2 here), see DESIGN.md.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float a, float b)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+constexpr int VP_TILE = 1024;     // pixels per tile, 32 B each
+
+__global__ void __launch_bounds__(VT_THREADS, 3)
+    k_vote_packed(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
+                  const int *__restrict__ tn_arr, int npx, int nb, int vn, int hn, int wh,
+                  const float2 *__restrict__ hyp, int *__restrict__ counts, float thresh, float t2, float band)
+{
+    __shared__ float4 tile[2 * VP_TILE];
+    __shared__ int red[VT_WARPS * 32 * VT_HPL];
+    __shared__ int tile_prefix[VT_MAX_B + 1];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        int acc = 0;
+        for (int i = 0; i < nb; ++i) {
+            tile_prefix[i] = acc;
+            acc += (tn_arr[i] + VP_TILE - 1) / VP_TILE;
+        }
+        tile_prefix[nb] = acc;
+    }
+    __syncthreads();
+    const int total_tiles = tile_prefix[nb];
+    const int HC = wh * 32 * VT_HPL;
+    const int hcn = (hn + HC - 1) / HC;
+    const long long n_items = (long long)total_tiles * vn * hcn;
+    const int wp_count = VT_WARPS / wh;
+    const int my_wh = warp % wh, my_wp = warp / wh;
+    const f32x2 nt2 = pk(-t2, -t2), band2 = pk(band, band), c2 = pk(4e-12f, 4e-12f);
+
+    for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int hc = (int)(it % hcn);
+        const long long r = it / hcn;
+        const int k = (int)(r % vn);
+        const int g = (int)(r / vn);
+        int lo = 0, hi = nb;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (tile_prefix[mid] <= g) lo = mid; else hi = mid;
+        }
+        const int b = lo;
+        const int tn = tn_arr[b];
+        const int t0 = (g - tile_prefix[b]) * VP_TILE;
+        const int len = min(VP_TILE, tn - t0);
+        const long long vbase = (long long)b * st.s[0] + (long long)k * st.s[3];
+
+        for (int i = tid; i < len; i += VT_THREADS) {
+            const unsigned p = __ldg(pix + (size_t)b * npx + t0 + i);
+            const int x = p & 0xffff, y = p >> 16;
+            const long long off = vbase + y * st.s[1] + x * st.s[2];
+            const float nx = __ldg(vertex + off), ny = __ldg(vertex + off + st.s[4]);
+            const float n2 = fmaf(nx, nx, ny * ny);
+            const float rinv = rsqrtf(n2);
+            float ux = nx * rinv, uy = ny * rinv;
+            if (!(n2 > 1e-11f && n2 < 1e30f)) ux = uy = __int_as_float(0x7fc00000);
+            tile[2 * i] = make_float4((float)x, (float)x, (float)y, (float)y);
+            tile[2 * i + 1] = make_float4(ux, ux, uy, uy);
+        }
+        for (int i = tid; i < HC; i += VT_THREADS) red[i] = 0;
+        __syncthreads();
+
+        const int hbase = hc * HC + my_wh * (32 * VT_HPL);
+        float hx[VT_HPL], hy[VT_HPL];
+        int cnt[VT_HPL];
+#pragma unroll
+        for (int j = 0; j < VT_HPL; ++j) {
+            const int h = hbase + j * 32 + lane;
+            float2 hp = make_float2(3.0e8f, 3.0e8f);
+            if (h < hn) hp = __ldg(hyp + ((size_t)b * vn + k) * hn + h);
+            hx[j] = hp.x;
+            hy[j] = hp.y;
+            cnt[j] = 0;
+        }
+        f32x2 hx2[VT_HPL / 2], hy2[VT_HPL / 2];
+#pragma unroll
+        for (int j = 0; j < VT_HPL / 2; ++j) {
+            hx2[j] = pk(hx[2 * j], hx[2 * j + 1]);
+            hy2[j] = pk(hy[2 * j], hy[2 * j + 1]);
+        }
+        const ulonglong2 *tile2 = reinterpret_cast<const ulonglong2 *>(tile);
+
+#pragma unroll 2
+        for (int i = my_wp; i < len; i += wp_count) {
+            const ulonglong2 pc = tile2[2 * i];        // {x,x} {y,y}
+            const ulonglong2 pu = tile2[2 * i + 1];    // {ux,ux} {uy,uy}
+            unsigned unc = 0;
+#pragma unroll
+            for (int j = 0; j < VT_HPL / 2; ++j) {
+                const f32x2 dx = sub2(hx2[j], pc.x), dy = sub2(hy2[j], pc.y);
+                const f32x2 d2 = fma2(dx, dx, mul2(dy, dy));
+                const f32x2 num = fma2(dx, pu.x, mul2(dy, pu.y));
+                const f32x2 e = fma2(nt2, d2, mul2(num, num));
+                const f32x2 bd = fma2(band2, d2, c2);
+                float e0, e1, b0, b1, n0, n1;
+                upk(e, e0, e1);
+                upk(bd, b0, b1);
+                upk(num, n0, n1);
+                cnt[2 * j] += (e0 > b0 && n0 > 0.f) ? 1 : 0;
+                cnt[2 * j + 1] += (e1 > b1 && n1 > 0.f) ? 1 : 0;
+                unc |= (fabsf(e0) > b0) ? 0u : (1u << (2 * j));
+                unc |= (fabsf(e1) > b1) ? 0u : (2u << (2 * j));
+            }
+            if (__any_sync(0xffffffffu, unc != 0)) {
+                if (unc) {
+                    float px, py, dummy;
+                    upk(pc.x, px, dummy);
+                    upk(pc.y, py, dummy);
+                    const long long off = vbase + (long long)py * st.s[1] + (long long)px * st.s[2];
+                    const float nx = __ldg(vertex + off), ny = __ldg(vertex + off + st.s[4]);
+#pragma unroll
+                    for (int j = 0; j < VT_HPL; ++j)
+                        if (unc & (1u << j)) cnt[j] += exact_inlier(nx, ny, px, py, hx[j], hy[j], thresh) ? 1 : 0;
+                }
+            }
+        }
+
+#pragma unroll
+        for (int j = 0; j < VT_HPL; ++j)
+            if (cnt[j]) atomicAdd(&red[my_wh * (32 * VT_HPL) + j * 32 + lane], cnt[j]);
+        __syncthreads();
+        for (int i = tid; i < HC; i += VT_THREADS) {
+            const int h = hc * HC + i;
+            const int v = red[i];
+            if (h < hn && v) atomicAdd(counts + ((size_t)b * vn + k) * hn + h, v);
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ argmax + refit
 __device__ __forceinline__ double warp_sum_d(double v)
 {
@@ -757,6 +922,19 @@ int launch_hyp_and_vote(const float *vertex, const Strides &st, const int32_t *i
     // thresh <= 0 (or NaN) has no squared form: NaN makes every test take the exact path
     const float t2 = (thresh > 0.f && thresh < 1e18f) ? thresh * thresh : nanf("");
     const float band = GUARD_EPS * (thresh > 0.f ? thresh * thresh : 1.f);
+    static const int packed = [] {
+        const char *e = getenv("PVNET_VOTE_PACKED");     // tuning knob: 0 = scalar FP32 kernel
+        return e ? atoi(e) : 1;
+    }();
+    if (packed) {
+        const long long max_items_p = (long long)b * ((npx + VP_TILE - 1) / VP_TILE) * vn * ((hn + HC - 1) / HC);
+        long long grid_p = (long long)pvnet::sm_count() * 3;
+        if (grid_p > max_items_p) grid_p = max_items_p;
+        k_vote_packed<<<(unsigned)grid_p, VT_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, npx, b, vn, hn, wh, ws.hyp,
+                                                             ws.counts, thresh, t2, band);
+        PV_LAUNCHED("k_vote_packed");
+        return PVNET_OK;
+    }
     k_vote<<<(unsigned)grid, VT_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, npx, b, vn, hn, wh, ws.hyp, ws.counts,
                                                  thresh, t2, band);
     PV_LAUNCHED("k_vote");
