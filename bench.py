@@ -129,6 +129,16 @@ def make_step(torch, net):
 
 
 # ----------------------------------------------------------------------------- roofline
+def _ncu_traffic():
+    """DRAM bytes (read+write) of the conv launches of one step from the committed ncu --set full
+    capture (profiles/r01_conv_dram_traffic.json); not measurable live without the profiler."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_dram_traffic.json")))
+        return {"dram_bytes_per_step": d["bytes_per_step"], "source": d["source"]}
+    except Exception:
+        return None
+
+
 def conv_roofline(torch, net, x, peaks):
     """Per-stage device time of one forward pass, CUDA events recorded on the launch stream
     between the single-kernel stages; aggregates the tcgen05 convolution launches."""
@@ -174,7 +184,7 @@ def conv_roofline(torch, net, x, peaks):
         "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tcgen05 tf32 = half the bf16 rate)"
                         if "bf16_tflops_sustained" in peaks else "fallback 1590/2"),
         "algorithmic_gflop_per_launch_set": round(flops / 1e9, 1), "conv_ms_per_step": round(conv_ms, 3),
-        "backbone_ms_per_step": round(float(ms.sum()), 3), "traffic": None,
+        "backbone_ms_per_step": round(float(ms.sum()), 3), "traffic": _ncu_traffic(),
     }, stages
 
 
