@@ -18,6 +18,7 @@
  *   lib/ransac_voting_gpu_layer/src/ransac_voting.cpp:41-55,104   voting_for_hypothesis
  *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:514-598      ransac_voting_layer_v3
  *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:333-406      estimate_voting_distribution_with_mean
+ *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:763-858      ransac_voting_layer_v5
  *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:983-1034     generate_hypothesis (python level)
  *   lib/networks/model_repository.py:64-80                        Resnet18_8s.forward
  * INTEGRATION.md shows the ctypes binding the reference's Python wrapper uses.
@@ -101,6 +102,18 @@ PVNET_API int pvnet_ransac_voting_v3(const void *mask, int mask_elem_size,
                                      float inlier_thresh, int min_num, int max_num,
                                      float *out_pts, int32_t *out_counts, float *out_hyp, int32_t *out_tn,
                                      void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
+
+/* ransac_voting_layer_v5 (ransac_voting_gpu.py:763-858): v3 plus a per-keypoint confidence
+ * out_conf [b,vn] = (inliers of the refitted point at conf_thresh, 0.999 in the reference :850)
+ * / tn; zeros for skipped images (:788-793).  Same arguments as pvnet_ransac_voting_v3 otherwise. */
+PVNET_API int pvnet_ransac_voting_v5(const void *mask, int mask_elem_size,
+                                     const float *vertex, const int64_t vertex_strides[5],
+                                     const int32_t *idxs, const float *selection,
+                                     int b, int h, int w, int vn, int hn,
+                                     float inlier_thresh, float conf_thresh, int min_num, int max_num,
+                                     float *out_pts, float *out_conf, int32_t *out_counts, float *out_hyp,
+                                     int32_t *out_tn, void *workspace, size_t workspace_bytes,
+                                     pvnet_stream_t stream);
 
 /* estimate_voting_distribution_with_mean (ransac_voting_gpu.py:333-406).
  *

@@ -4,4 +4,5 @@ from pvnet_b200.ransac_voting_gpu import (  # noqa: F401
     estimate_voting_distribution_with_mean,
     generate_hypothesis,
     ransac_voting_layer_v3,
+    ransac_voting_layer_v5,
 )

@@ -10,6 +10,7 @@ functions compute (paths relative to /root/reference):
 
   ransac_voting_layer_v3                    lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:514-598
   estimate_voting_distribution_with_mean    lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:333-406
+  ransac_voting_layer_v5                    lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:763-858
   generate_hypothesis (python, per batch)   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:983-1034
   b_inv (2x2 inverse via LU)                lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:503-512
   the two CUDA kernels                      lib/ransac_voting_gpu_layer/src/ransac_voting_kernel.cu:11-49, 88-126
@@ -217,6 +218,21 @@ def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, con
         debug.append(dict(tn=tn, coords=coords, direct=direct, hyp=hyp, counts=counts,
                           win_idx=win_idx, win_pts=all_win_pts, refit_inliers=inl))
     return (out, debug) if return_debug else out
+
+
+def ransac_voting_layer_v5(mask, vertex, round_hyp_num, inlier_thresh=0.999, min_num=5, max_num=100, idxs=None,
+                           selection=None):
+    """ransac_voting_gpu.py:763-858: v3 plus confidence = inliers of the refitted point at
+    threshold 0.999 (:850), divided by tn (:851); zeros for skipped images (:788-793)."""
+    kp, dbg = ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=inlier_thresh, min_num=min_num,
+                                     max_num=max_num, idxs=idxs, selection=selection, return_debug=True)
+    conf = np.zeros(kp.shape[:2], np.float32)
+    for bi, d in enumerate(dbg):
+        if d is None:
+            continue
+        cnt = vote_counts(d["direct"], d["coords"], kp[bi][None], 0.999)[0]
+        conf[bi] = cnt.astype(np.float32) / np.float32(d["tn"])
+    return kp, conf
 
 
 def generate_hypothesis(mask, vertex, round_hyp_num, inlier_thresh=0.999, min_num=5, max_num=30000,

@@ -688,6 +688,41 @@ __global__ void k_refit_final(const double *__restrict__ part, const int *__rest
     out_pts[bk * 2 + 1] = py;
 }
 
+// ransac_voting_layer_v5's confidence (ransac_voting_gpu.py:850-852): inliers of the REFITTED
+// point at a fixed threshold, divided by the pixel count.  grid (RF_CHUNKS, b*vn), integer atomics.
+__global__ void __launch_bounds__(RF_THREADS)
+    k_conf_count(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
+                 const int *__restrict__ tn_arr, int npx, int vn, const float *__restrict__ pts, float thresh,
+                 int *__restrict__ conf_cnt)
+{
+    __shared__ int scratch[96];
+    const int rc = blockIdx.x, bk = blockIdx.y, b = bk / vn, k = bk - b * vn;
+    const int tn = tn_arr[b];
+    if (tn == 0) return;
+    const float hx = pts[bk * 2], hy = pts[bk * 2 + 1];
+    const int per = (tn + RF_CHUNKS - 1) / RF_CHUNKS;
+    const int lo = rc * per, hi = min(tn, lo + per);
+    const long long vbase = (long long)b * st.s[0] + (long long)k * st.s[3];
+    int c = 0, z0 = 0, z1 = 0;
+    for (int t = lo + threadIdx.x; t < hi; t += RF_THREADS) {
+        const unsigned p = pix[(size_t)b * npx + t];
+        const int x = p & 0xffff, y = p >> 16;
+        const long long off = vbase + y * st.s[1] + x * st.s[2];
+        c += exact_inlier(vertex[off], vertex[off + st.s[4]], (float)x, (float)y, hx, hy, thresh) ? 1 : 0;
+    }
+    block_sum3(c, z0, z1, scratch);
+    if (threadIdx.x == 0 && c) atomicAdd(conf_cnt + bk, c);
+}
+
+__global__ void k_conf_final(const int *__restrict__ conf_cnt, const int *__restrict__ tn_arr, int nb, int vn,
+                             float *__restrict__ out_conf)
+{
+    const int bk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bk >= nb * vn) return;
+    const int tn = tn_arr[bk / vn];
+    out_conf[bk] = tn > 0 ? __fdiv_rn((float)conf_cnt[bk], (float)tn) : 0.f;   // skipped image: zeros (:792)
+}
+
 // internal [b][vn][hn] -> API layouts [b,hn,vn(,2)]
 __global__ void k_export(const float2 *__restrict__ hyp, const int *__restrict__ counts,
                          const int *__restrict__ tn_arr, int nb, int vn, int hn, float *__restrict__ out_hyp,
@@ -1024,6 +1059,31 @@ int pvnet_ransac_voting_v3(const void *mask, int mask_elem_size, const float *ve
     k_refit_final<<<(b * vn + 127) / 128, 128, 0, s>>>(ws.part, ws.tn, b, vn, out_pts);
     PV_LAUNCHED("k_refit_final");
     return launch_export(ws, b, vn, hn, out_hyp, out_counts, out_tn, s);
+}
+
+int pvnet_ransac_voting_v5(const void *mask, int mask_elem_size, const float *vertex,
+                           const int64_t vertex_strides[5], const int32_t *idxs, const float *selection, int b,
+                           int h, int w, int vn, int hn, float inlier_thresh, float conf_thresh, int min_num,
+                           int max_num, float *out_pts, float *out_conf, int32_t *out_counts, float *out_hyp,
+                           int32_t *out_tn, void *workspace, size_t workspace_bytes, pvnet_stream_t stream)
+{
+    PV_CHECK_ARG(out_conf, "null out_conf");
+    int rc = pvnet_ransac_voting_v3(mask, mask_elem_size, vertex, vertex_strides, idxs, selection, b, h, w, vn, hn,
+                                    inlier_thresh, min_num, max_num, out_pts, out_counts, out_hyp, out_tn, workspace,
+                                    workspace_bytes, stream);
+    if (rc) return rc;
+    Strides st;
+    for (int i = 0; i < 5; ++i) st.s[i] = vertex_strides[i];
+    VoteWs ws = carve(workspace, b, h, w, vn, hn);
+    cudaStream_t s = (cudaStream_t)stream;
+    int *conf_cnt = reinterpret_cast<int *>(ws.part);      // the refit partials are consumed by now
+    PV_CUDA(cudaMemsetAsync(conf_cnt, 0, sizeof(int) * (size_t)b * vn, s));
+    dim3 grid(RF_CHUNKS, b * vn);
+    k_conf_count<<<grid, RF_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, h * w, vn, out_pts, conf_thresh, conf_cnt);
+    PV_LAUNCHED("k_conf_count");
+    k_conf_final<<<(b * vn + 127) / 128, 128, 0, s>>>(conf_cnt, ws.tn, b, vn, out_conf);
+    PV_LAUNCHED("k_conf_final");
+    return PVNET_OK;
 }
 
 int pvnet_vote_cov_with_mean(const void *mask, int mask_elem_size, const float *vertex,

@@ -5,6 +5,7 @@ Same names, argument meaning and defaults as zju3dv/pvnet's
 inference hot path:
 
     ransac_voting_layer_v3                   (reference :514-598)
+    ransac_voting_layer_v5                   (reference :763-858)
     estimate_voting_distribution_with_mean   (reference :333-406)
     generate_hypothesis                      (reference :983-1034)
 
@@ -190,6 +191,39 @@ def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, con
     if return_debug:
         return out, dict(counts=counts, hyp=hyp, tn=tn, idxs=idxs, selection=selection)
     return out
+
+
+def ransac_voting_layer_v5(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                           min_num=5, max_num=100, *, idxs=None, selection=None, rng="reference"):
+    """Reference signature (ransac_voting_gpu.py:763-764; note its max_num default of 100).
+    Returns (keypoints [b,vn,2], confidence [b,vn]): confidence = share of the voting pixels
+    that are inliers of the REFITTED keypoint at threshold 0.999 (:850-852).  Used by
+    tools/train_linemod.py:104 (`EvalWrapper(use_uncertainty=True)`)."""
+    del confidence, max_iter
+    _require_cuda(mask, "mask")
+    _require_cuda(vertex, "vertex")
+    b, h, w, vn, _ = vertex.shape
+    hn = int(round_hyp_num)
+    dev = mask.device
+    m, esz = _prep_mask(mask, _MASK_NONZERO_BYTE)
+    v, strides = _prep_vertex(vertex)
+    with torch.cuda.device(dev):
+        if idxs is not None:
+            idxs, selection = _check_injected(idxs, selection, b, h, w, vn, hn, dev)
+        elif rng == "reference":
+            idxs, selection, _ = _draw_reference(m, _MASK_NONZERO_BYTE, b, h, w, vn, hn, 1, min_num, max_num)
+        elif rng == "batched":
+            idxs, selection = _draw_batched(b, h, w, vn, hn, max_num, dev)
+        else:
+            raise ValueError(f"unknown rng mode {rng!r}")
+        out = torch.empty([b, vn, 2], dtype=torch.float32, device=dev)
+        conf = torch.empty([b, vn], dtype=torch.float32, device=dev)
+        ws, ws_bytes = _workspace(b, h, w, vn, hn, dev)
+        _native.check(_native.lib().pvnet_ransac_voting_v5(
+            _ptr(m), esz, _ptr(v), strides, _ptr(idxs), _ptr(selection), b, h, w, vn, hn,
+            float(inlier_thresh), 0.999, int(min_num), int(min(max_num, 2 ** 31 - 1)),
+            _ptr(out), _ptr(conf), None, None, None, _ptr(ws), ws_bytes, _stream(dev)), "pvnet_ransac_voting_v5")
+    return out, conf
 
 
 def estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=256, min_hyp_num=4096, topk=128,

@@ -263,3 +263,30 @@ def test_rng_modes_run_and_agree_statistically():
     c = rv.ransac_voting_layer_v3(mask, vertex, 256, inlier_thresh=0.99, rng="batched")
     near = slice(0, None, 2)     # keypoints at R=90; the R=260 ones are noise-limited
     assert np.abs(a.cpu().numpy() - kps[None])[:, near].max() < 3 and np.abs(c.cpu().numpy() - kps[None])[:, near].max() < 3
+
+
+def test_v5_confidence_vs_oracle():
+    """ransac_voting_layer_v5 (reference :763-858): keypoints as v3, confidence = inlier share of
+    the refitted point at 0.999.  The refit sums run in a different order than numpy's, so the
+    fp32 keypoint may differ in the last bit and move a pixel across the 0.999 threshold:
+    confidence is compared to within 2 pixels' worth."""
+    ns = [6000, 3, 1500]
+    masks = np.stack([syn.disc_mask(n) for n in ns])
+    fields = np.stack([syn.planted_field(masks[i], 9, 500 + i, sigma=0.01)[0] for i in range(3)])
+    idxs = [syn.draw_idxs(n, 128, 9, seed=i) if n >= 5 else None for i, n in enumerate(ns)]
+    okp, oconf = po.ransac_voting_layer_v5(masks, syn.as_reference_view(fields), 128, inlier_thresh=0.99,
+                                           max_num=30000, idxs=idxs)
+    mask, vertex = _to_dev(masks, fields)
+    idxs_dev = np.zeros((3, 128, 9, 2), np.int32)
+    for i, ix in enumerate(idxs):
+        if ix is not None:
+            idxs_dev[i] = ix
+    kp, conf = rv.ransac_voting_layer_v5(mask, vertex, 128, inlier_thresh=0.99, max_num=30000,
+                                         idxs=torch.from_numpy(idxs_dev))
+    kp, conf = kp.cpu().numpy(), conf.cpu().numpy()
+    assert np.abs(kp - okp).max() <= KP_TOL
+    assert np.array_equal(conf[1], np.zeros(9, np.float32))
+    for bi, n in enumerate(ns):
+        if n >= 5:
+            assert np.abs(conf[bi] - oconf[bi]).max() <= 2.0 / n + 1e-7, (conf[bi], oconf[bi])
+    assert conf[0].max() > 0.05

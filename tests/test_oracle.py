@@ -118,3 +118,13 @@ def test_covariance_skip_branch():
     expect = np.outer(mean[0, 0], mean[0, 0]) * 16 / (16 + 1e-3)
     assert np.allclose(cov[0, 0], expect, rtol=1e-6)
     assert np.array_equal(cov[0, 1], np.zeros((2, 2), np.float32))
+
+
+def test_v5_confidence_oracle():
+    mask = syn.disc_mask(2000)
+    field = syn.planted_field(mask, 3, 8, sigma=0.0)[0]
+    idxs = syn.draw_idxs(2000, 64, 3, seed=2)
+    kp, conf = po.ransac_voting_layer_v5(mask[None], syn.as_reference_view(field[None]), 64, inlier_thresh=0.99,
+                                         max_num=30000, idxs=[idxs])
+    assert kp.shape == (1, 3, 2) and conf.shape == (1, 3)
+    assert (conf > 0.95).all()       # exact field: nearly every pixel agrees with the refitted point at 0.999
