@@ -117,14 +117,18 @@ def calibrate_foreground(torch, net, x):
         return float(mask.float().sum().item() / x.shape[0])
 
 
-def make_step(torch, net):
+def make_step(torch, net, with_cov=False):
     from pvnet_b200 import ransac_voting_gpu as rv
 
     def step(x):
         out, mask = net.forward_native(x, with_mask=True)
         b, c, h, w = out.shape
         vertex = out[:, 2:].permute(0, 2, 3, 1).view(b, h, w, K_KP, 2)      # tools/demo.py:48-50
-        return rv.ransac_voting_layer_v3(mask, vertex, HYP, inlier_thresh=THRESH, rng="batched")
+        kp = rv.ransac_voting_layer_v3(mask, vertex, HYP, inlier_thresh=THRESH, rng="batched")
+        if with_cov:       # train_linemod.py:128-129 (UncertaintyEvalWrapper)
+            rv.estimate_voting_distribution_with_mean(mask, vertex, kp, round_hyp_num=256, min_hyp_num=4096,
+                                                      inlier_thresh=THRESH, rng="batched")
+        return kp
     return step
 
 
@@ -270,6 +274,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-cov", action="store_true",
+                    help="BASELINE config 4: also run estimate_voting_distribution_with_mean(256, 4096) each step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -292,7 +298,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     net = build_model(torch, dev)
-    step = make_step(torch, net)
+    step = make_step(torch, net, with_cov=args.with_cov)
     # 3 rotating input batches (3 x 59 MB > 126 MB L2); different per rank
     hosts = [torch.from_numpy(syn.backbone_input(BATCH, 1000 * 2 + 17 * rank + i)).pin_memory() for i in range(3)]
     xs = [h.to(dev, non_blocking=True) for h in hosts]
@@ -335,7 +341,8 @@ def main():
 
         # ---------------- end to end from pinned host buffers (public API: PoseKeypointPipeline)
         from pvnet_b200.pipeline import PoseKeypointPipeline
-        pipe = PoseKeypointPipeline(net, round_hyp_num=HYP, inlier_thresh=THRESH, rng="batched")
+        pipe = PoseKeypointPipeline(net, round_hyp_num=HYP, inlier_thresh=THRESH, rng="batched",
+                                    with_covariance=args.with_cov)
         kp_hosts = [torch.empty([BATCH, K_KP, 2]).pin_memory() for _ in range(args.steps)]
 
         def gather_hook(i, kp):
@@ -372,8 +379,10 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate; vote fp32/fp64)", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: Resnet18_8s(18,2) forward + argmax + ransac_voting_layer_v3"
-                                   "(256 hyp, thresh 0.99), batch 16 per GPU, 480x640, K=9",
+            "config": {"workload": ("BASELINE config 4 (per-GPU part): config 2 + estimate_voting_distribution_with_mean"
+                                    "(256, 4096)" if args.with_cov else
+                                    "BASELINE config 2: Resnet18_8s(18,2) forward + argmax + ransac_voting_layer_v3"
+                                    "(256 hyp, thresh 0.99), batch 16 per GPU, 480x640, K=9"),
                        "global_batch": BATCH * world, "parallelism": f"batch-sharded dp{world}",
                        "fg_px_per_image": round(fg, 1), "rng": "batched", "weights": "random-init, BN stats randomised",
                        "l2": "3 rotating input batches (177 MB) and a ~3.7 GB activation working set per step, both > 126 MB L2"},

@@ -80,11 +80,7 @@ int launch_stem(const float *in, const float *w, const float *bias, float *out, 
                 int out_co, cudaStream_t s)
 {
     const size_t smem = (147 * 64 + 3 * STEM_PH * STEM_PWP) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        PV_CUDA(cudaFuncSetAttribute(k_stem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    PV_CUDA(ensure_max_smem((const void *)k_stem, (int)smem));
     dim3 grid((W / 2 + STEM_TX - 1) / STEM_TX, (H / 2 + STEM_TY - 1) / STEM_TY, b);
     k_stem<<<grid, 256, smem, s>>>(in, w, bias, out, H, W, out_cs, out_co);
     PV_LAUNCHED("k_stem");

@@ -2,6 +2,9 @@
 #include "common.cuh"
 
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 
 namespace pvnet {
 
@@ -30,6 +33,20 @@ int sm_count()
         cached_dev = dev;
     }
     return cached;
+}
+
+cudaError_t ensure_max_smem(const void *func, int bytes)
+{
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({func, dev})) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.insert({func, dev});
+    return e;
 }
 
 }  // namespace pvnet

@@ -13,6 +13,9 @@ namespace pvnet {
 void set_error(const char *fmt, ...);
 long long &launch_counter();
 int sm_count();
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): set it once for each pair
+// (DataParallel-style callers drive several devices from one process)
+cudaError_t ensure_max_smem(const void *func, int bytes);
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -493,15 +493,11 @@ void conv_col_set_head_ptrs(void *storage, float *out_nchw, void *mask, int mask
 int conv_col_launch_at(const void *storage, cudaStream_t s)
 {
     const ColPlan &p = *static_cast<const ColPlan *>(storage);
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = set_attr<32, false, 3>();
-        if (attr_err == cudaSuccess) attr_err = set_attr<16, false, 4>();
-        if (attr_err == cudaSuccess) attr_err = set_attr<8, false, 3>();
-        if (attr_err == cudaSuccess) attr_err = set_attr<32, true, 3>();
-        if (attr_err == cudaSuccess) attr_err = set_attr<8, true, 3>();
-    });
+    const void *fn = (p.kc == 32 && !p.head) ? (const void *)k_conv_col<32, false, 3>
+                     : (p.kc == 16 && !p.head) ? (const void *)k_conv_col<16, false, 4>
+                     : (p.kc == 8 && !p.head) ? (const void *)k_conv_col<8, false, 3>
+                     : p.kc == 32 ? (const void *)k_conv_col<32, true, 3> : (const void *)k_conv_col<8, true, 3>;
+    const cudaError_t attr_err = ensure_max_smem(fn, (int)SMEM_LIMIT);
     PV_CUDA(attr_err);
     const HeadDesc &h = p.hd;
 #define COL_LAUNCH(KC_, HEAD_, KH_)                                                                               \

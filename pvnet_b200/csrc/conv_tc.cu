@@ -632,21 +632,11 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
 
 int conv_launch(const ConvPlan &p, cudaStream_t s)
 {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(k_conv_tc<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)ConvCfg<32>::smem_bytes(256));
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(k_conv_tc<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)ConvCfg<32>::smem_bytes(256));
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(k_conv_tc<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)ConvCfg<32>::smem_bytes(256));
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(k_conv_tap_p<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)ConvCfg<32>::smem_bytes(256));
-    });
+    const int max_smem = (int)ConvCfg<32>::smem_bytes(256);
+    const void *fn = p.mc == 2 ? (const void *)k_conv_tc<32, 2>
+                     : p.mc == 1 ? (const void *)k_conv_tc<32, 1>
+                     : p.persist ? (const void *)k_conv_tap_p<32> : (const void *)k_conv_tc<32, 0>;
+    const cudaError_t attr_err = ensure_max_smem(fn, max_smem);
     PV_CUDA(attr_err);
     if (p.mc) {
         cudaLaunchConfig_t cfg = {};
