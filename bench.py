@@ -41,6 +41,19 @@ GFLOP_STEM_HEAD = 2 * (0.723 + 0.197)   # stem + 1x1 head run on the FP32 pipe, 
 TARGET_FG = 20000
 
 
+def _host_cores():
+    """Host threads this process may really use: CPU affinity capped by the cgroup CPU quota
+    (os.cpu_count() counts the box, not the container; oversubscribing made the CPU arm 4-40x slower)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
 def _rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -198,7 +211,7 @@ def cpu_vote_baseline(seconds_budget=15.0):
     sample = images of 20000 foreground px, K=9, 256 hypotheses."""
     from oracle import pvnet_oracle as po
     from pvnet_b200 import synthetic as syn
-    po.set_num_threads(os.cpu_count() or 1)
+    po.set_num_threads(_host_cores())
     mask = syn.disc_mask(TARGET_FG)
     field = syn.planted_field(mask, K_KP, 1)[0]
     vertex = syn.as_reference_view(field[None])
@@ -228,7 +241,7 @@ def run_reference_arm(args):
     from oracle import pvnet_oracle as po
     from pvnet_b200 import synthetic as syn
     from pvnet_b200.model_repository import Resnet18_8s
-    ncpu = os.cpu_count() or 1
+    ncpu = _host_cores()
     torch.set_num_threads(ncpu)          # torchrun exports OMP_NUM_THREADS=1; this arm may use every host core
     po.set_num_threads(ncpu)
     torch.manual_seed(0)
