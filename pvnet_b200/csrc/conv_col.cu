@@ -46,8 +46,11 @@ struct ColGeom {
 template <int KC>
 __host__ __device__ constexpr int col_a_bytes(int dil) { return (COL_TH + 2 * dil) * COL_TW * KC * 4; }
 
-template <int KC, bool HEAD, int KH>
-__global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTAs per SM when shared memory allows
+// EPI = number of epilogue warp sets (4 warps each).  ncu showed the stem and layer1 launches
+// epilogue-bound (epilogue warps never wait on tfull; 39 % of samples on the residual load): with
+// EPI = 2 the sets alternate tiles, one per TMEM accumulator stage.
+template <int KC, bool HEAD, int KH, int EPI>
+__global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
     k_conv_col(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmH, const ColGeom g,
                const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out,
@@ -103,9 +106,9 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
         ptx::tmem_alloc(tmem_slot, tmem_cols);
         ptx::tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < g.BN; i += COL_THREADS) s_bias[i] = bias[i];
+    for (int i = threadIdx.x; i < g.BN; i += blockDim.x) s_bias[i] = bias[i];
     if (HEAD)
-        for (int i = threadIdx.x; i < g.head_cout; i += COL_THREADS) s_head[i] = head_b[i];
+        for (int i = threadIdx.x; i < g.head_cout; i += blockDim.x) s_head[i] = head_b[i];
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -239,8 +242,9 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const int ty = m / COL_TW, tx = m - ty * COL_TW;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+        const int epi_set = (warp - 2) >> 2;                     // 0, or 1 when EPI == 2
+        uint32_t it = (uint32_t)epi_set;
+        for (int tile = blockIdx.x + epi_set * gridDim.x; tile < g.total_tiles; tile += EPI * gridDim.x, it += EPI) {
             const uint32_t as = it & 1u;
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
@@ -248,6 +252,14 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
             const int y = tyi * COL_TH + ty, x = txi * COL_TW + tx;
             const bool valid = (y < g.Ho) && (x < g.Wo);
             const size_t pix = ((size_t)img * g.Ho + y) * g.Wo + x;
+            // residual of the first 32 channels: issued before waiting for the accumulator so the
+            // global-load latency overlaps the MMAs of this tile
+            float4 rpre[8];
+            if (res != nullptr && valid) {
+                const float4 *rp = reinterpret_cast<const float4 *>(res + pix * g.res_cs + g.res_co);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rpre[j] = __ldg(rp + j);
+            }
             ptx::mbar_wait(&tfull[as], (it >> 1) & 1u);
             ptx::tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)g.BN;
@@ -274,7 +286,7 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
                     const float4 *rp = reinterpret_cast<const float4 *>(res + pix * g.res_cs + g.res_co + c0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 rv = __ldg(rp + j);
+                        const float4 rv = c0 == 0 ? rpre[j] : __ldg(rp + j);
                         v[4 * j] += rv.x;
                         v[4 * j + 1] += rv.y;
                         v[4 * j + 2] += rv.z;
@@ -344,7 +356,7 @@ __global__ void __launch_bounds__(COL_THREADS, 2)   // <= 170 registers: two CTA
 struct ColPlan {
     CUtensorMap tmA, tmB, tmH;
     ColGeom g;
-    int kc, head;
+    int kc, head, epi;
     unsigned grid;
     size_t smem;
     const float *bias, *res;
@@ -368,10 +380,10 @@ size_t col_smem(int kc, int ksize, int cin_chunks, int bn, int dil, int stages, 
            (size_t)(1 + 2 * stages + 4 + 5) * 8 + 16 + (size_t)(64 + 64) * 4 + 64 + (head_cout ? 4096 : 0);
 }
 
-template <int KC, bool HEAD, int KH>
+template <int KC, bool HEAD, int KH, int EPI>
 cudaError_t set_attr()
 {
-    return cudaFuncSetAttribute(k_conv_col<KC, HEAD, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    return cudaFuncSetAttribute(k_conv_col<KC, HEAD, KH, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
 }
 
 }  // namespace
@@ -472,6 +484,12 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
         p->tmH = p->tmB;
     }
     const int per_sm = (int)(SMEM_LIMIT / p->smem) >= 2 ? 2 : 1;
+    static const int env_epi = [] {
+        const char *e = getenv("PVNET_COL_EPI");       // tuning knob: 1 forces a single epilogue warp set
+        return e ? atoi(e) : 2;
+    }();
+    // two epilogue warp sets when the CTA is alone on its SM anyway (and the variant exists)
+    p->epi = (per_sm == 1 && !head && kc != 8 && env_epi == 2) ? 2 : 1;
     long long grid = (long long)sm_count() * per_sm;
     if (grid > g.total_tiles) grid = g.total_tiles;
     p->grid = (unsigned)grid;
@@ -493,22 +511,24 @@ void conv_col_set_head_ptrs(void *storage, float *out_nchw, void *mask, int mask
 int conv_col_launch_at(const void *storage, cudaStream_t s)
 {
     const ColPlan &p = *static_cast<const ColPlan *>(storage);
-    const void *fn = (p.kc == 32 && !p.head) ? (const void *)k_conv_col<32, false, 3>
-                     : (p.kc == 16 && !p.head) ? (const void *)k_conv_col<16, false, 4>
-                     : (p.kc == 8 && !p.head) ? (const void *)k_conv_col<8, false, 3>
-                     : p.kc == 32 ? (const void *)k_conv_col<32, true, 3> : (const void *)k_conv_col<8, true, 3>;
+    const void *fn = (p.kc == 32 && !p.head) ? (p.epi == 2 ? (const void *)k_conv_col<32, false, 3, 2> : (const void *)k_conv_col<32, false, 3, 1>)
+                     : (p.kc == 16 && !p.head) ? (p.epi == 2 ? (const void *)k_conv_col<16, false, 4, 2> : (const void *)k_conv_col<16, false, 4, 1>)
+                     : (p.kc == 8 && !p.head) ? (const void *)k_conv_col<8, false, 3, 1>
+                     : p.kc == 32 ? (const void *)k_conv_col<32, true, 3, 1> : (const void *)k_conv_col<8, true, 3, 1>;
     const cudaError_t attr_err = ensure_max_smem(fn, (int)SMEM_LIMIT);
     PV_CUDA(attr_err);
     const HeadDesc &h = p.hd;
-#define COL_LAUNCH(KC_, HEAD_, KH_)                                                                               \
-    k_conv_col<KC_, HEAD_, KH_><<<p.grid, COL_THREADS, p.smem, s>>>(p.tmA, p.tmB, p.tmH, p.g, p.bias, p.res, p.out,           \
+#define COL_LAUNCH(KC_, HEAD_, KH_, EPI_)                                                                         \
+    k_conv_col<KC_, HEAD_, KH_, EPI_><<<p.grid, 64 + 128 * EPI_, p.smem, s>>>(p.tmA, p.tmB, p.tmH, p.g, p.bias, p.res, p.out,           \
                                                                 p.head ? h.w : nullptr, p.head ? h.bias : nullptr, \
                                                                 p.head ? h.out_nchw : nullptr, p.head ? h.mask : nullptr)
-    if (p.kc == 32 && !p.head) COL_LAUNCH(32, false, 3);
-    else if (p.kc == 16 && !p.head) COL_LAUNCH(16, false, 4);
-    else if (p.kc == 8 && !p.head) COL_LAUNCH(8, false, 3);
-    else if (p.kc == 32) COL_LAUNCH(32, true, 3);
-    else COL_LAUNCH(8, true, 3);
+    if (p.kc == 32 && !p.head && p.epi == 2) COL_LAUNCH(32, false, 3, 2);
+    else if (p.kc == 32 && !p.head) COL_LAUNCH(32, false, 3, 1);
+    else if (p.kc == 16 && !p.head && p.epi == 2) COL_LAUNCH(16, false, 4, 2);
+    else if (p.kc == 16 && !p.head) COL_LAUNCH(16, false, 4, 1);
+    else if (p.kc == 8 && !p.head) COL_LAUNCH(8, false, 3, 1);
+    else if (p.kc == 32) COL_LAUNCH(32, true, 3, 1);
+    else COL_LAUNCH(8, true, 3, 1);
 #undef COL_LAUNCH
     PV_LAUNCHED("k_conv_col");
     return PVNET_OK;

@@ -406,6 +406,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
             const size_t pix = ((size_t)img * g.Ho + y) * g.Wo + x;
             float *optr = out + pix * g.out_cs + g.out_co + n0;
             const float *rptr = res ? res + pix * g.res_cs + g.res_co + n0 : nullptr;
+            // residual of the first 32 channels: loaded before waiting for the accumulator
+            float4 rpre[8];
+            if (rptr && valid) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rpre[j] = __ldg(reinterpret_cast<const float4 *>(rptr) + j);
+            }
             ptx::mbar_wait(&tfull[as], (it >> 1) & 1u);
             ptx::tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)g.BN;
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                         float4 v = make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
                                                __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w);
                         if (rptr) {
-                            const float4 rv = __ldg(reinterpret_cast<const float4 *>(rptr + c0 + j));
+                            const float4 rv = c0 == 0 ? rpre[j >> 2] : __ldg(reinterpret_cast<const float4 *>(rptr + c0 + j));
                             v.x += rv.x;
                             v.y += rv.y;
                             v.z += rv.z;
