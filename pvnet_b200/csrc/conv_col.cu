@@ -52,7 +52,7 @@ __host__ __device__ constexpr int col_a_bytes(int dil) { return (COL_TH + 2 * di
 template <int KC, bool HEAD, int KH, int EPI>
 __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
     k_conv_col(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmH, const ColGeom g,
+               const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmO, const ColGeom g,
                const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out,
                const float *__restrict__ head_w, const float *__restrict__ head_b, float *__restrict__ head_out,
                void *__restrict__ mask)
@@ -66,8 +66,10 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
     const int stage_bytes = a_bytes + (g.resident ? 0 : KH * b_tile);
     uint8_t *sB = smem;
     uint8_t *sA = smem + (g.resident ? (size_t)n_btiles * b_tile : 0);
-    uint8_t *sHB = sA + (size_t)g.stages * stage_bytes;            // head weights [32][32] (HEAD only), 4 KB
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sHB + (HEAD ? 4096 : 0));
+    // HEAD: head weights [32][32], 4 KB.  otherwise: one 128-pixel x 32-channel output staging tile
+    // (128B-swizzled rows) for the TMA store of the epilogue, 16 KB
+    uint8_t *sHB = sA + (size_t)g.stages * stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sHB + (HEAD ? 4096 : 16384));
     uint64_t *wfull = bars;
     uint64_t *full = bars + 1;
     uint64_t *empty = full + g.stages;
@@ -337,14 +339,28 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                             else reinterpret_cast<unsigned char *>(mask)[pix] = (unsigned char)best_c;
                         }
                     }
-                } else if (valid) {
-                    float4 *op = reinterpret_cast<float4 *>(out + pix * g.out_cs + g.out_co + c0);
+                } else {
+                    // Stores go through shared memory and ONE TMA box per 32 channels: a thread owns a
+                    // pixel, so direct 16-byte stores hit 32 different 256..768-byte-strided records per
+                    // instruction (LSU-transaction bound: two epilogue warp sets gave no speed-up).
+                    // Row m of the staging tile is 128 B; 16-byte chunk j sits at (j ^ (m & 7)).
+                    if (lane == 0 && q == 0) ptx::tma_store_wait_read();      // previous box has left the tile
+                    ptx::named_bar_sync(1, 128);
+                    float4 *srow = reinterpret_cast<float4 *>(sHB + (size_t)m * 128);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j)
+                        srow[j ^ (m & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    ptx::fence_proxy_async();
+                    ptx::named_bar_sync(1, 128);
+                    if (lane == 0 && q == 0) {
+                        ptx::tma_store_4d(&tmO, sHB, c0, txi * COL_TW, tyi * COL_TH, img);
+                        ptx::tma_store_commit();
+                    }
                 }
             }
         }
     }
+    if (!HEAD && warp == 4 && lane == 0) ptx::tma_store_wait_all();   // the thread that issued the stores (q == 0)
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -354,7 +370,7 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
 }
 
 struct ColPlan {
-    CUtensorMap tmA, tmB, tmH;
+    CUtensorMap tmA, tmB, tmH, tmO;
     ColGeom g;
     int kc, head, epi;
     unsigned grid;
@@ -377,7 +393,7 @@ size_t col_smem(int kc, int ksize, int cin_chunks, int bn, int dil, int stages, 
     const size_t a = (size_t)(COL_TH + (ksize - 1) * dil) * COL_TW * rowb, bt = (size_t)bn * rowb;
     return 1024 + (resident ? (size_t)ksize * ksize * cin_chunks * bt : 0) +
            (size_t)stages * (a + (resident ? 0 : (size_t)ksize * bt)) +
-           (size_t)(1 + 2 * stages + 4 + 5) * 8 + 16 + (size_t)(64 + 64) * 4 + 64 + (head_cout ? 4096 : 0);
+           (size_t)(1 + 2 * stages + 4 + 5) * 8 + 16 + (size_t)(64 + 64) * 4 + 64 + (head_cout ? 4096 : 16384);
 }
 
 template <int KC, bool HEAD, int KH, int EPI>
@@ -473,6 +489,16 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
         int rc = tma_encode(&p->tmB, d.w, 2, dims, strides, box, kc * 4);
         if (rc) return rc;
     }
+    if (!head) {     // output slice [b,H,W,out_cs] at out_co, stored by TMA in boxes {32 ch, TW, TH, 1}
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.b};
+        cuuint64_t strides[3] = {(cuuint64_t)d.out_cs * 4, (cuuint64_t)d.W * d.out_cs * 4,
+                                 (cuuint64_t)d.H * d.W * d.out_cs * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)COL_TW, (cuuint32_t)COL_TH, 1};
+        int rc = tma_encode(&p->tmO, d.out + d.out_co, 4, dims, strides, box, 128);
+        if (rc) return rc;
+    } else {
+        p->tmO = p->tmA;
+    }
     if (head) {      // convraw.3 weights [cout][32] fp32, read as a 32x32 K-major tile (rows beyond cout: zero fill)
         PV_CHECK_ARG((uintptr_t)head->w % 16 == 0, "conv(col): head weights must be 16-byte aligned");
         cuuint64_t dims[2] = {32, (cuuint64_t)head->cout};
@@ -489,7 +515,8 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
         return e ? atoi(e) : 2;
     }();
     // two epilogue warp sets when the CTA is alone on its SM anyway (and the variant exists)
-    p->epi = (per_sm == 1 && !head && kc != 8 && env_epi == 2) ? 2 : 1;
+    p->epi = 1;       // (a second epilogue warp set measured no gain: the epilogue was LSU-bound, see below)
+    (void)env_epi;
     long long grid = (long long)sm_count() * per_sm;
     if (grid > g.total_tiles) grid = g.total_tiles;
     p->grid = (unsigned)grid;
@@ -519,7 +546,7 @@ int conv_col_launch_at(const void *storage, cudaStream_t s)
     PV_CUDA(attr_err);
     const HeadDesc &h = p.hd;
 #define COL_LAUNCH(KC_, HEAD_, KH_, EPI_)                                                                         \
-    k_conv_col<KC_, HEAD_, KH_, EPI_><<<p.grid, 64 + 128 * EPI_, p.smem, s>>>(p.tmA, p.tmB, p.tmH, p.g, p.bias, p.res, p.out,           \
+    k_conv_col<KC_, HEAD_, KH_, EPI_><<<p.grid, 64 + 128 * EPI_, p.smem, s>>>(p.tmA, p.tmB, p.tmH, p.tmO, p.g, p.bias, p.res, p.out,           \
                                                                 p.head ? h.w : nullptr, p.head ? h.bias : nullptr, \
                                                                 p.head ? h.out_nchw : nullptr, p.head ? h.mask : nullptr)
     if (p.kc == 32 && !p.head && p.epi == 2) COL_LAUNCH(32, false, 3, 2);

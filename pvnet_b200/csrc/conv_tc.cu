@@ -287,7 +287,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 // cost as much as the MMAs themselves.
 template <int KC>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-    k_conv_tap_p(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap tmB, const ConvGeom g,
+    k_conv_tap_p(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const ConvGeom g,
                  const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out)
 {
     using Cfg = ConvCfg<KC>;
@@ -296,7 +297,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = g.BN * KC * 4;
     const int stage_bytes = Cfg::A_BYTES + b_bytes;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * stage_bytes);
+    uint8_t *sOut = smem + (size_t)STAGES * stage_bytes;   // 128 px x 32 ch staging tile of the TMA store, 16 KB
+    uint64_t *full = reinterpret_cast<uint64_t *>(sOut + 16384);
     uint64_t *empty = full + STAGES;
     uint64_t *tfull = empty + STAGES;      // [2]
     uint64_t *tempty = tfull + 2;          // [2]
@@ -424,6 +426,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tempty[as]);
                 }
+                float4 vout[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vout[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -454,11 +459,24 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                             v.z = ptx::round_tf32(v.z);
                             v.w = ptx::round_tf32(v.w);
                         }
-                        *reinterpret_cast<float4 *>(optr + c0 + j) = v;
+                        vout[j >> 2] = v;
                     }
+                }
+                // one TMA box per 32 channels instead of 32 strided 16-byte stores per instruction
+                if (lane == 0 && q == 0) ptx::tma_store_wait_read();
+                ptx::named_bar_sync(1, 128);
+                float4 *srow = reinterpret_cast<float4 *>(sOut + (size_t)m * 128);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) srow[j ^ (m & 7)] = vout[j];
+                ptx::fence_proxy_async();
+                ptx::named_bar_sync(1, 128);
+                if (lane == 0 && q == 0) {
+                    ptx::tma_store_4d(&tmO, sOut, n0 + c0, txi * g.TW, tyi * g.TH, img);
+                    ptx::tma_store_commit();
                 }
             }
         }
+        if (q == 0 && lane == 0) ptx::tma_store_wait_all();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -515,7 +533,7 @@ int tma_encode(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dim
 // long as the pointers and shapes stay the same).
 struct ConvPlan {
     AMaps amaps;
-    CUtensorMap tmB;
+    CUtensorMap tmB, tmO;
     ConvGeom g;
     int kc, mc, persist;
     dim3 grid;
@@ -620,7 +638,15 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
                          : ConvCfg<32>::smem_bytes(g.BN);
     // single-CTA tiles run on the persistent kernel: grid = resident CTAs
     p->persist = (p->mc == 0 && g_conv_persist) ? 1 : 0;
+    p->tmO = p->tmB;
     if (p->persist) {
+        p->smem += 16384;                       // output staging tile of the TMA-store epilogue
+        cuuint64_t odims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)d.b};
+        cuuint64_t ostr[3] = {(cuuint64_t)d.out_cs * 4, (cuuint64_t)g.Wo * d.out_cs * 4,
+                              (cuuint64_t)g.Ho * g.Wo * d.out_cs * 4};
+        cuuint32_t obox[4] = {32, (cuuint32_t)g.TW, (cuuint32_t)g.TH, 1};
+        int rc = tma_encode(&p->tmO, d.out + d.out_co, 4, odims, ostr, obox, 128);
+        if (rc) return rc;
         int per_sm = (int)((227 * 1024) / p->smem);
         if (per_sm > 2) per_sm = 2;
         if (per_sm * 2 * g.BN > 512) per_sm = 512 / (2 * g.BN);      // TMEM: two accumulator stages per CTA
@@ -638,7 +664,7 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
 
 int conv_launch(const ConvPlan &p, cudaStream_t s)
 {
-    const int max_smem = (int)ConvCfg<32>::smem_bytes(256);
+    const int max_smem = (int)ConvCfg<32>::smem_bytes(256) + 16384;
     const void *fn = p.mc == 2 ? (const void *)k_conv_tc<32, 2>
                      : p.mc == 1 ? (const void *)k_conv_tc<32, 1>
                      : p.persist ? (const void *)k_conv_tap_p<32> : (const void *)k_conv_tc<32, 0>;
@@ -662,7 +688,7 @@ int conv_launch(const ConvPlan &p, cudaStream_t s)
         else
             PV_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<32, 1>, p.amaps, p.tmB, p.g, p.bias, p.res, p.out));
     } else if (p.persist) {
-        k_conv_tap_p<32><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.g, p.bias, p.res, p.out);
+        k_conv_tap_p<32><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.tmO, p.g, p.bias, p.res, p.out);
     } else {
         k_conv_tc<32, 0><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.g, p.bias, p.res, p.out);
     }
