@@ -121,36 +121,60 @@ __global__ void __launch_bounds__(128)
     k_s2d_pack(const float *__restrict__ in, float *__restrict__ s2d, float *__restrict__ out, int H, int W, int out_cs,
                int out_co)
 {
-    // grid.y = image * H/2 + half-resolution row; threads over half-resolution columns
+    // grid.y = image * H/2 + half-resolution row; a block covers 128 half-resolution columns.
+    // Loads are coalesced float2 reads of the six (channel, row) lines; both outputs are staged in
+    // shared memory so that the stores are coalesced too (a thread-per-pixel store touches 32
+    // different 64-byte / 160-byte-strided records per instruction).
+    __shared__ float4 sS[128 * 4];        // [px][4 chunks], chunk j of px at j ^ ((px >> 1) & 3)
+    __shared__ float4 sI[2][256];         // [row parity][full-resolution column]: (r, g, b, 0)
     const int W2 = W >> 1, H2 = H >> 1;
-    const int x2 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x2 >= W2) return;
+    const int xb = blockIdx.x * 128, t = threadIdx.x;
+    const int x2 = xb + t;
     const int n = blockIdx.y / H2, y2 = blockIdx.y - n * H2;
     const size_t plane = (size_t)H * W;
-    const float *src = in + (size_t)n * 3 * plane + (size_t)(2 * y2) * W + 2 * x2;
-    float v[16];
+    if (x2 < W2) {
+        const float *src = in + (size_t)n * 3 * plane + (size_t)(2 * y2) * W + 2 * x2;
+        float v[16];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int py = 0; py < 2; ++py) {
-            const float2 t = __ldg(reinterpret_cast<const float2 *>(src + c * plane + py * W));
-            v[(py * 2 + 0) * 3 + c] = ptx::round_tf32(t.x);
-            v[(py * 2 + 1) * 3 + c] = ptx::round_tf32(t.y);
+            for (int py = 0; py < 2; ++py) {
+                const float2 q = __ldg(reinterpret_cast<const float2 *>(src + c * plane + py * W));
+                v[(py * 2 + 0) * 3 + c] = ptx::round_tf32(q.x);
+                v[(py * 2 + 1) * 3 + c] = ptx::round_tf32(q.y);
+            }
+        v[12] = v[13] = v[14] = v[15] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            sS[t * 4 + (j ^ ((t >> 1) & 3))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                const int b = (py * 2 + px) * 3;
+                sI[py][2 * t + px] = make_float4(v[b], v[b + 1], v[b + 2], 0.f);
+            }
+    }
+    __syncthreads();
+    const int npx = min(128, W2 - xb);                    // half-resolution pixels this block holds
+    float4 *so = reinterpret_cast<float4 *>(s2d + ((size_t)blockIdx.y * W2 + xb) * 16);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int L = t + 128 * r, px = L >> 2, j = L & 3;
+        if (px < npx) so[L] = sS[px * 4 + (j ^ ((px >> 1) & 3))];
+    }
+    // image slice: lane pairs write the 32 bytes (3 channels + 5 zeros) of one full-resolution pixel
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+        float *orow = out + (((size_t)n * H + 2 * y2 + py) * W + 2 * xb) * out_cs + out_co;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int L = t + 128 * r, px = L >> 1, half = L & 1;
+            if (px < 2 * npx)
+                *reinterpret_cast<float4 *>(orow + (size_t)px * out_cs + half * 4) =
+                    half ? make_float4(0.f, 0.f, 0.f, 0.f) : sI[py][px];
         }
-    v[12] = v[13] = v[14] = v[15] = 0.f;
-    float4 *so = reinterpret_cast<float4 *>(s2d + ((size_t)blockIdx.y * W2 + x2) * 16);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) so[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-#pragma unroll
-    for (int py = 0; py < 2; ++py)
-#pragma unroll
-        for (int px = 0; px < 2; ++px) {
-            const size_t pix = (size_t)n * plane + (size_t)(2 * y2 + py) * W + (2 * x2 + px);
-            float4 *o = reinterpret_cast<float4 *>(out + pix * out_cs + out_co);
-            const int b = (py * 2 + px) * 3;
-            o[0] = make_float4(v[b], v[b + 1], v[b + 2], 0.f);
-            o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    }
 }
 
 int launch_s2d_pack(const float *in, float *s2d, float *out, int b, int H, int W, int out_cs, int out_co,
@@ -209,31 +233,67 @@ __global__ void __launch_bounds__(256)
     k_upsample2x(const float *__restrict__ in, float *__restrict__ out, int h, int w, int C, int out_cs, int out_co,
                  float sy, float sx)
 {
-    // grid.y = image * 2h + output row; threads cover (output column, 4-channel group) of that row
-    const int c4 = C >> 2, Ho = 2 * h, Wo = 2 * w;
+    // One thread = the 2x2 output block (2j..2j+1, 2k..2k+1) of one 4-channel group.  With
+    // align_corners=True and scale 2 the source rows of output rows 2j, 2j+1 all lie in
+    // {j-1, j, j+1} (same for columns), so the block needs a 3x3 neighbourhood: 9 loads for 4
+    // outputs instead of 16.  Each output keeps PyTorch's separable form
+    // h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11); the third row/column enters with weight 0.
+    // grid.y = image * h + j; threads cover (k, channel group).
+    const int c4 = C >> 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Wo * c4) return;
-    const int ox = i / c4, cg = i - ox * c4;
-    const int n = blockIdx.y / Ho, oy = blockIdx.y - n * Ho;
-    const float fy = sy * (float)oy, fx = sx * (float)ox;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-    const float h1 = fy - (float)y0, h0 = 1.f - h1, w1 = fx - (float)x0, w0 = 1.f - w1;
+    if (i >= w * c4) return;
+    const int k = i / c4, cg = i - k * c4;
+    const int n = blockIdx.y / h, j = blockIdx.y - n * h;
+
+    float wy[2][3], wx[2][3];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+        const float fy = sy * (float)(2 * j + o), fx = sx * (float)(2 * k + o);
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float h1 = fy - (float)y0, h0 = 1.f - h1, w1 = fx - (float)x0, w0 = 1.f - w1;
+        const int iy0 = y0 - (j - 1), iy1 = y1 - (j - 1), ix0 = x0 - (k - 1), ix1 = x1 - (k - 1);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            wy[o][r] = (r == iy0 ? h0 : 0.f) + (r == iy1 ? h1 : 0.f);
+            wx[o][r] = (r == ix0 ? w0 : 0.f) + (r == ix1 ? w1 : 0.f);
+        }
+    }
     const float4 *base = reinterpret_cast<const float4 *>(in) + (size_t)n * h * w * c4 + cg;
-    const float4 v00 = __ldg(base + (y0 * w + x0) * c4), v01 = __ldg(base + (y0 * w + x1) * c4);
-    const float4 v10 = __ldg(base + (y1 * w + x0) * c4), v11 = __ldg(base + (y1 * w + x1) * c4);
-    float4 o;
-    o.x = ptx::round_tf32(h0 * (w0 * v00.x + w1 * v01.x) + h1 * (w0 * v10.x + w1 * v11.x));
-    o.y = ptx::round_tf32(h0 * (w0 * v00.y + w1 * v01.y) + h1 * (w0 * v10.y + w1 * v11.y));
-    o.z = ptx::round_tf32(h0 * (w0 * v00.z + w1 * v01.z) + h1 * (w0 * v10.z + w1 * v11.z));
-    o.w = ptx::round_tf32(h0 * (w0 * v00.w + w1 * v01.w) + h1 * (w0 * v10.w + w1 * v11.w));
-    *reinterpret_cast<float4 *>(out + ((size_t)blockIdx.y * Wo + ox) * out_cs + out_co + cg * 4) = o;
+    float4 t[3][2];                                      // per source row: the two horizontally interpolated values
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int y = min(max(j - 1 + r, 0), h - 1);
+        const float4 *row = base + (size_t)y * w * c4;
+        const float4 a = __ldg(row + max(k - 1, 0) * c4), bq = __ldg(row + k * c4),
+                     c = __ldg(row + min(k + 1, w - 1) * c4);
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            t[r][o].x = wx[o][0] * a.x + wx[o][1] * bq.x + wx[o][2] * c.x;
+            t[r][o].y = wx[o][0] * a.y + wx[o][1] * bq.y + wx[o][2] * c.y;
+            t[r][o].z = wx[o][0] * a.z + wx[o][1] * bq.z + wx[o][2] * c.z;
+            t[r][o].w = wx[o][0] * a.w + wx[o][1] * bq.w + wx[o][2] * c.w;
+        }
+    }
+    const int Wo = 2 * w;
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < 2; ++ox) {
+            float4 v;
+            v.x = ptx::round_tf32(wy[oy][0] * t[0][ox].x + wy[oy][1] * t[1][ox].x + wy[oy][2] * t[2][ox].x);
+            v.y = ptx::round_tf32(wy[oy][0] * t[0][ox].y + wy[oy][1] * t[1][ox].y + wy[oy][2] * t[2][ox].y);
+            v.z = ptx::round_tf32(wy[oy][0] * t[0][ox].z + wy[oy][1] * t[1][ox].z + wy[oy][2] * t[2][ox].z);
+            v.w = ptx::round_tf32(wy[oy][0] * t[0][ox].w + wy[oy][1] * t[1][ox].w + wy[oy][2] * t[2][ox].w);
+            const size_t pix = ((size_t)n * 2 * h + 2 * j + oy) * Wo + 2 * k + ox;
+            *reinterpret_cast<float4 *>(out + pix * out_cs + out_co + cg * 4) = v;
+        }
 }
 
 int launch_upsample2x(const float *in, float *out, int b, int h, int w, int C, int out_cs, int out_co, cudaStream_t s)
 {
     const float sy = (float)(h - 1) / (float)(2 * h - 1), sx = (float)(w - 1) / (float)(2 * w - 1);
-    dim3 grid((unsigned)((2 * w * (C / 4) + 255) / 256), (unsigned)(b * 2 * h));
+    dim3 grid((unsigned)((w * (C / 4) + 255) / 256), (unsigned)(b * h));
     k_upsample2x<<<grid, 256, 0, s>>>(in, out, h, w, C, out_cs, out_co, sy, sx);
     PV_LAUNCHED("k_upsample2x");
     return PVNET_OK;

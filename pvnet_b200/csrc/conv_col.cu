@@ -254,13 +254,15 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
             const int y = tyi * COL_TH + ty, x = txi * COL_TW + tx;
             const bool valid = (y < g.Ho) && (x < g.Wo);
             const size_t pix = ((size_t)img * g.Ho + y) * g.Wo + x;
-            // residual of the first 32 channels: issued before waiting for the accumulator so the
-            // global-load latency overlaps the MMAs of this tile
+            // Residual: fetched COALESCED (load i of lane l = pixel 4i + l/8 of this warp, 16-byte
+            // chunk l%8: four full 128-byte lines per instruction instead of 32 strided sectors) and
+            // handed to the pixel-owning lanes through this warp's rows of the staging tile. The first
+            // 32 channels are issued before waiting for the accumulator so the latency overlaps the MMAs.
             float4 rpre[8];
-            if (res != nullptr && valid) {
-                const float4 *rp = reinterpret_cast<const float4 *>(res + pix * g.res_cs + g.res_co);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rpre[j] = __ldg(rp + j);
+            const float *rbase = nullptr;
+            if (res != nullptr) {
+                rbase = res + (((size_t)img * g.Ho + tyi * COL_TH) * g.Wo + txi * COL_TW) * g.res_cs + g.res_co;
+                res_fetch8(rpre, rbase, q, lane, tyi * COL_TH, txi * COL_TW, g.Ho, g.Wo, g.res_cs);
             }
             ptx::mbar_wait(&tfull[as], (it >> 1) & 1u);
             ptx::tc_fence_after();
@@ -284,16 +286,27 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                     v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bv.z;
                     v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bv.w;
                 }
-                if (res != nullptr && valid) {
-                    const float4 *rp = reinterpret_cast<const float4 *>(res + pix * g.res_cs + g.res_co + c0);
+                if (!HEAD && res != nullptr) {
+                    if (lane == 0 && q == 0) ptx::tma_store_wait_read();      // previous box has left the tile
+                    ptx::named_bar_sync(1, 128);
+                    float4 *wrow = reinterpret_cast<float4 *>(sHB + (size_t)(q * 32) * 128);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + (lane >> 3);
+                        wrow[row * 8 + ((lane & 7) ^ (row & 7))] = rpre[i];
+                    }
+                    __syncwarp();
+                    const float4 *srow = reinterpret_cast<const float4 *>(sHB + (size_t)m * 128);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 rv = c0 == 0 ? rpre[j] : __ldg(rp + j);
+                        const float4 rv = srow[j ^ (m & 7)];
                         v[4 * j] += rv.x;
                         v[4 * j + 1] += rv.y;
                         v[4 * j + 2] += rv.z;
                         v[4 * j + 3] += rv.w;
                     }
+                    __syncwarp();
+                    if (c0 + 32 < g.BN) res_fetch8(rpre, rbase + c0 + 32, q, lane, tyi * COL_TH, txi * COL_TW, g.Ho, g.Wo, g.res_cs);
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -344,8 +357,10 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                     // pixel, so direct 16-byte stores hit 32 different 256..768-byte-strided records per
                     // instruction (LSU-transaction bound: two epilogue warp sets gave no speed-up).
                     // Row m of the staging tile is 128 B; 16-byte chunk j sits at (j ^ (m & 7)).
-                    if (lane == 0 && q == 0) ptx::tma_store_wait_read();      // previous box has left the tile
-                    ptx::named_bar_sync(1, 128);
+                    if (res == nullptr) {
+                        if (lane == 0 && q == 0) ptx::tma_store_wait_read();  // previous box has left the tile
+                        ptx::named_bar_sync(1, 128);
+                    }
                     float4 *srow = reinterpret_cast<float4 *>(sHB + (size_t)m * 128);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)

@@ -286,9 +286,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 // downsamples, conv8s/conv4s) the per-tile prologue + epilogue of the one-tile-per-CTA kernel
 // cost as much as the MMAs themselves.
 template <int KC>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(CONV_THREADS, 2)
     k_conv_tap_p(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmO, const ConvGeom g,
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvGeom g,
                  const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out)
 {
     using Cfg = ConvCfg<KC>;
@@ -395,7 +395,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     } else {
         const int q = warp & 3;
         const int m = q * 32 + lane;
-        const int ty = m / g.TW, tx = m - ty * g.TW;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t as = it & 1u;
@@ -403,16 +402,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
             const int img = m_tile / tiles_per_img;
             const int trem = m_tile - img * tiles_per_img;
             const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
-            const int y = tyi * g.TH + ty, x = txi * g.TW + tx, n0 = n_tile * g.BN;
-            const bool valid = (y < g.Ho) && (x < g.Wo);
-            const size_t pix = ((size_t)img * g.Ho + y) * g.Wo + x;
-            float *optr = out + pix * g.out_cs + g.out_co + n0;
-            const float *rptr = res ? res + pix * g.res_cs + g.res_co + n0 : nullptr;
-            // residual of the first 32 channels: loaded before waiting for the accumulator
+            const int n0 = n_tile * g.BN;
+            // Residual: fetched COALESCED (load i of lane l = pixel 4i + l/8 of this warp, 16-byte
+            // chunk l%8: four full 128-byte lines per instruction) and handed to the pixel-owning lanes
+            // through this warp's rows of the staging tile; the first 32 channels are issued before
+            // waiting for the accumulator.
             float4 rpre[8];
-            if (rptr && valid) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rpre[j] = __ldg(reinterpret_cast<const float4 *>(rptr) + j);
+            const float *rbase = nullptr;
+            if (res != nullptr) {
+                rbase = res + (((size_t)img * g.Ho + tyi * g.TH) * g.Wo + txi * g.TW) * g.res_cs + g.res_co + n0;
+                res_fetch8(rpre, rbase, q, lane, tyi * g.TH, txi * g.TW, g.Ho, g.Wo, g.res_cs);
             }
             ptx::mbar_wait(&tfull[as], (it >> 1) & 1u);
             ptx::tc_fence_after();
@@ -426,48 +425,54 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tempty[as]);
                 }
-                float4 vout[8];
+                float v[32];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) vout[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) {
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n0 + c0) + j);
+                    v[4 * j] = __uint_as_float(r[4 * j]) + bv.x;
+                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bv.y;
+                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bv.z;
+                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bv.w;
+                }
+                if (res != nullptr) {
+                    if (lane == 0 && q == 0) ptx::tma_store_wait_read();      // previous box has left the tile
+                    ptx::named_bar_sync(1, 128);
+                    float4 *wrow = reinterpret_cast<float4 *>(sOut + (size_t)(q * 32) * 128);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n0 + c0 + j));
-                        float4 v = make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
-                                               __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w);
-                        if (rptr) {
-                            const float4 rv = c0 == 0 ? rpre[j >> 2] : __ldg(reinterpret_cast<const float4 *>(rptr + c0 + j));
-                            v.x += rv.x;
-                            v.y += rv.y;
-                            v.z += rv.z;
-                            v.w += rv.w;
-                        }
-                        if (g.act == 1) {
-                            v.x = fmaxf(v.x, 0.f);
-                            v.y = fmaxf(v.y, 0.f);
-                            v.z = fmaxf(v.z, 0.f);
-                            v.w = fmaxf(v.w, 0.f);
-                        } else if (g.act == 2) {
-                            v.x = v.x > 0.f ? v.x : 0.1f * v.x;
-                            v.y = v.y > 0.f ? v.y : 0.1f * v.y;
-                            v.z = v.z > 0.f ? v.z : 0.1f * v.z;
-                            v.w = v.w > 0.f ? v.w : 0.1f * v.w;
-                        }
-                        if (g.round_out) {
-                            v.x = ptx::round_tf32(v.x);
-                            v.y = ptx::round_tf32(v.y);
-                            v.z = ptx::round_tf32(v.z);
-                            v.w = ptx::round_tf32(v.w);
-                        }
-                        vout[j >> 2] = v;
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + (lane >> 3);
+                        wrow[row * 8 + ((lane & 7) ^ (row & 7))] = rpre[i];
                     }
+                    __syncwarp();
+                    const float4 *rrow = reinterpret_cast<const float4 *>(sOut + (size_t)m * 128);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 rv = rrow[j ^ (m & 7)];
+                        v[4 * j] += rv.x;
+                        v[4 * j + 1] += rv.y;
+                        v[4 * j + 2] += rv.z;
+                        v[4 * j + 3] += rv.w;
+                    }
+                    __syncwarp();
+                    if (c0 + 32 < g.BN)
+                        res_fetch8(rpre, rbase + c0 + 32, q, lane, tyi * g.TH, txi * g.TW, g.Ho, g.Wo, g.res_cs);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (g.act == 1) v[j] = fmaxf(v[j], 0.f);
+                    else if (g.act == 2) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
+                    if (g.round_out) v[j] = ptx::round_tf32(v[j]);
                 }
                 // one TMA box per 32 channels instead of 32 strided 16-byte stores per instruction
-                if (lane == 0 && q == 0) ptx::tma_store_wait_read();
-                ptx::named_bar_sync(1, 128);
+                // (pixels outside the image are clipped by the TMA store)
+                if (res == nullptr) {
+                    if (lane == 0 && q == 0) ptx::tma_store_wait_read();
+                    ptx::named_bar_sync(1, 128);
+                }
                 float4 *srow = reinterpret_cast<float4 *>(sOut + (size_t)m * 128);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) srow[j ^ (m & 7)] = vout[j];
+                for (int j = 0; j < 8; ++j)
+                    srow[j ^ (m & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 ptx::fence_proxy_async();
                 ptx::named_bar_sync(1, 128);
                 if (lane == 0 && q == 0) {
