@@ -7,9 +7,14 @@
 // 128-pixel A tile and every CTA re-reads all weights.  Here:
 //   * ALL weights of the layer (<= 147 KB) are loaded into shared memory once per CTA, and the
 //     CTA is persistent over output tiles (grid = resident CTAs, static round-robin);
-//   * "column mode": for each kernel column kw and channel chunk, ONE TMA box of (TH+2d) rows is
-//     loaded, and the three vertical taps kh are descriptor offsets into it (kh*d*TW rows is a
-//     multiple of the 8-row swizzle atom), so A traffic drops from 9x to 3*(TH+2)/TH = 3.75x;
+//   * "halo box": for each channel chunk ONE TMA box of (TH+2d) x (TW+2d) pixels is loaded and
+//     all KH x KW taps are operand-descriptor offsets into it.  The tile is 16 rows x 8 pixels, so
+//     an 8-row descriptor group is one tile row and the group stride (SBO) is the box pitch
+//     (TW+2d rows); tcgen05 applies the 128/64/32-byte swizzle to ABSOLUTE shared-memory address
+//     bits -- the same function TMA used when it wrote the box -- so start addresses and group
+//     strides need not be multiples of the 1024-byte swizzle repeat (verified on B200 by
+//     benchmarks/micro/desc_offset.cu).  A traffic drops from 9x (per-tap kernel) and 3.75x (one
+//     box per kernel column, the previous scheme) to (TH+2)(TW+2)/(TH*TW) = 1.41x;
 //   * two TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1;
 //   * optional fused head (convraw.3 1x1 + bias + argmax, exact fp32) in the epilogue, writing
 //     the reference's NCHW output directly -- the [b,H,W,32] intermediate never exists.
@@ -27,7 +32,7 @@ int g_conv_mode = 0;
 namespace {
 
 constexpr int COL_THREADS = 192;
-constexpr int COL_TH = 8, COL_TW = 16;
+constexpr int COL_TH = 16, COL_TW = 8;
 constexpr int HEAD_MAX = 64;
 
 struct ColGeom {
@@ -43,8 +48,6 @@ struct ColGeom {
     int head_cout, head_seg, mask_esz;
 };
 
-template <int KC>
-__host__ __device__ constexpr int col_a_bytes(int dil) { return (COL_TH + 2 * dil) * COL_TW * KC * 4; }
 
 // EPI = number of epilogue warp sets (4 warps each).  ncu showed the stem and layer1 launches
 // epilogue-bound (epilogue warps never wait on tfull; 39 % of samples on the residual load): with
@@ -62,8 +65,10 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_tile = g.BN * ROWB;                    // one [BN][KC] weight tile
     const int n_btiles = g.KW * KH * g.cin_chunks;
-    const int a_bytes = (COL_TH + (KH - 1) * g.dil) * COL_TW * ROWB;
-    const int stage_bytes = a_bytes + (g.resident ? 0 : KH * b_tile);
+    constexpr int PITCH = COL_TW + KH - 1;             // box pitch in pixels (= shared-memory rows); dilation 1 only
+    constexpr int a_box = (COL_TH + KH - 1) * PITCH * ROWB;
+    constexpr int a_bytes = (a_box + 1023) & ~1023;    // stages stay 1024-byte aligned
+    const int stage_bytes = a_bytes + (g.resident ? 0 : KH * KH * b_tile);
     uint8_t *sB = smem;
     uint8_t *sA = smem + (g.resident ? (size_t)n_btiles * b_tile : 0);
     // HEAD: head weights [32][32], 4 KB.  otherwise: one 128-pixel x 32-channel output staging tile
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int tiles_per_img = g.tiles_x * g.tiles_y;
-    const int kb_per_tile = g.KW * g.cin_chunks;
+    const int kb_per_tile = g.cin_chunks;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -124,38 +129,36 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                 ptx::mbar_arrive_expect_tx(hfull, 4096u);
                 ptx::tma_load_2d(sHB, &tmH, hfull, 0, 0);
             }
-            // all weights, once: tile t = ((kw*cin_chunks + cc)*KH + kh) <- packed [Cout][kh][kw][cin]
+            // all weights, once: tile t = (cc*KH + kh)*KW + kw <- packed [Cout][kh][kw][cin]
             if (g.resident) {
                 ptx::mbar_arrive_expect_tx(wfull, (uint32_t)(n_btiles * b_tile));
-                for (int kw = 0; kw < g.KW; ++kw)
-                    for (int cc = 0; cc < g.cin_chunks; ++cc)
-                        for (int kh = 0; kh < KH; ++kh)
-                            ptx::tma_load_2d(sB + (size_t)((kw * g.cin_chunks + cc) * KH + kh) * b_tile, &tmB,
-                                             wfull, (kh * g.KW + kw) * g.cin_pad + cc * KC, 0);
+                for (int cc = 0; cc < g.cin_chunks; ++cc)
+                    for (int t = 0; t < KH * KH; ++t)
+                        ptx::tma_load_2d(sB + (size_t)(cc * KH * KH + t) * b_tile, &tmB, wfull,
+                                         t * g.cin_pad + cc * KC, 0);
             }
             int s = 0;
             uint32_t ph = 0;
+            const uint32_t tx_bytes = (uint32_t)(a_box + (g.resident ? 0 : KH * KH * b_tile));
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
                 const int img = tile / tiles_per_img;
                 const int trem = tile - img * tiles_per_img;
                 const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
                 const int y0 = tyi * COL_TH, x0 = txi * COL_TW;
-                for (int kw = 0; kw < g.KW; ++kw)
-                    for (int cc = 0; cc < g.cin_chunks; ++cc) {
-                        ptx::mbar_wait(&empty[s], ph ^ 1u);
-                        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
-                        uint8_t *st = sA + (size_t)s * stage_bytes;
-                        ptx::tma_load_4d(st, &tmA, &full[s], cc * KC, x0 + (kw - g.pad_l) * g.dil,
-                                         y0 - g.pad_t * g.dil, img);
-                        if (!g.resident)
-                            for (int kh = 0; kh < KH; ++kh)
-                                ptx::tma_load_2d(st + a_bytes + (size_t)kh * b_tile, &tmB, &full[s],
-                                                 (kh * g.KW + kw) * g.cin_pad + cc * KC, 0);
-                        if (++s == g.stages) {
-                            s = 0;
-                            ph ^= 1u;
-                        }
+                for (int cc = 0; cc < g.cin_chunks; ++cc) {
+                    ptx::mbar_wait(&empty[s], ph ^ 1u);
+                    ptx::mbar_arrive_expect_tx(&full[s], tx_bytes);
+                    uint8_t *st = sA + (size_t)s * stage_bytes;
+                    ptx::tma_load_4d(st, &tmA, &full[s], cc * KC, x0 - g.pad_l, y0 - g.pad_t, img);
+                    if (!g.resident)
+                        for (int t = 0; t < KH * KH; ++t)
+                            ptx::tma_load_2d(st + a_bytes + (size_t)t * b_tile, &tmB, &full[s],
+                                             t * g.cin_pad + cc * KC, 0);
+                    if (++s == g.stages) {
+                        s = 0;
+                        ph ^= 1u;
                     }
+                }
             }
         }
     } else if (warp == 1) {
@@ -168,9 +171,11 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
             // instructions per MMA: descriptors are a constant plus a 16-byte-unit offset, the
             // (kh, k) nest is fully unrolled, stage/phase are running counters.
             const uint64_t dbase = ptx::make_kmajor_desc(0, ROWB);
+            // A: 8-row groups are tile rows, one box pitch apart
+            const uint64_t abase = (dbase & ~(0x3fffull << 32)) | ((uint64_t)((uint32_t)(PITCH * ROWB) >> 4) << 32);
             const uint32_t hidesc = ptx::make_idesc_tf32(128, 32);
-            const uint32_t a_kh = (uint32_t)(g.dil * COL_TW * ROWB) >> 4;
-            const uint32_t b_kh = (uint32_t)b_tile >> 4;
+            constexpr uint32_t a_kh = (uint32_t)(PITCH * ROWB) >> 4, a_kw = (uint32_t)ROWB >> 4;   // compile-time tap offsets
+            const uint32_t b_t = (uint32_t)b_tile >> 4;
             const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB);
             int s = 0;
             uint32_t ph = 0, it = 0;
@@ -185,20 +190,24 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                     ptx::tc_fence_after();
                     const uint32_t a0 = sA_u + (uint32_t)s * (uint32_t)stage_bytes;
                     const uint32_t b0 = g.resident ? bres : a0 + (uint32_t)a_bytes;
-                    const uint64_t ad = dbase + (uint64_t)(a0 >> 4);
+                    const uint64_t ad = abase + (uint64_t)(a0 >> 4);
                     const uint64_t bd = dbase + (uint64_t)(b0 >> 4);
                     if (ptx::elect_one()) {
 #pragma unroll
                         for (int kh = 0; kh < KH; ++kh) {
 #pragma unroll
-                            for (int k = 0; k < KC / 8; ++k)
-                                ptx::mma_tf32_ss(tacc, ad + (uint64_t)(kh * a_kh + 2 * k),
-                                                 bd + (uint64_t)(kh * b_kh + 2 * k), idesc, (kb | kh | k) != 0 ? 1u : 0u);
+                            for (int kw = 0; kw < KH; ++kw) {
+#pragma unroll
+                                for (int k = 0; k < KC / 8; ++k)
+                                    ptx::mma_tf32_ss(tacc, ad + (uint64_t)(kh * a_kh + kw * a_kw + 2 * k),
+                                                     bd + (uint64_t)((kh * KH + kw) * b_t + 2 * k), idesc,
+                                                     (kb | kh | kw | k) != 0 ? 1u : 0u);
+                            }
                         }
                         ptx::mma_commit(&empty[s]);
                     }
                     __syncwarp();
-                    bres += (uint32_t)(KH * b_tile);
+                    bres += (uint32_t)(KH * KH * b_tile);
                     if (++s == g.stages) {
                         s = 0;
                         ph ^= 1u;
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
             const float *rbase = nullptr;
             if (res != nullptr) {
                 rbase = res + (((size_t)img * g.Ho + tyi * COL_TH) * g.Wo + txi * COL_TW) * g.res_cs + g.res_co;
-                res_fetch8(rpre, rbase, q, lane, tyi * COL_TH, txi * COL_TW, g.Ho, g.Wo, g.res_cs);
+                res_fetch8<COL_TW>(rpre, rbase, q, lane, tyi * COL_TH, txi * COL_TW, g.Ho, g.Wo, g.res_cs);
             }
             ptx::mbar_wait(&tfull[as], (it >> 1) & 1u);
             ptx::tc_fence_after();
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                         v[4 * j + 3] += rv.w;
                     }
                     __syncwarp();
-                    if (c0 + 32 < g.BN) res_fetch8(rpre, rbase + c0 + 32, q, lane, tyi * COL_TH, txi * COL_TW, g.Ho, g.Wo, g.res_cs);
+                    if (c0 + 32 < g.BN) res_fetch8<COL_TW>(rpre, rbase + c0 + 32, q, lane, tyi * COL_TH, txi * COL_TW, g.Ho, g.Wo, g.res_cs);
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -405,9 +414,10 @@ int col_cin_pad(int Cin) { return Cin == 16 ? 16 : (Cin + 31) / 32 * 32; }   // 
 size_t col_smem(int kc, int ksize, int cin_chunks, int bn, int dil, int stages, int head_cout, bool resident = true)
 {
     const size_t rowb = (size_t)kc * 4;
-    const size_t a = (size_t)(COL_TH + (ksize - 1) * dil) * COL_TW * rowb, bt = (size_t)bn * rowb;
+    const size_t a_box = (size_t)(COL_TH + (ksize - 1) * dil) * (COL_TW + (ksize - 1) * dil) * rowb;
+    const size_t a = (a_box + 1023) & ~(size_t)1023, bt = (size_t)bn * rowb;
     return 1024 + (resident ? (size_t)ksize * ksize * cin_chunks * bt : 0) +
-           (size_t)stages * (a + (resident ? 0 : (size_t)ksize * bt)) +
+           (size_t)stages * (a + (resident ? 0 : (size_t)ksize * ksize * bt)) +
            (size_t)(1 + 2 * stages + 4 + 5) * 8 + 16 + (size_t)(64 + 64) * 4 + 64 + (head_cout ? 4096 : 16384);
 }
 
@@ -422,11 +432,12 @@ cudaError_t set_attr()
 bool conv_col_eligible(const ConvDesc &d)
 {
     // ksize 4 = the space-to-depth form of the 7x7/2 stem: taps at offsets {-2,-1,0,1}
-    if ((d.ksize != 3 && d.ksize != 4) || d.stride != 1 || d.Cout > 64 || d.Cout % 32 != 0) return false;
+    if ((d.ksize != 3 && d.ksize != 4) || d.stride != 1 || d.dilation != 1 || d.Cout > 64 || d.Cout % 32 != 0)
+        return false;
     const int kc = col_kc(d.Cin);
     if (d.Cin % kc != 0) return false;
     if ((d.ksize == 4) != (kc == 16)) return false;   // instantiated: 4x4 taps with 16 channels, 3x3 otherwise
-    return col_smem(kc, d.ksize, (d.Cin + kc - 1) / kc, d.Cout, d.dilation, 3, HEAD_MAX, false) <= SMEM_LIMIT;
+    return col_smem(kc, d.ksize, (d.Cin + kc - 1) / kc, d.Cout, d.dilation, 2, HEAD_MAX, false) <= SMEM_LIMIT;
 }
 
 size_t conv_col_plan_size() { return sizeof(ColPlan); }
@@ -464,16 +475,16 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     g.head_cout = head ? head->cout : 0;
     g.head_seg = head ? head->seg_dim : 0;
     g.mask_esz = head ? head->mask_esz : 0;
-    // Resident weights whenever at least 3 A stages still fit next to them (measured on conv2s.0:
-    // 0.43 ms resident with 3 stages vs 0.49 ms streaming with 6); otherwise the KH weight tiles
-    // of a K-block travel with its A box.  Two CTAs per SM when the footprint allows.
+    // Resident weights whenever at least 2 A stages (one channel chunk with all its taps each) still
+    // fit next to them; otherwise the KH*KW weight tiles of a chunk travel with its A box.  Two CTAs
+    // per SM when the footprint allows.
     int stages = 8;
     bool resident = true;
     while (stages > 2 && col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, true) > SMEM_LIMIT)
         --stages;
     static const int min_res_stages = [] {
-        const char *e = getenv("PVNET_COL_RESIDENT_MIN_STAGES");   // tuning knob, default 3
-        return e ? atoi(e) : 3;
+        const char *e = getenv("PVNET_COL_RESIDENT_MIN_STAGES");   // tuning knob, default 2
+        return e ? atoi(e) : 2;
     }();
     if (stages < min_res_stages || col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, true) > SMEM_LIMIT) {
         resident = false;
@@ -493,7 +504,8 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
         cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.b};
         cuuint64_t strides[3] = {(cuuint64_t)d.in_cs * 4, (cuuint64_t)d.W * d.in_cs * 4,
                                  (cuuint64_t)d.H * d.W * d.in_cs * 4};
-        cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)COL_TW, (cuuint32_t)(COL_TH + (d.ksize - 1) * d.dilation), 1};
+        cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(COL_TW + (d.ksize - 1) * d.dilation),
+                             (cuuint32_t)(COL_TH + (d.ksize - 1) * d.dilation), 1};
         int rc = tma_encode(&p->tmA, base, 4, dims, strides, box, kc * 4);
         if (rc) return rc;
     }

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
             const float *rbase = nullptr;
             if (res != nullptr) {
                 rbase = res + (((size_t)img * g.Ho + tyi * g.TH) * g.Wo + txi * g.TW) * g.res_cs + g.res_co + n0;
-                res_fetch8(rpre, rbase, q, lane, tyi * g.TH, txi * g.TW, g.Ho, g.Wo, g.res_cs);
+                res_fetch8<16>(rpre, rbase, q, lane, tyi * g.TH, txi * g.TW, g.Ho, g.Wo, g.res_cs);
             }
             ptx::mbar_wait(&tfull[as], (it >> 1) & 1u);
             ptx::tc_fence_after();
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
                     }
                     __syncwarp();
                     if (c0 + 32 < g.BN)
-                        res_fetch8(rpre, rbase + c0 + 32, q, lane, tyi * g.TH, txi * g.TW, g.Ho, g.Wo, g.res_cs);
+                        res_fetch8<16>(rpre, rbase + c0 + 32, q, lane, tyi * g.TH, txi * g.TW, g.Ho, g.Wo, g.res_cs);
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {

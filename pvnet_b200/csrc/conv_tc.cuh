@@ -59,19 +59,22 @@ int launch_head(const float *in, const float *w, const float *bias, float *out, 
                 int seg_dim, int Cout, int b, int H, int W, cudaStream_t s);
 
 #ifdef __CUDACC__
-// Coalesced residual fetch shared by the conv epilogues (8 x 16 pixel tiles, one pixel per thread,
-// epilogue warp q owns tile rows 2q and 2q+1).  Load i of lane l reads the 16-byte chunk (l % 8) of
-// warp-pixel 4*i + l/8, i.e. four full 128-byte lines per instruction instead of 32 strided
-// sectors.  `base` points at (tile origin, first channel of the 32-channel group); out-of-image
-// pixels read nothing.
+// Coalesced residual fetch shared by the conv epilogues (128-pixel tiles TW pixels wide, one pixel
+// per thread, epilogue warp q owns tile rows q*32/TW ...).  Load i of lane l reads the 16-byte chunk
+// (l % 8) of warp-pixel 4*i + l/8, i.e. four full 128-byte lines per instruction instead of 32
+// strided sectors.  `base` points at (tile origin, first channel of the 32-channel group);
+// out-of-image pixels read nothing.
+template <int TW>
 __device__ __forceinline__ void res_fetch8(float4 (&dst)[8], const float *base, int q, int lane, int y0, int x0,
                                            int Ho, int Wo, int res_cs)
 {
-    const int yy = y0 + 2 * q, xx = x0 + (lane >> 3);
-    const float *p = base + ((size_t)(2 * q) * Wo + (lane >> 3)) * res_cs + (lane & 7) * 4;
+    static_assert(TW == 8 || TW == 16, "tile width");
+    constexpr int ROWS = 32 / TW;                       // tile rows per warp
+    const int yy = y0 + ROWS * q, xx = x0 + (lane >> 3);
+    const float *p = base + ((size_t)(ROWS * q) * Wo + (lane >> 3)) * res_cs + (lane & 7) * 4;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int dy = i >> 2, dx = (i & 3) * 4;
+        const int dy = (4 * i) / TW, dx = (4 * i) % TW;
         dst[i] = (yy + dy < Ho && xx + dx < Wo)
                      ? __ldg(reinterpret_cast<const float4 *>(p + ((size_t)dy * Wo + dx) * res_cs))
                      : make_float4(0.f, 0.f, 0.f, 0.f);

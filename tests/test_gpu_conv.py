@@ -96,12 +96,23 @@ def test_conv_persistent_many_items_per_cta():
     (1, 40, 48, 40, 32, 3, 1, 1, 2, False),     # convraw.0: Cin=40 -> 8-channel chunks, LeakyReLU
     (1, 48, 80, 128, 32, 3, 1, 1, 2, False),    # conv2s.0 shape (weights 147 KB resident)
     (3, 64, 96, 64, 64, 3, 1, 1, 1, False),     # many tiles per CTA: exercises the persistent loop / TMEM ping-pong
-    (1, 24, 40, 32, 32, 3, 1, 2, 0, False),     # dilation 2 in column mode
+    (1, 32, 40, 192, 64, 3, 1, 1, 2, False),    # conv4s.0 shape: 442 KB of weights -> tiles stream with the A boxes
+    (2, 20, 44, 64, 64, 3, 1, 1, 1, True),      # width and height not multiples of the 16 x 8 tile, residual
 ])
 def test_conv_column_kernel_vs_torch(cfg):
     pc.set_mode(pc.MODE_COLUMN)
     try:
         _run_case(*cfg)
+    finally:
+        pc.set_mode(pc.MODE_AUTO)
+
+
+def test_conv_column_kernel_rejects_dilation():
+    """The halo-box kernel is dilation-1 only; forcing it on a dilated layer is an error, not a fallback."""
+    pc.set_mode(pc.MODE_COLUMN)
+    try:
+        with pytest.raises((RuntimeError, ValueError)):
+            _run_case(1, 24, 40, 32, 32, 3, 1, 2, 0, False)
     finally:
         pc.set_mode(pc.MODE_AUTO)
 
