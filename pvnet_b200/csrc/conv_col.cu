@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
     // HEAD: head weights [32][32], 4 KB.  otherwise: one 128-pixel x 32-channel output staging tile
     // (128B-swizzled rows) for the TMA store of the epilogue, 16 KB
     uint8_t *sHB = sA + (size_t)g.stages * stage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sHB + (HEAD ? 4096 : 16384));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sHB + (HEAD ? 4096 : 32768 * EPI));
     uint64_t *wfull = bars;
     uint64_t *full = bars + 1;
     uint64_t *empty = full + g.stages;
@@ -254,6 +254,8 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
         const int m = q * 32 + lane;
         const int ty = m / COL_TW, tx = m - ty * COL_TW;
         const int epi_set = (warp - 2) >> 2;                     // 0, or 1 when EPI == 2
+        const uint32_t stage_u = ptx::smem_u32(sHB) + (uint32_t)epi_set * 32768u;   // 4 warps x 2 buffers x 4 KB
+        uint32_t nstore = 0;
         uint32_t it = (uint32_t)epi_set;
         for (int tile = blockIdx.x + epi_set * gridDim.x; tile < g.total_tiles; tile += EPI * gridDim.x, it += EPI) {
             const uint32_t as = it & 1u;
@@ -295,34 +297,18 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                     v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bv.z;
                     v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bv.w;
                 }
-                if (!HEAD && res != nullptr) {
-                    if (lane == 0 && q == 0) ptx::tma_store_wait_read();      // previous box has left the tile
-                    ptx::named_bar_sync(1, 128);
-                    float4 *wrow = reinterpret_cast<float4 *>(sHB + (size_t)(q * 32) * 128);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = i * 4 + (lane >> 3);
-                        wrow[row * 8 + ((lane & 7) ^ (row & 7))] = rpre[i];
-                    }
+                // staging buffer of this chunk: the store issued two chunks ago has left it
+                const uint32_t buf = stage_u + (uint32_t)(q * 8192) + (nstore & 1u) * 4096u;
+                if (!HEAD) {
+                    if (lane == 0) ptx::tma_store_wait_read1();
                     __syncwarp();
-                    const float4 *srow = reinterpret_cast<const float4 *>(sHB + (size_t)m * 128);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 rv = srow[j ^ (m & 7)];
-                        v[4 * j] += rv.x;
-                        v[4 * j + 1] += rv.y;
-                        v[4 * j + 2] += rv.z;
-                        v[4 * j + 3] += rv.w;
+                    if (res != nullptr) {
+                        epi_add_residual(v, rpre, buf, lane);
+                        if (c0 + 32 < g.BN)
+                            res_fetch8<COL_TW>(rpre, rbase + c0 + 32, q, lane, tyi * COL_TH, txi * COL_TW, g.Ho, g.Wo, g.res_cs);
                     }
-                    __syncwarp();
-                    if (c0 + 32 < g.BN) res_fetch8<COL_TW>(rpre, rbase + c0 + 32, q, lane, tyi * COL_TH, txi * COL_TW, g.Ho, g.Wo, g.res_cs);
                 }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (g.act == 1) v[j] = fmaxf(v[j], 0.f);
-                    else if (g.act == 2) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
-                    if (g.round_out) v[j] = ptx::round_tf32(v[j]);
-                }
+                epi_activate(v, g.act, g.round_out);
                 if (HEAD) {
                     // convraw.3 (model_repository.py:57) on the tensor cores: the activated tile goes
                     // back to TMEM as the A operand of a 128x32x32 MMA issued by the MMA warp, then
@@ -362,29 +348,22 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                         }
                     }
                 } else {
-                    // Stores go through shared memory and ONE TMA box per 32 channels: a thread owns a
-                    // pixel, so direct 16-byte stores hit 32 different 256..768-byte-strided records per
-                    // instruction (LSU-transaction bound: two epilogue warp sets gave no speed-up).
-                    // Row m of the staging tile is 128 B; 16-byte chunk j sits at (j ^ (m & 7)).
-                    if (res == nullptr) {
-                        if (lane == 0 && q == 0) ptx::tma_store_wait_read();  // previous box has left the tile
-                        ptx::named_bar_sync(1, 128);
-                    }
-                    float4 *srow = reinterpret_cast<float4 *>(sHB + (size_t)m * 128);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        srow[j ^ (m & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    // Stores go through shared memory and one TMA box per warp and 32 channels: a thread
+                    // owns a pixel, so direct 16-byte stores hit 32 different 256..768-byte-strided
+                    // records per instruction (LSU-transaction bound).
+                    epi_stage(v, buf, lane);
                     ptx::fence_proxy_async();
-                    ptx::named_bar_sync(1, 128);
-                    if (lane == 0 && q == 0) {
-                        ptx::tma_store_4d(&tmO, sHB, c0, txi * COL_TW, tyi * COL_TH, img);
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_4d_u32(&tmO, buf, c0, txi * COL_TW, tyi * COL_TH + q * (32 / COL_TW), img);
                         ptx::tma_store_commit();
                     }
+                    ++nstore;
                 }
             }
         }
+        if (!HEAD && lane == 0) ptx::tma_store_wait_all();      // every issuing lane drains its own bulk groups
     }
-    if (!HEAD && warp == 4 && lane == 0) ptx::tma_store_wait_all();   // the thread that issued the stores (q == 0)
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -418,7 +397,7 @@ size_t col_smem(int kc, int ksize, int cin_chunks, int bn, int dil, int stages, 
     const size_t a = (a_box + 1023) & ~(size_t)1023, bt = (size_t)bn * rowb;
     return 1024 + (resident ? (size_t)ksize * ksize * cin_chunks * bt : 0) +
            (size_t)stages * (a + (resident ? 0 : (size_t)ksize * ksize * bt)) +
-           (size_t)(1 + 2 * stages + 4 + 5) * 8 + 16 + (size_t)(64 + 64) * 4 + 64 + (head_cout ? 4096 : 16384);
+           (size_t)(1 + 2 * stages + 4 + 5) * 8 + 16 + (size_t)(64 + 64) * 4 + 64 + (head_cout ? 4096 : 32768);
 }
 
 template <int KC, bool HEAD, int KH, int EPI>
@@ -520,7 +499,7 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
         cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.b};
         cuuint64_t strides[3] = {(cuuint64_t)d.out_cs * 4, (cuuint64_t)d.W * d.out_cs * 4,
                                  (cuuint64_t)d.H * d.W * d.out_cs * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)COL_TW, (cuuint32_t)COL_TH, 1};
+        cuuint32_t box[4] = {32, (cuuint32_t)COL_TW, (cuuint32_t)(32 / COL_TW), 1};     // one epilogue warp: 32 pixels
         int rc = tma_encode(&p->tmO, d.out + d.out_co, 4, dims, strides, box, 128);
         if (rc) return rc;
     } else {

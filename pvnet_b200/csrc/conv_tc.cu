@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = g.BN * KC * 4;
     const int stage_bytes = Cfg::A_BYTES + b_bytes;
-    uint8_t *sOut = smem + (size_t)STAGES * stage_bytes;   // 128 px x 32 ch staging tile of the TMA store, 16 KB
-    uint64_t *full = reinterpret_cast<uint64_t *>(sOut + 16384);
+    uint8_t *sOut = smem + (size_t)STAGES * stage_bytes;   // TMA-store staging: 4 epilogue warps x 2 buffers x 4 KB
+    uint64_t *full = reinterpret_cast<uint64_t *>(sOut + 32768);
     uint64_t *empty = full + STAGES;
     uint64_t *tfull = empty + STAGES;      // [2]
     uint64_t *tempty = tfull + 2;          // [2]
@@ -394,8 +394,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
         }
     } else {
         const int q = warp & 3;
-        const int m = q * 32 + lane;
-        uint32_t it = 0;
+        const uint32_t stage_u = ptx::smem_u32(sOut) + (uint32_t)(q * 8192);
+        uint32_t it = 0, nstore = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t as = it & 1u;
             const int n_tile = item % n_tiles_n, m_tile = item / n_tiles_n;
@@ -434,54 +434,30 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
                     v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bv.z;
                     v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bv.w;
                 }
+                // Stores go through shared memory and one TMA box per warp and 32 channels (a thread owns
+                // a pixel: direct 16-byte stores would hit 32 strided records per instruction); pixels
+                // outside the image are clipped by the TMA store.  Two buffers per warp: the store issued
+                // two chunks ago has left the one used now.
+                const uint32_t buf = stage_u + (nstore & 1u) * 4096u;
+                if (lane == 0) ptx::tma_store_wait_read1();
+                __syncwarp();
                 if (res != nullptr) {
-                    if (lane == 0 && q == 0) ptx::tma_store_wait_read();      // previous box has left the tile
-                    ptx::named_bar_sync(1, 128);
-                    float4 *wrow = reinterpret_cast<float4 *>(sOut + (size_t)(q * 32) * 128);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = i * 4 + (lane >> 3);
-                        wrow[row * 8 + ((lane & 7) ^ (row & 7))] = rpre[i];
-                    }
-                    __syncwarp();
-                    const float4 *rrow = reinterpret_cast<const float4 *>(sOut + (size_t)m * 128);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 rv = rrow[j ^ (m & 7)];
-                        v[4 * j] += rv.x;
-                        v[4 * j + 1] += rv.y;
-                        v[4 * j + 2] += rv.z;
-                        v[4 * j + 3] += rv.w;
-                    }
-                    __syncwarp();
+                    epi_add_residual(v, rpre, buf, lane);
                     if (c0 + 32 < g.BN)
                         res_fetch8<16>(rpre, rbase + c0 + 32, q, lane, tyi * g.TH, txi * g.TW, g.Ho, g.Wo, g.res_cs);
                 }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (g.act == 1) v[j] = fmaxf(v[j], 0.f);
-                    else if (g.act == 2) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
-                    if (g.round_out) v[j] = ptx::round_tf32(v[j]);
-                }
-                // one TMA box per 32 channels instead of 32 strided 16-byte stores per instruction
-                // (pixels outside the image are clipped by the TMA store)
-                if (res == nullptr) {
-                    if (lane == 0 && q == 0) ptx::tma_store_wait_read();
-                    ptx::named_bar_sync(1, 128);
-                }
-                float4 *srow = reinterpret_cast<float4 *>(sOut + (size_t)m * 128);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    srow[j ^ (m & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                epi_activate(v, g.act, g.round_out);
+                epi_stage(v, buf, lane);
                 ptx::fence_proxy_async();
-                ptx::named_bar_sync(1, 128);
-                if (lane == 0 && q == 0) {
-                    ptx::tma_store_4d(&tmO, sOut, n0 + c0, txi * g.TW, tyi * g.TH, img);
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_4d_u32(&tmO, buf, n0 + c0, txi * g.TW, tyi * g.TH + 2 * q, img);
                     ptx::tma_store_commit();
                 }
+                ++nstore;
             }
         }
-        if (q == 0 && lane == 0) ptx::tma_store_wait_all();
+        if (lane == 0) ptx::tma_store_wait_all();      // every issuing lane drains its own bulk groups
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -645,11 +621,11 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
     p->persist = (p->mc == 0 && g_conv_persist) ? 1 : 0;
     p->tmO = p->tmB;
     if (p->persist) {
-        p->smem += 16384;                       // output staging tile of the TMA-store epilogue
+        p->smem += 32768;                       // staging buffers of the TMA-store epilogue
         cuuint64_t odims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)d.b};
         cuuint64_t ostr[3] = {(cuuint64_t)d.out_cs * 4, (cuuint64_t)g.Wo * d.out_cs * 4,
                               (cuuint64_t)g.Ho * g.Wo * d.out_cs * 4};
-        cuuint32_t obox[4] = {32, (cuuint32_t)g.TW, (cuuint32_t)g.TH, 1};
+        cuuint32_t obox[4] = {32, (cuuint32_t)g.TW, (cuuint32_t)(32 / g.TW), 1};      // one epilogue warp: 32 pixels
         int rc = tma_encode(&p->tmO, d.out + d.out_co, 4, odims, ostr, obox, 128);
         if (rc) return rc;
         int per_sm = (int)((227 * 1024) / p->smem);
@@ -669,7 +645,7 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
 
 int conv_launch(const ConvPlan &p, cudaStream_t s)
 {
-    const int max_smem = (int)ConvCfg<32>::smem_bytes(256) + 16384;
+    const int max_smem = (int)ConvCfg<32>::smem_bytes(256) + 32768;
     const void *fn = p.mc == 2 ? (const void *)k_conv_tc<32, 2>
                      : p.mc == 1 ? (const void *)k_conv_tc<32, 1>
                      : p.persist ? (const void *)k_conv_tap_p<32> : (const void *)k_conv_tc<32, 0>;
