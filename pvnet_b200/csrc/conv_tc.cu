@@ -42,7 +42,31 @@ struct ConvGeom {
     int round_out;  // round stored values to tf32 (they feed another tensor-core conv)
     signed char tap_map[9];
     short tap_ox[9], tap_oy[9];
+    // persistent kernel, tail split: items [0, n_full) are (M tile, BN-channel) tiles; each of the
+    // remaining (M tile, N tile) pairs is cut into tail_split items of tail_bn channels so that the
+    // last, partially filled round of the static schedule costs a fraction of a full round
+    int n_full, n_items, tail_bn, tail_split;
 };
+
+// item index -> (M tile, first output channel, channels) of the persistent schedule
+struct ConvItem {
+    int m_tile, n0, bn;
+};
+__device__ __forceinline__ ConvItem conv_item(const ConvGeom &g, int item, int n_tiles_n)
+{
+    ConvItem r;
+    int base = item, sub = 0;
+    r.bn = g.BN;
+    if (item >= g.n_full) {
+        const int j = item - g.n_full;
+        base = g.n_full + j / g.tail_split;
+        sub = j - (j / g.tail_split) * g.tail_split;
+        r.bn = g.tail_bn;
+    }
+    r.m_tile = base / n_tiles_n;                       // N tile fastest
+    r.n0 = (base - r.m_tile * n_tiles_n) * g.BN + sub * g.tail_bn;
+    return r;
+}
 
 struct AMaps {
     CUtensorMap m[4];
@@ -288,6 +312,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 template <int KC>
 __global__ void __launch_bounds__(CONV_THREADS, 2)
     k_conv_tap_p(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmB2 /* {KC, tail_bn} boxes of the same weights */,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvGeom g,
                  const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out)
 {
@@ -307,7 +332,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = g.tiles_x * g.tiles_y;
     const int n_tiles_n = g.Cout / g.BN;
-    const int n_items = g.total_m_tiles * n_tiles_n;
+    const int n_items = g.n_items;
     const int nkb = g.taps * g.cin_chunks;
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(2 * g.BN)) tmem_cols <<= 1;
@@ -339,19 +364,21 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
             int s = 0;
             uint32_t ph = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int n_tile = item % n_tiles_n, m_tile = item / n_tiles_n;   // N tile fastest
-                const int img = m_tile / tiles_per_img;
-                const int trem = m_tile - img * tiles_per_img;
+                const ConvItem ci = conv_item(g, item, n_tiles_n);
+                const int img = ci.m_tile / tiles_per_img;
+                const int trem = ci.m_tile - img * tiles_per_img;
                 const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
-                const int y0 = tyi * g.TH, x0 = txi * g.TW, n0 = n_tile * g.BN;
+                const int y0 = tyi * g.TH, x0 = txi * g.TW;
+                const CUtensorMap *bmap = ci.bn == g.BN ? &tmB : &tmB2;
+                const uint32_t tx_bytes = (uint32_t)(Cfg::A_BYTES + ci.bn * KC * 4);
                 for (int tap = 0; tap < g.taps; ++tap)
                     for (int cc = 0; cc < g.cin_chunks; ++cc) {
                         ptx::mbar_wait(&empty[s], ph ^ 1u);
-                        ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+                        ptx::mbar_arrive_expect_tx(&full[s], tx_bytes);
                         uint8_t *sa = smem + (size_t)s * stage_bytes;
                         ptx::tma_load_4d(sa, &amaps.m[g.tap_map[tap]], &full[s], cc * KC, x0 + g.tap_ox[tap],
                                          y0 + g.tap_oy[tap], img);
-                        ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], tap * g.cin_pad + cc * KC, n0);
+                        ptx::tma_load_2d(sa + Cfg::A_BYTES, bmap, &full[s], tap * g.cin_pad + cc * KC, ci.n0);
                         if (++s == STAGES) {
                             s = 0;
                             ph ^= 1u;
@@ -360,13 +387,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = ptx::make_idesc_tf32(128, g.BN);
         const uint64_t dbase = ptx::make_kmajor_desc(0, Cfg::SWIZZLE);
         const uint32_t smem_u = ptx::smem_u32(smem);
         int s = 0;
         uint32_t ph = 0, it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t as = it & 1u;
+            const uint32_t idesc = ptx::make_idesc_tf32(128, item < g.n_full ? g.BN : g.tail_bn);
             ptx::mbar_wait(&tempty[as], ((it >> 1) & 1u) ^ 1u);
             ptx::tc_fence_after();
             const uint32_t tacc = tmem_base + as * (uint32_t)g.BN;
@@ -398,11 +425,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
         uint32_t it = 0, nstore = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t as = it & 1u;
-            const int n_tile = item % n_tiles_n, m_tile = item / n_tiles_n;
-            const int img = m_tile / tiles_per_img;
-            const int trem = m_tile - img * tiles_per_img;
+            const ConvItem ci = conv_item(g, item, n_tiles_n);
+            const int img = ci.m_tile / tiles_per_img;
+            const int trem = ci.m_tile - img * tiles_per_img;
             const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
-            const int n0 = n_tile * g.BN;
+            const int n0 = ci.n0, bn = ci.bn;
             // Residual: fetched COALESCED (load i of lane l = pixel 4i + l/8 of this warp, 16-byte
             // chunk l%8: four full 128-byte lines per instruction) and handed to the pixel-owning lanes
             // through this warp's rows of the staging tile; the first 32 channels are issued before
@@ -416,11 +443,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
             ptx::mbar_wait(&tfull[as], (it >> 1) & 1u);
             ptx::tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)g.BN;
-            for (int c0 = 0; c0 < g.BN; c0 += 32) {
+            for (int c0 = 0; c0 < bn; c0 += 32) {
                 uint32_t r[32];
                 ptx::tmem_ld_32x32b_x32(tacc + (uint32_t)c0, r);
                 ptx::tmem_ld_wait();
-                if (c0 + 32 >= g.BN) {      // everything is in registers: give the TMEM stage back
+                if (c0 + 32 >= bn) {      // everything is in registers: give the TMEM stage back
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tempty[as]);
@@ -443,7 +470,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
                 __syncwarp();
                 if (res != nullptr) {
                     epi_add_residual(v, rpre, buf, lane);
-                    if (c0 + 32 < g.BN)
+                    if (c0 + 32 < bn)
                         res_fetch8<16>(rpre, rbase + c0 + 32, q, lane, tyi * g.TH, txi * g.TW, g.Ho, g.Wo, g.res_cs);
                 }
                 epi_activate(v, g.act, g.round_out);
@@ -514,7 +541,7 @@ int tma_encode(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dim
 // long as the pointers and shapes stay the same).
 struct ConvPlan {
     AMaps amaps;
-    CUtensorMap tmB, tmO;
+    CUtensorMap tmB, tmB2, tmO;
     ConvGeom g;
     int kc, mc, persist;
     dim3 grid;
@@ -632,10 +659,43 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
         if (per_sm > 2) per_sm = 2;
         if (per_sm * 2 * g.BN > 512) per_sm = 512 / (2 * g.BN);      // TMEM: two accumulator stages per CTA
         if (per_sm < 1) per_sm = 1;
-        long long grid = (long long)sm_count() * per_sm;
+        const long long G = (long long)sm_count() * per_sm;
         const long long items = (long long)g.total_m_tiles * (d.Cout / g.BN);
-        if (grid > items) grid = items;
+        // Tail split.  The schedule is static round-robin, so `rem` leftover items would cost a whole
+        // extra round on `rem` CTAs while the others idle (600 items on 148 CTAs: 5 rounds for 4.05
+        // rounds of work).  Cut each leftover item into `split` channel slices: the last round then
+        // lasts floor(tail_bn)/floor(BN) of a full one (MMA issue floors in cycles per K=8 step,
+        // benchmarks/micro/mma_rate.cu: N=256 128, N=128 64, N=64 48, N=32 40).
+        const long long rem = items % G;
+        int split = 1;
+        static const int env_tail = [] {
+            const char *e = getenv("PVNET_CONV_TAIL_SPLIT");     // tuning knob: 0 disables the tail split
+            return e ? atoi(e) : 1;
+        }();
+        if (rem > 0 && env_tail) {
+            auto floor_cycles = [](int n) { return n >= 256 ? 128 : (n >= 128 ? 64 : (n >= 64 ? 48 : 40)); };
+            int best_cost = floor_cycles(g.BN);
+            for (int sp = 2; g.BN / sp >= 32 && rem * sp <= G; sp *= 2)
+                if (floor_cycles(g.BN / sp) < best_cost) {
+                    best_cost = floor_cycles(g.BN / sp);
+                    split = sp;
+                }
+        }
+        g.tail_split = split;
+        g.tail_bn = g.BN / split;
+        g.n_full = (int)(split > 1 ? items - rem : items);
+        g.n_items = (int)(g.n_full + (split > 1 ? rem * split : 0));
+        long long grid = G;
+        if (grid > g.n_items) grid = g.n_items;
         p->grid = dim3((unsigned)grid);
+        p->tmB2 = p->tmB;
+        if (split > 1) {
+            cuuint64_t dims[2] = {(cuuint64_t)g.taps * g.cin_pad, (cuuint64_t)d.Cout};
+            cuuint64_t strides[1] = {(cuuint64_t)g.taps * g.cin_pad * 4};
+            cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)g.tail_bn};
+            rc = tma_encode(&p->tmB2, d.w, 2, dims, strides, box, swz);
+            if (rc) return rc;
+        }
     }
     p->bias = d.bias;
     p->res = d.res;
@@ -669,7 +729,7 @@ int conv_launch(const ConvPlan &p, cudaStream_t s)
         else
             PV_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<32, 1>, p.amaps, p.tmB, p.g, p.bias, p.res, p.out));
     } else if (p.persist) {
-        k_conv_tap_p<32><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.tmO, p.g, p.bias, p.res, p.out);
+        k_conv_tap_p<32><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.tmB2, p.tmO, p.g, p.bias, p.res, p.out);
     } else {
         k_conv_tc<32, 0><<<p.grid, CONV_THREADS, p.smem, s>>>(p.amaps, p.tmB, p.g, p.bias, p.res, p.out);
     }
