@@ -299,17 +299,33 @@ __global__ void __launch_bounds__(256)
     hyp[((size_t)b * vn + vi) * hn + hi] = out;
 }
 
+// fast-path helpers of the vote kernels
+constexpr int VT_GROUP = 4;       // pixels per guard-band check
+__device__ __forceinline__ uint32_t ptx_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// cnt += (a > b): one FSETP + one predicated IADD (the C form compiled to add + predicated move + move)
+__device__ __forceinline__ void count_if_gt(int &cnt, float a, float b)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "f"(a), "f"(b));
+}
+
 // ------------------------------------------------------------------ the vote
 // Persistent CTAs walk items (pixel tile, keypoint, hypothesis group).  Warps are
 // split wh (hypothesis groups of 128) x wp (pixel interleave); each lane owns
 // VT_HPL hypotheses; pixels come from shared memory as one broadcast LDS.128.
-__global__ void __launch_bounds__(VT_THREADS, 3)
+template <int HPL, int TILE>
+__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
     k_vote(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
            const int *__restrict__ tn_arr, int npx, int nb, int vn, int hn, int wh,
            const float2 *__restrict__ hyp, int *__restrict__ counts, float thresh, float t2, float band)
 {
-    __shared__ float4 tile[VT_TILE];
-    __shared__ int red[VT_WARPS * 32 * VT_HPL];
+    __shared__ float4 tile[TILE];
+    __shared__ int red[VT_WARPS * 32 * HPL];
     __shared__ int tile_prefix[VT_MAX_B + 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -317,13 +333,13 @@ __global__ void __launch_bounds__(VT_THREADS, 3)
         int acc = 0;
         for (int i = 0; i < nb; ++i) {
             tile_prefix[i] = acc;
-            acc += (tn_arr[i] + VT_TILE - 1) / VT_TILE;
+            acc += (tn_arr[i] + TILE - 1) / TILE;
         }
         tile_prefix[nb] = acc;
     }
     __syncthreads();
     const int total_tiles = tile_prefix[nb];
-    const int HC = wh * 32 * VT_HPL;               // hypotheses per item
+    const int HC = wh * 32 * HPL;               // hypotheses per item
     const int hcn = (hn + HC - 1) / HC;
     const long long n_items = (long long)total_tiles * vn * hcn;
     const int wp_count = VT_WARPS / wh;
@@ -341,8 +357,8 @@ __global__ void __launch_bounds__(VT_THREADS, 3)
         }
         const int b = lo;
         const int tn = tn_arr[b];
-        const int t0 = (g - tile_prefix[b]) * VT_TILE;
-        const int len = min(VT_TILE, tn - t0);
+        const int t0 = (g - tile_prefix[b]) * TILE;
+        const int len = min(TILE, tn - t0);
         const long long vbase = (long long)b * st.s[0] + (long long)k * st.s[3];
 
         // ---- stage: gather this tile's pixels and unit directions
@@ -361,11 +377,11 @@ __global__ void __launch_bounds__(VT_THREADS, 3)
         __syncthreads();
 
         // ---- this lane's hypotheses
-        const int hbase = hc * HC + my_wh * (32 * VT_HPL);
-        float hx[VT_HPL], hy[VT_HPL];
-        int cnt[VT_HPL];
+        const int hbase = hc * HC + my_wh * (32 * HPL);
+        float hx[HPL], hy[HPL];
+        int cnt[HPL];
 #pragma unroll
-        for (int j = 0; j < VT_HPL; ++j) {
+        for (int j = 0; j < HPL; ++j) {
             const int h = hbase + j * 32 + lane;
             float2 hp = make_float2(3.0e8f, 3.0e8f);   // padding hypothesis, count discarded
             if (h < hn) hp = __ldg(hyp + ((size_t)b * vn + k) * hn + h);
@@ -374,38 +390,59 @@ __global__ void __launch_bounds__(VT_THREADS, 3)
             cnt[j] = 0;
         }
 
-        // ---- sweep the tile
-#pragma unroll 2
-        for (int i = my_wp; i < len; i += wp_count) {
-            const float4 p = tile[i];
-            unsigned unc = 0;
+        // ---- sweep the tile, VT_GROUP pixels at a time.  The fast path only counts and ORs one
+        // "some test fell inside the guard band" flag per lane; when any lane of the warp raises it
+        // (rare), the group is re-walked and exactly those tests are re-decided with the reference's
+        // own instruction sequence (they were NOT counted by the fast path: |e| <= bd excludes e > bd).
+        const uint32_t tile_u = ptx_smem_u32(tile);
+        auto sweep = [&](int i0, int n) {           // pixels i0, i0 + wp_count, ... (n of them, n <= VT_GROUP)
+            bool unc = false;
 #pragma unroll
-            for (int j = 0; j < VT_HPL; ++j) {
-                const float dx = hx[j] - p.x, dy = hy[j] - p.y;
-                const float d2 = fmaf(dx, dx, dy * dy);
-                const float num = fmaf(dx, p.z, dy * p.w);
-                const float s = num * fabsf(num);
-                const float e = fmaf(-t2, d2, s);
-                const float bd = fmaf(band, d2, 4e-12f);
-                cnt[j] += (e > bd) ? 1 : 0;
-                unc |= (fabsf(e) > bd) ? 0u : (1u << j);
-            }
-            if (__any_sync(0xffffffffu, unc != 0)) {
-                if (unc) {
-                    const long long off = vbase + (long long)p.y * st.s[1] + (long long)p.x * st.s[2];
-                    const float nx = __ldg(vertex + off), ny = __ldg(vertex + off + st.s[4]);
+            for (int u = 0; u < VT_GROUP; ++u) {
+                if (u < n) {
+                    const float4 p = lds_f4(tile_u + (uint32_t)(i0 + u * wp_count) * 16u);
 #pragma unroll
-                    for (int j = 0; j < VT_HPL; ++j)
-                        if (unc & (1u << j))
-                            cnt[j] += exact_inlier(nx, ny, p.x, p.y, hx[j], hy[j], thresh) ? 1 : 0;
+                    for (int j = 0; j < HPL; ++j) {
+                        const float dx = hx[j] - p.x, dy = hy[j] - p.y;
+                        const float d2 = fmaf(dx, dx, dy * dy);
+                        const float num = fmaf(dx, p.z, dy * p.w);
+                        const float s = num * fabsf(num);
+                        const float e = fmaf(-t2, d2, s);
+                        const float bd = fmaf(band, d2, 4e-12f);
+                        count_if_gt(cnt[j], e, bd);
+                        unc |= !(fabsf(e) > bd);
+                    }
                 }
             }
-        }
+            if (__any_sync(0xffffffffu, unc)) {
+                if (unc) {
+                    for (int u = 0; u < n; ++u) {
+                        const float4 p = tile[i0 + u * wp_count];
+                        const long long off = vbase + (long long)p.y * st.s[1] + (long long)p.x * st.s[2];
+                        const float nx = __ldg(vertex + off), ny = __ldg(vertex + off + st.s[4]);
+#pragma unroll
+                        for (int j = 0; j < HPL; ++j) {
+                            const float dx = hx[j] - p.x, dy = hy[j] - p.y;
+                            const float d2 = fmaf(dx, dx, dy * dy);
+                            const float num = fmaf(dx, p.z, dy * p.w);
+                            const float s = num * fabsf(num);
+                            const float e = fmaf(-t2, d2, s);
+                            const float bd = fmaf(band, d2, 4e-12f);
+                            if (!(fabsf(e) > bd))
+                                cnt[j] += exact_inlier(nx, ny, p.x, p.y, hx[j], hy[j], thresh) ? 1 : 0;
+                        }
+                    }
+                }
+            }
+        };
+        int i = my_wp;
+        for (; i + (VT_GROUP - 1) * wp_count < len; i += VT_GROUP * wp_count) sweep(i, VT_GROUP);
+        if (i < len) sweep(i, (len - i + wp_count - 1) / wp_count);
 
         // ---- combine the pixel-interleaved warps, then one atomic per hypothesis
 #pragma unroll
-        for (int j = 0; j < VT_HPL; ++j)
-            if (cnt[j]) atomicAdd(&red[my_wh * (32 * VT_HPL) + j * 32 + lane], cnt[j]);
+        for (int j = 0; j < HPL; ++j)
+            if (cnt[j]) atomicAdd(&red[my_wh * (32 * HPL) + j * 32 + lane], cnt[j]);
         __syncthreads();
         for (int i = tid; i < HC; i += VT_THREADS) {
             const int h = hc * HC + i;
@@ -947,12 +984,20 @@ int launch_hyp_and_vote(const float *vertex, const Strides &st, const int32_t *i
     dim3 ghyp((hn * vn + 255) / 256, b);
     k_gen_hyp<<<ghyp, 256, 0, s>>>(vertex, st, idxs, ws.pix, ws.tn, npx, vn, hn, ws.hyp);
     PV_LAUNCHED("k_gen_hyp");
-    // hypothesis warps per CTA: 128 hypotheses per warp
+    // (hypotheses per lane, pixels per tile): items are (tile, keypoint, hypothesis group) on a static
+    // round-robin over 3 CTAs per SM, so small tiles keep the last round short (2048-pixel tiles:
+    // 1440 items on 444 CTAs = 4 rounds for 3.2 rounds of work at 16 x 20k px, K=9, 256 hyp).
+    static const int cfg = [] {
+        const char *e = getenv("PVNET_VOTE_CFG");      // tuning knob: 0 = 4x2048, 1 = 4x512, 2 = 8x512, 3 = 8x1024
+        return e ? atoi(e) : 1;
+    }();
+    const int HPL = cfg >= 2 ? 8 : 4, TILE = cfg == 0 ? 2048 : (cfg == 3 ? 1024 : 512);
+    // hypothesis warps per CTA: 32*HPL hypotheses per warp
     int wh = 1;
-    while (wh < VT_WARPS && wh * 32 * VT_HPL < hn) wh <<= 1;
-    const int HC = wh * 32 * VT_HPL;
-    const long long max_items = (long long)b * ((npx + VT_TILE - 1) / VT_TILE) * vn * ((hn + HC - 1) / HC);
-    long long grid = (long long)pvnet::sm_count() * 3;
+    while (wh < VT_WARPS && wh * 32 * HPL < hn) wh <<= 1;
+    const int HC = wh * 32 * HPL;
+    const long long max_items = (long long)b * ((npx + TILE - 1) / TILE) * vn * ((hn + HC - 1) / HC);
+    long long grid = (long long)pvnet::sm_count() * (HPL > 4 ? 2 : 3);
     if (grid > max_items) grid = max_items;
     // thresh <= 0 (or NaN) has no squared form: NaN makes every test take the exact path
     const float t2 = (thresh > 0.f && thresh < 1e18f) ? thresh * thresh : nanf("");
@@ -972,8 +1017,14 @@ int launch_hyp_and_vote(const float *vertex, const Strides &st, const int32_t *i
         PV_LAUNCHED("k_vote_packed");
         return PVNET_OK;
     }
-    k_vote<<<(unsigned)grid, VT_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, npx, b, vn, hn, wh, ws.hyp, ws.counts,
-                                                 thresh, t2, band);
+#define VOTE_LAUNCH(H_, T_)                                                                                    \
+    k_vote<H_, T_><<<(unsigned)grid, VT_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, npx, b, vn, hn, wh, ws.hyp, \
+                                                         ws.counts, thresh, t2, band)
+    if (cfg == 0) VOTE_LAUNCH(4, 2048);
+    else if (cfg == 2) VOTE_LAUNCH(8, 512);
+    else if (cfg == 3) VOTE_LAUNCH(8, 1024);
+    else VOTE_LAUNCH(4, 512);
+#undef VOTE_LAUNCH
     PV_LAUNCHED("k_vote");
     return PVNET_OK;
 }
