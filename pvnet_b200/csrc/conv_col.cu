@@ -520,9 +520,19 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
         const char *e = getenv("PVNET_COL_EPI");       // tuning knob: 1 forces a single epilogue warp set
         return e ? atoi(e) : 2;
     }();
-    // two epilogue warp sets when the CTA is alone on its SM anyway (and the variant exists)
-    p->epi = 1;       // (a second epilogue warp set measured no gain: the epilogue was LSU-bound, see below)
-    (void)env_epi;
+    // Two epilogue warp sets (alternating tiles, one per TMEM accumulator stage, own staging buffers)
+    // when the CTA is alone on its SM anyway, the variant exists and 32 KB more shared memory fit
+    // with at least 2 stages: short-K layers such as the stem are epilogue-bound (ncu: tensor pipe 40 %).
+    p->epi = 1;
+    if (env_epi == 2 && !head && kc != 8 && resident && per_sm == 1) {
+        int st2 = stages;
+        while (st2 > 2 && col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, st2, 0, true) + 32768 > SMEM_LIMIT) --st2;
+        if (col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, st2, 0, true) + 32768 <= SMEM_LIMIT) {
+            p->epi = 2;
+            g.stages = st2;
+            p->smem = col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, st2, 0, true) + 32768;
+        }
+    }
     long long grid = (long long)sm_count() * per_sm;
     if (grid > g.total_tiles) grid = g.total_tiles;
     p->grid = (unsigned)grid;
