@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
     // HEAD: head weights [32][32], 4 KB.  otherwise: one 128-pixel x 32-channel output staging tile
     // (128B-swizzled rows) for the TMA store of the epilogue, 16 KB
     uint8_t *sHB = sA + (size_t)g.stages * stage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sHB + (HEAD ? 4096 : 32768 * EPI));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sHB + (HEAD ? 4096 : 32768));
     uint64_t *wfull = bars;
     uint64_t *full = bars + 1;
     uint64_t *empty = full + g.stages;
@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
         const int m = q * 32 + lane;
         const int ty = m / COL_TW, tx = m - ty * COL_TW;
         const int epi_set = (warp - 2) >> 2;                     // 0, or 1 when EPI == 2
-        const uint32_t stage_u = ptx::smem_u32(sHB) + (uint32_t)epi_set * 32768u;   // 4 warps x 2 buffers x 4 KB
+        // staging: 32 KB = 4 warps x 2 buffers x 4 KB (EPI 1) or 2 sets x 4 warps x 1 buffer (EPI 2)
+        const uint32_t stage_u = ptx::smem_u32(sHB) + (uint32_t)epi_set * 16384u + (uint32_t)q * (EPI == 2 ? 4096u : 8192u);
         uint32_t nstore = 0;
         uint32_t it = (uint32_t)epi_set;
         for (int tile = blockIdx.x + epi_set * gridDim.x; tile < g.total_tiles; tile += EPI * gridDim.x, it += EPI) {
@@ -298,9 +299,12 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                     v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bv.w;
                 }
                 // staging buffer of this chunk: the store issued two chunks ago has left it
-                const uint32_t buf = stage_u + (uint32_t)(q * 8192) + (nstore & 1u) * 4096u;
+                const uint32_t buf = stage_u + (EPI == 2 ? 0u : (nstore & 1u) * 4096u);
                 if (!HEAD) {
-                    if (lane == 0) ptx::tma_store_wait_read1();
+                    if (lane == 0) {
+                        if (EPI == 2) ptx::tma_store_wait_read();
+                        else ptx::tma_store_wait_read1();
+                    }
                     __syncwarp();
                     if (res != nullptr) {
                         epi_add_residual(v, rpre, buf, lane);
@@ -520,19 +524,10 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
         const char *e = getenv("PVNET_COL_EPI");       // tuning knob: 1 forces a single epilogue warp set
         return e ? atoi(e) : 2;
     }();
-    // Two epilogue warp sets (alternating tiles, one per TMEM accumulator stage, own staging buffers)
-    // when the CTA is alone on its SM anyway, the variant exists and 32 KB more shared memory fit
-    // with at least 2 stages: short-K layers such as the stem are epilogue-bound (ncu: tensor pipe 40 %).
-    p->epi = 1;
-    if (env_epi == 2 && !head && kc != 8 && resident && per_sm == 1) {
-        int st2 = stages;
-        while (st2 > 2 && col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, st2, 0, true) + 32768 > SMEM_LIMIT) --st2;
-        if (col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, st2, 0, true) + 32768 <= SMEM_LIMIT) {
-            p->epi = 2;
-            g.stages = st2;
-            p->smem = col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, st2, 0, true) + 32768;
-        }
-    }
+    // Two epilogue warp sets (alternating tiles, one per TMEM accumulator stage; the 32 KB of staging
+    // are then 8 single buffers instead of 4 double ones) when the CTA is alone on its SM anyway and
+    // the variant exists: the short-K layers are epilogue-bound (ncu: stem tensor pipe 40 %).
+    p->epi = (env_epi == 2 && !head && kc != 8 && per_sm == 1) ? 2 : 1;
     long long grid = (long long)sm_count() * per_sm;
     if (grid > g.total_tiles) grid = g.total_tiles;
     p->grid = (unsigned)grid;
