@@ -115,6 +115,28 @@ PVNET_API int pvnet_ransac_voting_v5(const void *mask, int mask_elem_size,
                                      int32_t *out_tn, void *workspace, size_t workspace_bytes,
                                      pvnet_stream_t stream);
 
+/* ransac_voting_layer_v4 (ransac_voting_gpu.py:669-760): v3 plus the residual variance of the
+ * refit, out_var [b,vn] = sum over the winner's inliers of (n.p - n.c)^2 / #inliers with
+ * n = (d_y,-d_x) and p the refitted point (:750-752; 0/0 = NaN as in torch); a skipped image
+ * gives zeros and var = 1 (:685-689).  Same arguments as pvnet_ransac_voting_v3 otherwise. */
+PVNET_API int pvnet_ransac_voting_v4(const void *mask, int mask_elem_size,
+                                     const float *vertex, const int64_t vertex_strides[5],
+                                     const int32_t *idxs, const float *selection,
+                                     int b, int h, int w, int vn, int hn,
+                                     float inlier_thresh, int min_num, int max_num,
+                                     float *out_pts, float *out_var, int32_t *out_counts, float *out_hyp,
+                                     int32_t *out_tn, void *workspace, size_t workspace_bytes,
+                                     pvnet_stream_t stream);
+
+/* ransac_motion_voting (ransac_voting_gpu.py:960-981; tools/train_linemod.py:117
+ * `MotionEvalWrapper`): out_pts [b,vn,2] = mean over the foreground pixels (low byte nonzero, as
+ * `.byte()`) of vertex + (x, y); zeros for an empty mask (:971-973).  Workspace:
+ * pvnet_vote_workspace_bytes(b, h, w, vn, 1). */
+PVNET_API int pvnet_ransac_motion_voting(const void *mask, int mask_elem_size,
+                                         const float *vertex, const int64_t vertex_strides[5],
+                                         int b, int h, int w, int vn, float *out_pts,
+                                         void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
+
 /* estimate_voting_distribution_with_mean (ransac_voting_gpu.py:333-406).
  *
  *   mask       foreground = element == 1

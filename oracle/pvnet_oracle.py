@@ -316,6 +316,143 @@ def estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=256
     return (mean, cov, debug) if return_debug else (mean, cov)
 
 
+# ------------------------------------------------------------ remaining layer variants
+def ransac_motion_voting(mask, vertex):
+    """ransac_voting_gpu.py:960-981: per image and keypoint the mean over the foreground
+    pixels (`.byte()` nonzero) of vertex + (x, y); zeros when the mask is empty (:971-973).
+    Sums in float64 (the reference's torch.mean is fp32 with library-defined order)."""
+    mask = np.asarray(mask)
+    vertex = np.asarray(vertex)
+    b, h, w, vn, _ = vertex.shape
+    out = np.zeros((b, vn, 2), np.float32)
+    for bi in range(b):
+        coords, direct = compact(_byte_mask(mask[bi]), vertex[bi])
+        if coords.shape[0] < 1:
+            continue
+        out[bi] = (direct.astype(np.float64) + coords[:, None, :].astype(np.float64)).mean(0).astype(np.float32)
+    return out
+
+
+def ransac_voting_layer(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                        min_num=5, max_num=30000, idxs=None, selection=None):
+    """ransac_voting_gpu.py:10-97 (the first layer): for every class k+1 in 1..class_num-1 the
+    pixels with mask == k+1 vote; the result is the WINNING HYPOTHESIS itself (no refit),
+    [b, class_num-1, vn, 2].  idxs[bi][k] is the [hn,vn,2] draw of (image, class); as in v3 the
+    extra rounds re-score the same draw, so one evaluation is the result."""
+    mask = np.asarray(mask)
+    vertex = np.asarray(vertex)
+    b, h, w, vn, _ = vertex.shape
+    out = np.zeros((b, class_num - 1, vn, 2), np.float32)
+    for bi in range(b):
+        for k in range(class_num - 1):
+            cur_mask = (mask[bi] == k + 1)
+            fg = int(cur_mask.sum())
+            if fg < min_num:                               # :28-31
+                continue
+            if fg > max_num:                               # :34-37
+                p = subsample_probability(max_num, fg)
+                cur_mask = cur_mask & (np.asarray(selection[bi][k], np.float32) < p)
+            coords, direct = compact(cur_mask.astype(np.uint8), vertex[bi])
+            tn = coords.shape[0]
+            hyp = generate_hypothesis_kernel(direct, coords, np.ascontiguousarray(idxs[bi][k], np.int32))
+            counts = vote_counts(direct, coords, hyp, inlier_thresh)
+            win_idx = counts.argmax(0)
+            win_counts = counts[win_idx, np.arange(vn)]
+            ratio = win_counts.astype(np.float32) / np.float32(tn)
+            larger = np.float32(0) < ratio                 # :74
+            out[bi, k][larger] = hyp[win_idx, np.arange(vn)][larger]
+    return out
+
+
+def ransac_voting_layer_v4(mask, vertex, round_hyp_num, inlier_thresh=0.99, confidence=0.999, max_iter=20,
+                           min_num=5, max_num=30000, idxs=None, selection=None):
+    """ransac_voting_gpu.py:669-760: v3 plus var[b,vn] = sum over the winner's inliers of
+    (n.p - n.c)^2 / #inliers, n = (d_y,-d_x), p the refitted point (:750-752); skipped images
+    give zeros and var = 1 (:685-689).  float64 sums."""
+    kp, dbg = ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=inlier_thresh, min_num=min_num,
+                                     max_num=max_num, idxs=idxs, selection=selection, return_debug=True)
+    var = np.ones(kp.shape[:2], np.float32)
+    for bi, d in enumerate(dbg):
+        if d is None:
+            continue
+        direct, coords, inl = d["direct"], d["coords"], d["refit_inliers"]     # inl [vn,tn]
+        nx = direct[:, :, 1].T.astype(np.float64)
+        ny = (-direct[:, :, 0]).T.astype(np.float64)
+        bb = nx * coords[None, :, 0] + ny * coords[None, :, 1]
+        res = nx * kp[bi][:, 0:1].astype(np.float64) + ny * kp[bi][:, 1:2].astype(np.float64) - bb
+        w = inl.astype(np.float64)
+        with np.errstate(all="ignore"):
+            var[bi] = ((res * res * w).sum(1) / w.sum(1)).astype(np.float32)
+    return kp, var
+
+
+def ransac_voting_hypothesis(mask, vertex, round_hyp_num, inlier_thresh=0.999, min_num=5, max_num=30000,
+                             idxs=None, selection=None):
+    """ransac_voting_gpu.py:218-261: hypotheses [b,hn,vn,2] and inlier counts [b,hn,vn] (int64)
+    of the pixels with mask == 1; a skipped image gives zero hypotheses and counts of ONE (:228-233)."""
+    mask = np.asarray(mask)
+    vertex = np.asarray(vertex)
+    b, h, w, vn, _ = vertex.shape
+    hyps = np.zeros((b, round_hyp_num, vn, 2), np.float32)
+    cnts = np.ones((b, round_hyp_num, vn), np.int64)
+    for bi in range(b):
+        cur_mask = (mask[bi] == 1)
+        fg = int(cur_mask.sum())
+        if fg < min_num:
+            continue
+        if fg > max_num:
+            p = subsample_probability(max_num, fg)
+            cur_mask = cur_mask & (np.asarray(selection[bi], np.float32) < p)
+        coords, direct = compact(cur_mask.astype(np.uint8), vertex[bi])
+        hyps[bi] = generate_hypothesis_kernel(direct, coords, np.ascontiguousarray(idxs[bi], np.int32))
+        cnts[bi] = vote_counts(direct, coords, hyps[bi], inlier_thresh)
+    return hyps, cnts
+
+
+def estimate_voting_distribution(mask, vertex, round_hyp_num=256, min_hyp_num=4096, topk=128, inlier_thresh=0.99,
+                                 min_num=5, max_num=30000, idxs=None, selection=None, return_ratio=False):
+    """ransac_voting_gpu.py:263-331: ratio-weighted mean and covariance of the top-k hypotheses
+    per keypoint.  idxs as in estimate_voting_distribution_with_mean.  When several ratios tie at
+    the k-th place torch.topk's choice among them is unspecified; this restatement keeps the
+    lowest hypothesis indices (tests avoid ties).  float64 sums."""
+    mask = np.asarray(mask)
+    vertex = np.asarray(vertex)
+    b, h, w, vn, _ = vertex.shape
+    rounds = int(np.ceil(min_hyp_num / round_hyp_num))
+    hn = rounds * round_hyp_num
+    hyp = np.zeros((b, hn, vn, 2), np.float32)
+    ratio = np.ones((b, hn, vn), np.float32)
+    for bi in range(b):
+        cur_mask = (mask[bi] == 1)
+        fg = int(cur_mask.sum())
+        if fg < min_num:                                   # :271-277 (the reference's shapes only fit hn == round_hyp_num)
+            continue
+        if fg > max_num:
+            p = subsample_probability(max_num, fg)
+            cur_mask = cur_mask & (np.asarray(selection[bi], np.float32) < p)
+            fg = int(cur_mask.sum())
+        coords, direct = compact(cur_mask.astype(np.uint8), vertex[bi])
+        for r in range(rounds):
+            hp = generate_hypothesis_kernel(direct, coords, np.asarray(idxs[bi][r], np.int32))
+            c = vote_counts(direct, coords, hp, inlier_thresh)
+            hyp[bi, r * round_hyp_num:(r + 1) * round_hyp_num] = hp
+            ratio[bi, r * round_hyp_num:(r + 1) * round_hyp_num] = c.astype(np.float32) / np.float32(fg)
+    hyp = hyp.transpose(0, 2, 1, 3)                        # [b,vn,hn,2]
+    ratio = ratio.transpose(0, 2, 1)                       # [b,vn,hn]
+    order = np.argsort(-ratio, axis=2, kind="stable")[:, :, :topk]
+    kept = np.zeros_like(ratio)
+    np.put_along_axis(kept, order, np.take_along_axis(ratio, order, 2), 2)   # :316-317
+    w64 = kept.astype(np.float64)
+    wsum = w64.sum(2)
+    with np.errstate(all="ignore"):
+        mean = (w64[..., None] * hyp.astype(np.float64)).sum(2) / wsum[..., None]              # :319-320
+        diff = hyp.astype(np.float64) - mean[:, :, None, :]
+        cov = np.einsum("bvhi,bvhj->bvij", diff, diff * w64[..., None]) / wsum[..., None, None]  # :322-325
+    if return_ratio:       # [b,vn,hn] ratios before the top-k cut (tests use them to find ties at the cut)
+        return mean.astype(np.float32), cov.astype(np.float32), ratio
+    return mean.astype(np.float32), cov.astype(np.float32)
+
+
 def num_threads():
     return int(lib().pvo_num_threads())
 

@@ -36,6 +36,11 @@ SIGNATURES = {
     "pvnet_ransac_voting_v5": (c_int, [c_void_p, c_int, c_void_p, c_int64_p, c_void_p, c_void_p,
                                        c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pvnet_ransac_voting_v4": (c_int, [c_void_p, c_int, c_void_p, c_int64_p, c_void_p, c_void_p,
+                                       c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pvnet_ransac_motion_voting": (c_int, [c_void_p, c_int, c_void_p, c_int64_p, c_int, c_int, c_int, c_int,
+                                           c_void_p, c_void_p, c_size_t, c_void_p]),
     "pvnet_vote_cov_with_mean": (c_int, [c_void_p, c_int, c_void_p, c_int64_p, c_void_p, c_void_p, c_void_p,
                                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -760,6 +760,133 @@ __global__ void k_conf_final(const int *__restrict__ conf_cnt, const int *__rest
     out_conf[bk] = tn > 0 ? __fdiv_rn((float)conf_cnt[bk], (float)tn) : 0.f;   // skipped image: zeros (:792)
 }
 
+// ------------------------------------------------------------------ v4 residual variance, motion voting
+// block-wide fixed-order sum of two doubles (RF_THREADS threads); result valid in thread 0
+__device__ __forceinline__ void block_sum2_d(double &a, double &b, double (*s_acc)[2])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_sum_d(a);
+    b = warp_sum_d(b);
+    if (lane == 0) {
+        s_acc[warp][0] = a;
+        s_acc[warp][1] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = b = 0.0;
+        for (int i = 0; i < RF_THREADS / 32; ++i) {
+            a += s_acc[i][0];
+            b += s_acc[i][1];
+        }
+    }
+}
+
+// ransac_voting_layer_v4 (ransac_voting_gpu.py:733-752): over the inliers of the WINNING hypothesis
+// (the set the refit used), residual r = n.p - n.c with n = (d_y,-d_x) and p the refitted point;
+// partial sums of r^2 and of the inlier count in fp64.  grid (RF_CHUNKS, b*vn).
+__global__ void __launch_bounds__(RF_THREADS)
+    k_resid_sum(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
+                const int *__restrict__ tn_arr, int npx, int vn, const float2 *__restrict__ win,
+                const float *__restrict__ pts, float thresh, double *__restrict__ part)
+{
+    __shared__ double s_acc[RF_THREADS / 32][2];
+    const int rc = blockIdx.x, bk = blockIdx.y, b = bk / vn, k = bk - b * vn;
+    const int tn = tn_arr[b];
+    double *my_part = part + ((size_t)bk * RF_CHUNKS + rc) * 2;
+    double r2 = 0.0, cnt = 0.0;
+    if (tn > 0) {
+        const float2 wp = win[bk];
+        const double px = (double)pts[bk * 2], py = (double)pts[bk * 2 + 1];
+        const int per = (tn + RF_CHUNKS - 1) / RF_CHUNKS;
+        const int lo = rc * per, hi = min(tn, lo + per);
+        const long long vbase = (long long)b * st.s[0] + (long long)k * st.s[3];
+        for (int t = lo + threadIdx.x; t < hi; t += RF_THREADS) {
+            const unsigned p = pix[(size_t)b * npx + t];
+            const int x = p & 0xffff, y = p >> 16;
+            const long long off = vbase + y * st.s[1] + x * st.s[2];
+            const float dxv = vertex[off], dyv = vertex[off + st.s[4]];
+            if (exact_inlier(dxv, dyv, (float)x, (float)y, wp.x, wp.y, thresh)) {
+                const double n0 = (double)dyv, n1 = -(double)dxv;
+                const double r = n0 * px + n1 * py - (n0 * (double)x + n1 * (double)y);
+                r2 += r * r;
+                cnt += 1.0;
+            }
+        }
+    }
+    block_sum2_d(r2, cnt, s_acc);
+    if (threadIdx.x == 0) {
+        my_part[0] = r2;
+        my_part[1] = cnt;
+    }
+}
+
+// var = sum r^2 / #inliers (0/0 = NaN like torch); skipped image: 1 (:688)
+__global__ void k_resid_final(const double *__restrict__ part, const int *__restrict__ tn_arr, int nb, int vn,
+                              float *__restrict__ out_var)
+{
+    const int bk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bk >= nb * vn) return;
+    float v = 1.f;
+    if (tn_arr[bk / vn] > 0) {
+        double r2 = 0.0, cnt = 0.0;
+        for (int rc = 0; rc < RF_CHUNKS; ++rc) {
+            r2 += part[((size_t)bk * RF_CHUNKS + rc) * 2];
+            cnt += part[((size_t)bk * RF_CHUNKS + rc) * 2 + 1];
+        }
+        v = (float)(r2 / cnt);
+    }
+    out_var[bk] = v;
+}
+
+// ransac_motion_voting (ransac_voting_gpu.py:960-981): sum over the foreground pixels of
+// vertex + (x, y), fp64 partials.  grid (RF_CHUNKS, b*vn).
+__global__ void __launch_bounds__(RF_THREADS)
+    k_motion_sum(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
+                 const int *__restrict__ tn_arr, int npx, int vn, double *__restrict__ part)
+{
+    __shared__ double s_acc[RF_THREADS / 32][2];
+    const int rc = blockIdx.x, bk = blockIdx.y, b = bk / vn, k = bk - b * vn;
+    const int tn = tn_arr[b];
+    double sx = 0.0, sy = 0.0;
+    const int per = (tn + RF_CHUNKS - 1) / RF_CHUNKS;
+    const int lo = rc * per, hi = min(tn, lo + per);
+    const long long vbase = (long long)b * st.s[0] + (long long)k * st.s[3];
+    for (int t = lo + threadIdx.x; t < hi; t += RF_THREADS) {
+        const unsigned p = pix[(size_t)b * npx + t];
+        const int x = p & 0xffff, y = p >> 16;
+        const long long off = vbase + y * st.s[1] + x * st.s[2];
+        // the reference adds in fp32 before averaging: cur_vert[cur_mask] + coords (:978)
+        sx += (double)__fadd_rn(vertex[off], (float)x);
+        sy += (double)__fadd_rn(vertex[off + st.s[4]], (float)y);
+    }
+    block_sum2_d(sx, sy, s_acc);
+    if (threadIdx.x == 0) {
+        double *my_part = part + ((size_t)bk * RF_CHUNKS + rc) * 2;
+        my_part[0] = sx;
+        my_part[1] = sy;
+    }
+}
+
+__global__ void k_motion_final(const double *__restrict__ part, const int *__restrict__ tn_arr, int nb, int vn,
+                               float *__restrict__ out_pts)
+{
+    const int bk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bk >= nb * vn) return;
+    const int tn = tn_arr[bk / vn];
+    float px = 0.f, py = 0.f;      // empty mask: zeros (:971-973)
+    if (tn > 0) {
+        double sx = 0.0, sy = 0.0;
+        for (int rc = 0; rc < RF_CHUNKS; ++rc) {
+            sx += part[((size_t)bk * RF_CHUNKS + rc) * 2];
+            sy += part[((size_t)bk * RF_CHUNKS + rc) * 2 + 1];
+        }
+        px = (float)(sx / (double)tn);
+        py = (float)(sy / (double)tn);
+    }
+    out_pts[bk * 2] = px;
+    out_pts[bk * 2 + 1] = py;
+}
+
 // internal [b][vn][hn] -> API layouts [b,hn,vn(,2)]
 __global__ void k_export(const float2 *__restrict__ hyp, const int *__restrict__ counts,
                          const int *__restrict__ tn_arr, int nb, int vn, int hn, float *__restrict__ out_hyp,
@@ -1134,6 +1261,59 @@ int pvnet_ransac_voting_v5(const void *mask, int mask_elem_size, const float *ve
     PV_LAUNCHED("k_conf_count");
     k_conf_final<<<(b * vn + 127) / 128, 128, 0, s>>>(conf_cnt, ws.tn, b, vn, out_conf);
     PV_LAUNCHED("k_conf_final");
+    return PVNET_OK;
+}
+
+int pvnet_ransac_voting_v4(const void *mask, int mask_elem_size, const float *vertex,
+                           const int64_t vertex_strides[5], const int32_t *idxs, const float *selection, int b,
+                           int h, int w, int vn, int hn, float inlier_thresh, int min_num, int max_num,
+                           float *out_pts, float *out_var, int32_t *out_counts, float *out_hyp, int32_t *out_tn,
+                           void *workspace, size_t workspace_bytes, pvnet_stream_t stream)
+{
+    PV_CHECK_ARG(out_var, "null out_var");
+    int rc = pvnet_ransac_voting_v3(mask, mask_elem_size, vertex, vertex_strides, idxs, selection, b, h, w, vn, hn,
+                                    inlier_thresh, min_num, max_num, out_pts, out_counts, out_hyp, out_tn, workspace,
+                                    workspace_bytes, stream);
+    if (rc) return rc;
+    Strides st;
+    for (int i = 0; i < 5; ++i) st.s[i] = vertex_strides[i];
+    VoteWs ws = carve(workspace, b, h, w, vn, hn);
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid(RF_CHUNKS, b * vn);                          // the refit partials are consumed by now
+    k_resid_sum<<<grid, RF_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, h * w, vn, ws.win, out_pts, inlier_thresh,
+                                            ws.part);
+    PV_LAUNCHED("k_resid_sum");
+    k_resid_final<<<(b * vn + 127) / 128, 128, 0, s>>>(ws.part, ws.tn, b, vn, out_var);
+    PV_LAUNCHED("k_resid_final");
+    return PVNET_OK;
+}
+
+int pvnet_ransac_motion_voting(const void *mask, int mask_elem_size, const float *vertex,
+                               const int64_t vertex_strides[5], int b, int h, int w, int vn, float *out_pts,
+                               void *workspace, size_t workspace_bytes, pvnet_stream_t stream)
+{
+    PV_CHECK_ARG(mask && vertex && vertex_strides && out_pts && workspace, "null pointer");
+    PV_CHECK_ARG(mask_elem_size == 1 || mask_elem_size == 2 || mask_elem_size == 4 || mask_elem_size == 8,
+                 "mask element size %d not in {1,2,4,8}", mask_elem_size);
+    PV_CHECK_ARG(b >= 1 && b <= VT_MAX_B, "batch %d outside [1,%d]", b, VT_MAX_B);
+    PV_CHECK_ARG(h >= 1 && w >= 1 && h <= 65535 && w <= 65535, "image size %dx%d unsupported", h, w);
+    PV_CHECK_ARG(vn >= 1 && vn <= 65535, "keypoint count %d unsupported", vn);
+    Strides st;
+    for (int i = 0; i < 5; ++i) st.s[i] = vertex_strides[i];
+    VoteWs ws = carve(workspace, b, h, w, vn, 1);
+    if (workspace_bytes < ws.bytes) {
+        pvnet::set_error("workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+        return PVNET_E_WORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    // every foreground pixel takes part: min_num 1, no subsampling
+    int rc = launch_compaction(mask, mask_elem_size, PVNET_MASK_NONZERO_BYTE, nullptr, b, h, w, 1, 0x7fffffff, ws, s);
+    if (rc) return rc;
+    dim3 grid(RF_CHUNKS, b * vn);
+    k_motion_sum<<<grid, RF_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, h * w, vn, ws.part);
+    PV_LAUNCHED("k_motion_sum");
+    k_motion_final<<<(b * vn + 127) / 128, 128, 0, s>>>(ws.part, ws.tn, b, vn, out_pts);
+    PV_LAUNCHED("k_motion_final");
     return PVNET_OK;
 }
 

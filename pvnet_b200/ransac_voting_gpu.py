@@ -8,6 +8,11 @@ inference hot path:
     ransac_voting_layer_v5                   (reference :763-858)
     estimate_voting_distribution_with_mean   (reference :333-406)
     generate_hypothesis                      (reference :983-1034)
+    ransac_motion_voting                     (reference :960-981)
+    ransac_voting_layer_v4                   (reference :669-760)
+    ransac_voting_layer                      (reference :10-97)
+    ransac_voting_hypothesis                 (reference :218-261)
+    estimate_voting_distribution             (reference :263-331)
 
 so ``tools/demo.py`` / ``tools/train_linemod.py --test_model`` keep working when
 ``lib/ransac_voting_gpu_layer/ransac_voting_gpu.py`` is this module (the shim under
@@ -289,3 +294,131 @@ def generate_hypothesis(mask, vertex, round_hyp_num, inlier_thresh=0.999, confid
     _, dbg = ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh, confidence, max_iter, min_num,
                                     max_num, idxs=idxs, selection=selection, rng=rng, return_debug=True)
     return dbg["hyp"], dbg["counts"].long()
+
+
+# ------------------------------------------------------------------ the other variants of the module
+def ransac_motion_voting(mask, vertex):
+    """Reference ransac_voting_gpu.py:960-981 (tools/train_linemod.py:117, `MotionEvalWrapper`):
+    [b,vn,2] mean over the foreground pixels of vertex + (x, y); zeros for an empty mask."""
+    _require_cuda(mask, "mask")
+    _require_cuda(vertex, "vertex")
+    b, h, w, vn, _ = vertex.shape
+    dev = mask.device
+    m, esz = _prep_mask(mask, _MASK_NONZERO_BYTE)
+    v, strides = _prep_vertex(vertex)
+    with torch.cuda.device(dev):
+        out = torch.empty([b, vn, 2], dtype=torch.float32, device=dev)
+        ws, ws_bytes = _workspace(b, h, w, vn, 1, dev)
+        _native.check(_native.lib().pvnet_ransac_motion_voting(_ptr(m), esz, _ptr(v), strides, b, h, w, vn, _ptr(out),
+                                                               _ptr(ws), ws_bytes, _stream(dev)),
+                      "pvnet_ransac_motion_voting")
+    return out
+
+
+def ransac_voting_layer_v4(mask, vertex, round_hyp_num, inlier_thresh=0.99, confidence=0.999, max_iter=20,
+                           min_num=5, max_num=30000, *, idxs=None, selection=None, rng="reference"):
+    """Reference signature (ransac_voting_gpu.py:669-670).  Returns (keypoints [b,vn,2],
+    var [b,vn]): var = mean squared residual n.p - n.c of the refit over the winner's inliers
+    (:750-752); skipped images: zeros and var = 1."""
+    del confidence, max_iter
+    _require_cuda(mask, "mask")
+    _require_cuda(vertex, "vertex")
+    b, h, w, vn, _ = vertex.shape
+    hn = int(round_hyp_num)
+    dev = mask.device
+    m, esz = _prep_mask(mask, _MASK_NONZERO_BYTE)
+    v, strides = _prep_vertex(vertex)
+    with torch.cuda.device(dev):
+        if idxs is not None:
+            idxs, selection = _check_injected(idxs, selection, b, h, w, vn, hn, dev)
+        elif rng == "reference":
+            idxs, selection, _ = _draw_reference(m, _MASK_NONZERO_BYTE, b, h, w, vn, hn, 1, min_num, max_num)
+        elif rng == "batched":
+            idxs, selection = _draw_batched(b, h, w, vn, hn, max_num, dev)
+        else:
+            raise ValueError(f"unknown rng mode {rng!r}")
+        out = torch.empty([b, vn, 2], dtype=torch.float32, device=dev)
+        var = torch.empty([b, vn], dtype=torch.float32, device=dev)
+        ws, ws_bytes = _workspace(b, h, w, vn, hn, dev)
+        _native.check(_native.lib().pvnet_ransac_voting_v4(
+            _ptr(m), esz, _ptr(v), strides, _ptr(idxs), _ptr(selection), b, h, w, vn, hn,
+            float(inlier_thresh), int(min_num), int(min(max_num, 2 ** 31 - 1)),
+            _ptr(out), _ptr(var), None, None, None, _ptr(ws), ws_bytes, _stream(dev)), "pvnet_ransac_voting_v4")
+    return out, var
+
+
+def _class_mask(mask, value):
+    """`mask == value` as a uint8 tensor (the class-selecting variants: :24, :223, :269)."""
+    return (mask == value).to(torch.uint8)
+
+
+def ransac_voting_layer(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                        min_num=5, max_num=30000, *, idxs=None, selection=None, rng="reference"):
+    """Reference signature (ransac_voting_gpu.py:10-11), the first voting layer: for every class
+    1..class_num-1 the pixels with mask == class vote and the WINNING HYPOTHESIS (no refit) is
+    returned: [b, class_num-1, vn, 2].  idxs / selection, when injected, carry a leading class
+    axis: [class_num-1, b, hn, vn, 2] / [class_num-1, b, h, w]."""
+    del confidence, max_iter
+    b, h, w, vn, _ = vertex.shape
+    outs = []
+    for k in range(int(class_num) - 1):
+        _, dbg = ransac_voting_layer_v3(_class_mask(mask, k + 1), vertex, round_hyp_num, inlier_thresh, min_num=min_num,
+                                        max_num=max_num, idxs=None if idxs is None else idxs[k],
+                                        selection=None if selection is None else selection[k], rng=rng,
+                                        return_debug=True)
+        counts, hyp = dbg["counts"], dbg["hyp"]                   # [b,hn,vn], [b,hn,vn,2]
+        win = torch.argmax(counts, 1)                              # first maximum (:68)
+        win_cnt = torch.gather(counts, 1, win[:, None, :])[:, 0]   # [b,vn]
+        win_pts = torch.gather(hyp, 1, win[:, None, :, None].expand(b, 1, vn, 2))[:, 0]
+        outs.append(torch.where((win_cnt > 0)[..., None], win_pts, torch.zeros_like(win_pts)))   # :74-75
+    if not outs:
+        return torch.zeros([b, 0, vn, 2], dtype=torch.float32, device=vertex.device)
+    return torch.stack(outs, 1)
+
+
+def ransac_voting_hypothesis(mask, vertex, round_hyp_num, inlier_thresh=0.999, min_num=5, max_num=30000, *,
+                             idxs=None, selection=None, rng="reference"):
+    """Reference signature (ransac_voting_gpu.py:218): hypotheses [b,hn,vn,2] and int64 inlier
+    counts [b,hn,vn] of the pixels with mask == 1; a skipped image has zero hypotheses and
+    counts of one (:228-233)."""
+    _, dbg = ransac_voting_layer_v3(_class_mask(mask, 1), vertex, round_hyp_num, inlier_thresh, min_num=min_num,
+                                    max_num=max_num, idxs=idxs, selection=selection, rng=rng, return_debug=True)
+    counts = dbg["counts"].long()
+    skipped = (dbg["tn"] == 0)[:, None, None]
+    return dbg["hyp"], torch.where(skipped, torch.ones_like(counts), counts)
+
+
+def estimate_voting_distribution(mask, vertex, round_hyp_num=256, min_hyp_num=4096, topk=128, inlier_thresh=0.99,
+                                 min_num=5, max_num=30000, *, idxs=None, selection=None, rng="reference"):
+    """Reference signature (ransac_voting_gpu.py:263-264): (mean [b,vn,2], cov [b,vn,2,2]) of
+    the top-k hypotheses per keypoint weighted by their inlier ratio.  The hypotheses and
+    counts come from the vote kernels; the top-k / moment arithmetic on the [b,vn,hn] result is
+    the reference's own torch expression (:315-325) evaluated on the device."""
+    _require_cuda(mask, "mask")
+    b, h, w, vn, _ = vertex.shape
+    hn = int(round_hyp_num)
+    rounds = int(math.ceil(min_hyp_num / hn))
+    dev = mask.device
+    m = _class_mask(mask, 1)
+    with torch.cuda.device(dev):
+        if idxs is not None:
+            idxs, selection = _check_injected(idxs, selection, b, h, w, vn, hn * rounds, dev)
+        elif rng == "reference":
+            idxs, selection, _ = _draw_reference(m, _MASK_NONZERO_BYTE, b, h, w, vn, hn, rounds, min_num, max_num)
+        elif rng == "batched":
+            idxs, selection = _draw_batched(b, h, w, vn, hn * rounds, max_num, dev)
+        else:
+            raise ValueError(f"unknown rng mode {rng!r}")
+        _, dbg = ransac_voting_layer_v3(m, vertex, hn * rounds, inlier_thresh, min_num=min_num, max_num=max_num,
+                                        idxs=idxs, selection=selection, return_debug=True)
+        tn = dbg["tn"].float()[:, None, None]
+        ratio = torch.where(tn > 0, dbg["counts"].float() / tn.clamp(min=1), torch.ones_like(tn))   # :276, :302
+        hyp = dbg["hyp"].permute(0, 2, 1, 3)                       # [b,vn,hn,2]   :313
+        ratio = ratio.permute(0, 2, 1)                             # [b,vn,hn]     :314
+        values, indexes = torch.topk(ratio, min(int(topk), ratio.shape[2]), dim=2, sorted=False)
+        ratio = torch.zeros_like(ratio).scatter_(2, indexes, values)
+        wsum = torch.sum(ratio, 2)
+        mean = torch.sum(ratio[..., None] * hyp, 2) / wsum[..., None]
+        diff = hyp - mean[:, :, None]
+        cov = torch.matmul(diff.transpose(2, 3), diff * ratio[..., None]) / wsum[..., None, None]
+    return mean, cov

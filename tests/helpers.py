@@ -63,3 +63,29 @@ def seeded_state_dict(model, seed=0):
         else:                                    # BN beta / conv bias
             out[name] = torch.randn(t.shape, generator=g) * 0.1
     return out
+
+
+# ---------------------------------------------------------------- inputs of tests/golden/ref_variants.npz
+VARIANT_HWK = (64, 80, 5)
+
+
+def variant_inputs(seed, n_fg=900, classes=1):
+    """mask [1,H,W] int64 with `classes` disc-shaped regions (values 1..classes), vertex
+    [1,H,W,K,2] f32: unit vectors towards K planted keypoints, rotated by N(0, 0.05 rad) noise.
+    Shared by tests/golden/make_golden_variants.py (which feeds them to the reference's own
+    Python functions) and the tests that replay the recorded samples."""
+    H, W, K = VARIANT_HWK
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    mask = np.zeros((H, W), np.int64)
+    for c in range(classes):
+        cx, cy = W * (c + 1) / (classes + 1), H / 2
+        d2 = (xx - cx) ** 2 + (yy - cy) ** 2
+        order = np.argsort(d2.ravel(), kind="stable")[:n_fg // classes]
+        mask.ravel()[order] = c + 1
+    kps = np.stack([W / 2 + 30 * np.cos(2 * np.pi * np.arange(K) / K), H / 2 + 20 * np.sin(2 * np.pi * np.arange(K) / K)], 1)
+    d = kps[None, None] - np.stack([xx, yy], -1)[:, :, None, :].astype(np.float64)      # [H,W,K,2]
+    ang = np.arctan2(d[..., 1], d[..., 0]) + rng.normal(0, 0.05, d.shape[:-1])
+    vertex = np.stack([np.cos(ang), np.sin(ang)], -1).astype(np.float32)
+    vertex[mask == 0] = 0
+    return mask[None], vertex[None], kps
