@@ -2,6 +2,7 @@
 
   python benchmarks/ncu_tables.py conv  gpurun_out/conv_full.ncu-rep   profiles/r01_ncu_conv_final.md profiles/r01_conv_dram_traffic.json
   python benchmarks/ncu_tables.py list  gpurun_out/launches.csv        profiles/r01_ncu_launches_final.md
+  python benchmarks/ncu_tables.py vote  gpurun_out/vote_full.ncu-rep   profiles/r01_ncu_vote_final.md
   python benchmarks/ncu_tables.py top   gpurun_out/conv_full.ncu-rep   <kernel index> [n]     (hottest source lines)
 
 Captures (see the header each table carries):
@@ -72,7 +73,12 @@ def conv(rep, md, js, batch=16):
         us = to_unit(r[col["gpu__time_duration.sum"]], units[col["gpu__time_duration.sum"]], "us")
         rmb = to_unit(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]], "MB")
         wmb = to_unit(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]], "MB")
-        tp = max(float(r[col[c]].replace(",", "") or 0) for c in tens) if tens else float("nan")
+        def num(v):
+            try:
+                return float(v.replace(",", ""))
+            except ValueError:
+                return 0.0
+        tp = max(num(r[col[c]]) for c in tens) if tens else float("nan")
         l2 = float(r[col["lts__throughput.avg.pct_of_peak_sustained_elapsed"]])
         dr = float(r[col["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]])
         tf = 2 * gm[i] * batch * 1e9 / (us * 1e-6) / 1e12
@@ -88,6 +94,37 @@ def conv(rep, md, js, batch=16):
                "dram_read_mb": round(rd, 1), "dram_write_mb": round(wr, 1), "bytes_per_step": int((rd + wr) * 1e6),
                "source": md}, open(js, "w"), indent=1)
     print("\n".join(lines[-3:]))
+
+
+VOTE_METRICS = ["launch__grid_size", "launch__block_size", "gpu__time_duration.sum", "dram__bytes_read.sum",
+                "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+                "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+                "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+                "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "smsp__inst_executed.sum",
+                "sm__cycles_elapsed.avg.per_second"]
+
+
+def vote(rep, md):
+    h, units, rows = raw(rep)
+    col = {c: i for i, c in enumerate(h)}
+    r = rows[0]
+    lines = ["# ncu --set full, k_vote inside one bench step (16 images x ~19900 px, 256 hyp, K=9)", "",
+             "`ncu --profile-from-start off --set full --clock-control none -k regex:k_vote -c 1 python "
+             "benchmarks/profile_step.py 1` -> `python benchmarks/ncu_tables.py vote ...`", "",
+             f"Kernel: `{r[col['Kernel Name']][:100]}`", "", "| metric | value | unit |", "|---|---|---|"]
+    for m in VOTE_METRICS:
+        if m in col:
+            lines.append(f"| {m} | {r[col[m]]} | {units[col[m]]} |")
+    inst = float(r[col["smsp__inst_executed.sum"]].replace(",", ""))
+    tests = 16 * 19905 * 9 * 256
+    lines += ["", f"Tests in this launch: 16 x ~19905 px x 9 kp x 256 hyp = {tests / 1e6:.0f} M -> "
+                  f"{inst * 32 / tests:.1f} lane-instructions per test (all kernel phases included).  Algorithmic HBM bytes "
+                  "(DESIGN.md) ~ 16 x (480*640*8 + 19905*9*8 + 256*9*8) = 62.5 MB; DRAM traffic above is the measured "
+                  "figure.  The kernel is FP32-issue bound (issue-active and pipe % above), not HBM bound: see DESIGN.md §3."]
+    open(md, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines[6:]))
 
 
 def launch_list(csvf, md, steps=2):
@@ -148,5 +185,7 @@ if __name__ == "__main__":
         conv(sys.argv[2], sys.argv[3], sys.argv[4])
     elif cmd == "list":
         launch_list(sys.argv[2], sys.argv[3])
+    elif cmd == "vote":
+        vote(sys.argv[2], sys.argv[3])
     elif cmd == "top":
         top(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 16)

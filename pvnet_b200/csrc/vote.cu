@@ -319,7 +319,7 @@ __device__ __forceinline__ void count_if_gt(int &cnt, float a, float b)
 // split wh (hypothesis groups of 128) x wp (pixel interleave); each lane owns
 // VT_HPL hypotheses; pixels come from shared memory as one broadcast LDS.128.
 template <int HPL, int TILE>
-__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
+__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 4)
     k_vote(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
            const int *__restrict__ tn_arr, int npx, int nb, int vn, int hn, int wh,
            const float2 *__restrict__ hyp, int *__restrict__ counts, float thresh, float t2, float band)
@@ -1112,8 +1112,9 @@ int launch_hyp_and_vote(const float *vertex, const Strides &st, const int32_t *i
     k_gen_hyp<<<ghyp, 256, 0, s>>>(vertex, st, idxs, ws.pix, ws.tn, npx, vn, hn, ws.hyp);
     PV_LAUNCHED("k_gen_hyp");
     // (hypotheses per lane, pixels per tile): items are (tile, keypoint, hypothesis group) on a static
-    // round-robin over 3 CTAs per SM, so small tiles keep the last round short (2048-pixel tiles:
-    // 1440 items on 444 CTAs = 4 rounds for 3.2 rounds of work at 16 x 20k px, K=9, 256 hyp).
+    // round-robin over 4 CTAs per SM (63 registers; +2..4 % over 3 CTAs in the sweep), so small tiles
+    // keep the last round short (2048-pixel tiles: 1440 items on 444 CTAs = 4 rounds for 3.2 rounds of
+    // work at 16 x 20k px, K=9, 256 hyp).
     static const int cfg = [] {
         const char *e = getenv("PVNET_VOTE_CFG");      // tuning knob: 0 = 4x2048, 1 = 4x512, 2 = 8x512, 3 = 8x1024
         return e ? atoi(e) : 1;
@@ -1124,7 +1125,11 @@ int launch_hyp_and_vote(const float *vertex, const Strides &st, const int32_t *i
     while (wh < VT_WARPS && wh * 32 * HPL < hn) wh <<= 1;
     const int HC = wh * 32 * HPL;
     const long long max_items = (long long)b * ((npx + TILE - 1) / TILE) * vn * ((hn + HC - 1) / HC);
-    long long grid = (long long)pvnet::sm_count() * (HPL > 4 ? 2 : 3);
+    static const int ctas_per_sm = [] {
+        const char *e = getenv("PVNET_VOTE_CTAS");     // tuning knob: resident vote CTAs per SM (HPL 4), default 4
+        return e ? atoi(e) : 4;
+    }();
+    long long grid = (long long)pvnet::sm_count() * (HPL > 4 ? 2 : ctas_per_sm);
     if (grid > max_items) grid = max_items;
     // thresh <= 0 (or NaN) has no squared form: NaN makes every test take the exact path
     const float t2 = (thresh > 0.f && thresh < 1e18f) ? thresh * thresh : nanf("");
