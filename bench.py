@@ -408,7 +408,7 @@ def main():
             "roofline": roofline,
             "stages_ms": stages,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:        # the host-core baseline is an N=1 figure
             try:
                 line["cpu_baseline"] = cpu_path_baseline()
             except Exception as e:          # the checker being unavailable must not hide the GPU number
