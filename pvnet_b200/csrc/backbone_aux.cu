@@ -233,16 +233,18 @@ __global__ void __launch_bounds__(256)
     k_upsample2x(const float *__restrict__ in, float *__restrict__ out, int h, int w, int C, int out_cs, int out_co,
                  float sy, float sx)
 {
-    // One thread = the 2x2 output block (2j..2j+1, 2k..2k+1) of one 4-channel group.  With
+    // One thread = the 2x2 output block (2j..2j+1, 2k..2k+1) of 4-channel groups cg, cg+8, ...  With
     // align_corners=True and scale 2 the source rows of output rows 2j, 2j+1 all lie in
     // {j-1, j, j+1} (same for columns), so the block needs a 3x3 neighbourhood: 9 loads for 4
     // outputs instead of 16.  Each output keeps PyTorch's separable form
-    // h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11); the third row/column enters with weight 0.
-    // grid.y = image * h + j; threads cover (k, channel group).
+    // h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11); the third row/column enters with weight 0 (and a
+    // clamped row/column index reproduces v10 = v00 at the border, as ATen's index clamp does).
+    // The kernel was instruction-issue bound (ncu: 79 % issue-active, 31 instructions per output
+    // float), so weights and offsets are computed once per thread and kept in 32-bit arithmetic.
+    // blockDim = (8 channel groups, 32 pixel pairs); grid.y = image * h + j.
     const int c4 = C >> 2;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w * c4) return;
-    const int k = i / c4, cg = i - k * c4;
+    const int k = blockIdx.x * blockDim.y + threadIdx.y;
+    if (k >= w) return;
     const int n = blockIdx.y / h, j = blockIdx.y - n * h;
 
     float wy[2][3], wx[2][3];
@@ -250,51 +252,66 @@ __global__ void __launch_bounds__(256)
     for (int o = 0; o < 2; ++o) {
         const float fy = sy * (float)(2 * j + o), fx = sx * (float)(2 * k + o);
         const int y0 = (int)fy, x0 = (int)fx;
-        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
         const float h1 = fy - (float)y0, h0 = 1.f - h1, w1 = fx - (float)x0, w0 = 1.f - w1;
-        const int iy0 = y0 - (j - 1), iy1 = y1 - (j - 1), ix0 = x0 - (k - 1), ix1 = x1 - (k - 1);
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            wy[o][r] = (r == iy0 ? h0 : 0.f) + (r == iy1 ? h1 : 0.f);
-            wx[o][r] = (r == ix0 ? w0 : 0.f) + (r == ix1 ? w1 : 0.f);
-        }
+        const bool uy = y0 >= j, ux = x0 >= k;          // source pair is rows (j, j+1) rather than (j-1, j)
+        wy[o][0] = uy ? 0.f : h0;
+        wy[o][1] = uy ? h0 : h1;
+        wy[o][2] = uy ? h1 : 0.f;
+        wx[o][0] = ux ? 0.f : w0;
+        wx[o][1] = ux ? w0 : w1;
+        wx[o][2] = ux ? w1 : 0.f;
     }
-    const float4 *base = reinterpret_cast<const float4 *>(in) + (size_t)n * h * w * c4 + cg;
-    float4 t[3][2];                                      // per source row: the two horizontally interpolated values
+    // element offsets of the 3x3 neighbourhood (clamped) and of the 2x2 outputs; 32-bit by contract
+    unsigned ioff[3][3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const int y = min(max(j - 1 + r, 0), h - 1);
-        const float4 *row = base + (size_t)y * w * c4;
-        const float4 a = __ldg(row + max(k - 1, 0) * c4), bq = __ldg(row + k * c4),
-                     c = __ldg(row + min(k + 1, w - 1) * c4);
+        const unsigned y = (unsigned)min(max(j - 1 + r, 0), h - 1);
+        const unsigned rowb = ((unsigned)n * h + y) * (unsigned)w;
 #pragma unroll
-        for (int o = 0; o < 2; ++o) {
-            t[r][o].x = wx[o][0] * a.x + wx[o][1] * bq.x + wx[o][2] * c.x;
-            t[r][o].y = wx[o][0] * a.y + wx[o][1] * bq.y + wx[o][2] * c.y;
-            t[r][o].z = wx[o][0] * a.z + wx[o][1] * bq.z + wx[o][2] * c.z;
-            t[r][o].w = wx[o][0] * a.w + wx[o][1] * bq.w + wx[o][2] * c.w;
-        }
+        for (int c = 0; c < 3; ++c) ioff[r][c] = (rowb + (unsigned)min(max(k - 1 + c, 0), w - 1)) * (unsigned)C;
     }
-    const int Wo = 2 * w;
+    const unsigned Wo = 2u * w;
+    const unsigned o00 = (((unsigned)n * 2u * h + 2u * j) * Wo + 2u * k) * (unsigned)out_cs + (unsigned)out_co;
+    const unsigned orow = Wo * (unsigned)out_cs;
+
+    for (int cg = threadIdx.x; cg < c4; cg += 8) {
+        const float *ip = in + cg * 4;
+        float4 t[3][2];                                   // per source row: the two horizontally interpolated values
 #pragma unroll
-    for (int oy = 0; oy < 2; ++oy)
+        for (int r = 0; r < 3; ++r) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(ip + ioff[r][0]));
+            const float4 bq = __ldg(reinterpret_cast<const float4 *>(ip + ioff[r][1]));
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(ip + ioff[r][2]));
 #pragma unroll
-        for (int ox = 0; ox < 2; ++ox) {
-            float4 v;
-            v.x = ptx::round_tf32(wy[oy][0] * t[0][ox].x + wy[oy][1] * t[1][ox].x + wy[oy][2] * t[2][ox].x);
-            v.y = ptx::round_tf32(wy[oy][0] * t[0][ox].y + wy[oy][1] * t[1][ox].y + wy[oy][2] * t[2][ox].y);
-            v.z = ptx::round_tf32(wy[oy][0] * t[0][ox].z + wy[oy][1] * t[1][ox].z + wy[oy][2] * t[2][ox].z);
-            v.w = ptx::round_tf32(wy[oy][0] * t[0][ox].w + wy[oy][1] * t[1][ox].w + wy[oy][2] * t[2][ox].w);
-            const size_t pix = ((size_t)n * 2 * h + 2 * j + oy) * Wo + 2 * k + ox;
-            *reinterpret_cast<float4 *>(out + pix * out_cs + out_co + cg * 4) = v;
+            for (int o = 0; o < 2; ++o) {
+                t[r][o].x = wx[o][0] * a.x + wx[o][1] * bq.x + wx[o][2] * c.x;
+                t[r][o].y = wx[o][0] * a.y + wx[o][1] * bq.y + wx[o][2] * c.y;
+                t[r][o].z = wx[o][0] * a.z + wx[o][1] * bq.z + wx[o][2] * c.z;
+                t[r][o].w = wx[o][0] * a.w + wx[o][1] * bq.w + wx[o][2] * c.w;
+            }
         }
+        float *op = out + cg * 4;
+#pragma unroll
+        for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+            for (int ox = 0; ox < 2; ++ox) {
+                float4 v;
+                v.x = ptx::round_tf32(wy[oy][0] * t[0][ox].x + wy[oy][1] * t[1][ox].x + wy[oy][2] * t[2][ox].x);
+                v.y = ptx::round_tf32(wy[oy][0] * t[0][ox].y + wy[oy][1] * t[1][ox].y + wy[oy][2] * t[2][ox].y);
+                v.z = ptx::round_tf32(wy[oy][0] * t[0][ox].z + wy[oy][1] * t[1][ox].z + wy[oy][2] * t[2][ox].z);
+                v.w = ptx::round_tf32(wy[oy][0] * t[0][ox].w + wy[oy][1] * t[1][ox].w + wy[oy][2] * t[2][ox].w);
+                *reinterpret_cast<float4 *>(op + o00 + (unsigned)oy * orow + (unsigned)ox * (unsigned)out_cs) = v;
+            }
+    }
 }
 
 int launch_upsample2x(const float *in, float *out, int b, int h, int w, int C, int out_cs, int out_co, cudaStream_t s)
 {
+    PV_CHECK_ARG((long long)b * 4 * h * w * out_cs < (1LL << 32) && (long long)b * h * w * C < (1LL << 32),
+                 "upsample: tensor too large for 32-bit element offsets");
     const float sy = (float)(h - 1) / (float)(2 * h - 1), sx = (float)(w - 1) / (float)(2 * w - 1);
-    dim3 grid((unsigned)((w * (C / 4) + 255) / 256), (unsigned)(b * h));
-    k_upsample2x<<<grid, 256, 0, s>>>(in, out, h, w, C, out_cs, out_co, sy, sx);
+    dim3 grid((unsigned)((w + 31) / 32), (unsigned)(b * h));
+    k_upsample2x<<<grid, dim3(8, 32), 0, s>>>(in, out, h, w, C, out_cs, out_co, sy, sx);
     PV_LAUNCHED("k_upsample2x");
     return PVNET_OK;
 }

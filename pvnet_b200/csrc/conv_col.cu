@@ -31,7 +31,6 @@ int g_conv_mode = 0;
 
 namespace {
 
-constexpr int COL_THREADS = 192;
 constexpr int COL_TH = 16, COL_TW = 8;
 constexpr int HEAD_MAX = 64;
 

@@ -43,8 +43,7 @@ constexpr int CH_PX = 2048;       // pixels per compaction chunk
 constexpr int CH_THREADS = 256;   // 8 consecutive pixels per thread
 constexpr int VT_THREADS = 256;
 constexpr int VT_WARPS = VT_THREADS / 32;
-constexpr int VT_TILE = 2048;     // pixels per shared-memory tile (16 B each)
-constexpr int VT_HPL = 4;         // hypotheses held in registers per lane
+constexpr int VT_HPL = 4;         // hypotheses per lane of the packed variant (k_vote is templated on HPL and tile size)
 constexpr int VT_MAX_B = 1024;    // images per call (prefix table in shared memory)
 constexpr int RF_CHUNKS = 8;      // CTAs per (image, keypoint) in the refit pass
 constexpr int RF_THREADS = 256;
