@@ -46,6 +46,7 @@ struct ConvGeom {
     // remaining (M tile, N tile) pairs is cut into tail_split items of tail_bn channels so that the
     // last, partially filled round of the static schedule costs a fraction of a full round
     int n_full, n_items, tail_bn, tail_split;
+    int stages;     // persistent kernel: depth of the TMA ring (4..8, as many as fit next to the staging buffers)
 };
 
 // item index -> (M tile, first output channel, channels) of the persistent schedule
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2)
                  const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out)
 {
     using Cfg = ConvCfg<KC>;
-    constexpr int STAGES = Cfg::STAGES;
+    const int STAGES = g.stages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = g.BN * KC * 4;
@@ -648,6 +649,23 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
     p->persist = (p->mc == 0 && g_conv_persist) ? 1 : 0;
     p->tmO = p->tmB;
     if (p->persist) {
+        // ring depth: 4 stages when two CTAs share the SM (BN <= 64), otherwise as many (<= 8) as fit
+        // next to the 32 KB of epilogue staging: BN=128 tiles need 128 B/clk/SM of L2->SM fill at full
+        // MMA rate, a deeper ring covers more of the L2 latency
+        const size_t stage_b = (size_t)ConvCfg<32>::A_BYTES + (size_t)g.BN * 32 * 4;
+        static const int env_stages = [] {
+            const char *e = getenv("PVNET_CONV_STAGES");        // tuning knob: 0 = auto
+            return e ? atoi(e) : 0;
+        }();
+        int st = 4;
+        if (g.BN > 64) {
+            st = (int)((227 * 1024 - 32768 - 2048) / stage_b);
+            if (st > 8) st = 8;
+            if (st < 4) st = 4;
+        }
+        if (env_stages >= 2 && env_stages <= 8 && 1024 + env_stages * stage_b + 256 + 32768 <= 227 * 1024) st = env_stages;
+        g.stages = st;
+        p->smem = 1024 + (size_t)st * stage_b + 256;
         p->smem += 32768;                       // staging buffers of the TMA-store epilogue
         cuuint64_t odims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)d.b};
         cuuint64_t ostr[3] = {(cuuint64_t)d.out_cs * 4, (cuuint64_t)g.Wo * d.out_cs * 4,
@@ -705,7 +723,7 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
 
 int conv_launch(const ConvPlan &p, cudaStream_t s)
 {
-    const int max_smem = (int)ConvCfg<32>::smem_bytes(256) + 32768;
+    const int max_smem = 227 * 1024;
     const void *fn = p.mc == 2 ? (const void *)k_conv_tc<32, 2>
                      : p.mc == 1 ? (const void *)k_conv_tc<32, 1>
                      : p.persist ? (const void *)k_conv_tap_p<32> : (const void *)k_conv_tc<32, 0>;
