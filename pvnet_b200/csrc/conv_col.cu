@@ -15,7 +15,9 @@
 //     strides need not be multiples of the 1024-byte swizzle repeat (verified on B200 by
 //     benchmarks/micro/desc_offset.cu).  A traffic drops from 9x (per-tap kernel) and 3.75x (one
 //     box per kernel column, the previous scheme) to (TH+2)(TW+2)/(TH*TW) = 1.41x;
-//   * two TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * two TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1; with
+//     EPI = 2 two epilogue warp sets alternate tiles (short-K layers are epilogue-bound);
+//   * TMA-store epilogue shared with conv_tc.cu (conv_tc.cuh: epi_activate / epi_stage / ...);
 //   * optional fused head (convraw.3 1x1 + bias + argmax, exact fp32) in the epilogue, writing
 //     the reference's NCHW output directly -- the [b,H,W,32] intermediate never exists.
 #include "conv_tc.cuh"

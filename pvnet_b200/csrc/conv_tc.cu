@@ -16,8 +16,15 @@
 //   warp 1    TMEM allocation; one elected lane issues tcgen05.mma.kind::tf32 (fp32
 //             accumulate in TMEM) and commits to the stage's "empty" mbarrier.
 //   warps 2-5 epilogue: tcgen05.ld 32 columns at a time -> +bias (+residual) -> ReLU /
-//             LeakyReLU(0.1) -> optional round-to-tf32 -> 128-bit NHWC stores at a channel
-//             offset of a (possibly wider) destination buffer, so torch.cat never happens.
+//             LeakyReLU(0.1) -> optional round-to-tf32 -> NHWC output at a channel offset of a
+//             (possibly wider) destination buffer, so torch.cat never happens.  The persistent
+//             kernel (k_conv_tap_p, the one the backbone runs) stages each warp's 32 pixels x 32
+//             channels in shared memory and stores them with one TMA box; k_conv_tc keeps
+//             direct 128-bit stores.
+//
+// k_conv_tap_p adds: CTAs persistent over (M tile, N tile) items with a continuous TMA ring
+// (4..8 stages, as many as fit), two TMEM accumulator stages (epilogue of item i overlaps the MMAs
+// of item i+1), and the tail split of the static schedule (see conv_plan).
 //
 // Stride-2 convolutions read the input through four "parity plane" tensor maps (even/odd
 // rows x even/odd columns); each tap then is a stride-1 box in one plane.
