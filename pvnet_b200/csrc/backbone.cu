@@ -39,6 +39,7 @@ struct pvnet_backbone {
     bool use_col[CV_COUNT] = {};         // slot runs on the persistent column kernel (conv_col.cu)
     bool head_fused = false;             // convraw.3 + argmax run inside convraw.0's epilogue
     bool stem_tc = false;                // stem runs as a 4x4 conv on the space-to-depth image
+    bool raw_split = false;              // convraw.0 reads the upsampled features and the image slice from two dense buffers
 };
 
 static size_t plan_stride()
@@ -173,8 +174,27 @@ int build_plans(pvnet_backbone *m, const Buffers &B, int b, int h, int w)
     if ((rc = plan(CV_CONV8S, cd(m, CV_CONV8S, B.C8, c8s, 0, c8s, B.U8, m->s8, 0, m->s8, b, h8, w8, 3, 1, 1, 2)))) return rc;
     if ((rc = plan(CV_CONV4S, cd(m, CV_CONV4S, B.C4, c4s, 0, c4s, B.U4, m->s4, 0, m->s4, b, h4, w4, 3, 1, 1, 2)))) return rc;
     if ((rc = plan(CV_CONV2S, cd(m, CV_CONV2S, B.C2, c2s, 0, c2s, B.U2, m->s2, 0, m->s2, b, h2, w2, 3, 1, 1, 2)))) return rc;
-    if ((rc = plan(CV_CONVRAW0, cd(m, CV_CONVRAW0, B.C1, c1s, 0, c1s, B.R0, m->raw, 0, m->raw, b, h, w, 3, 1, 1, 2,
-                                   nullptr, 0, 0, /*round_out=*/0)))) return rc;
+    // convraw.0 reads cat(upsampled features [s2], image [3 -> 8]).  With the column kernel the two
+    // parts live in two dense buffers (the first p1*s2 and the next p1*8 floats of C1) read through two
+    // tensor maps: a 32-byte image slice inside every 160-byte record made both producers write at
+    // ~2 TB/s.  The per-tap kernel (test mode) keeps the single interleaved buffer.
+    ConvDesc draw = cd(m, CV_CONVRAW0, B.C1, c1s, 0, c1s, B.R0, m->raw, 0, m->raw, b, h, w, 3, 1, 1, 2, nullptr, 0, 0,
+                       /*round_out=*/0);
+    m->raw_split = false;
+    if (g_conv_mode != 1 && m->s2 % 8 == 0) {
+        ConvDesc ds = draw;
+        ds.in_cs = m->s2;
+        ds.Cin = m->s2;
+        ds.in2 = B.C1 + (size_t)b * h * w * m->s2;
+        ds.in2_cs = 8;
+        ds.in2_co = 0;
+        ds.Cin2 = 8;
+        if (conv_col_eligible(ds)) {
+            draw = ds;
+            m->raw_split = true;
+        }
+    }
+    if ((rc = plan(CV_CONVRAW0, draw))) return rc;
     return PVNET_OK;
 }
 
@@ -297,6 +317,8 @@ int run_stage(pvnet_backbone *m, const Stage &st, const Buffers &B, const float 
         if (m->stem_tc) return conv_col_launch_at(m->plans.data() + plan_stride() * CV_STEM_TC, s);
         return launch_stem(image_nchw, m->w[CV_STEM], m->bias[CV_STEM], B.C2, b, h, w, c2s, m->s4, s);
     case ST_PACK:
+        if (m->stem_tc && m->raw_split)
+            return launch_s2d_pack(image_nchw, B.S2D, B.C1 + (size_t)b * h * w * m->s2, b, h, w, 8, 0, s);
         if (m->stem_tc) return launch_s2d_pack(image_nchw, B.S2D, B.C1, b, h, w, c1s, m->s2, s);
         return launch_pack_image(image_nchw, B.C1, b, h, w, c1s, m->s2, s);
     case ST_POOL: return launch_maxpool(B.C2, B.P, b, h2, w2, 64, c2s, m->s4, s);
@@ -308,7 +330,7 @@ int run_stage(pvnet_backbone *m, const Stage &st, const Buffers &B, const float 
     }
     case ST_UP8: return launch_upsample2x(B.U8, B.C4, b, h8, w8, m->s8, c4s, 0, s);
     case ST_UP4: return launch_upsample2x(B.U4, B.C2, b, h4, w4, m->s4, c2s, 0, s);
-    case ST_UP2: return launch_upsample2x(B.U2, B.C1, b, h2, w2, m->s2, c1s, 0, s);
+    case ST_UP2: return launch_upsample2x(B.U2, B.C1, b, h2, w2, m->s2, m->raw_split ? m->s2 : c1s, 0, s);
     case ST_HEAD:
         if (m->head_fused) return PVNET_OK;    // already written by convraw.0's epilogue
         return launch_head(B.R0, m->w[CV_HEAD], m->bias[CV_HEAD], out_nchw, mask_out, mask_elem_size, m->seg_dim,

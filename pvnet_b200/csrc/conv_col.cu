@@ -39,6 +39,7 @@ constexpr int HEAD_MAX = 64;
 struct ColGeom {
     int Ho, Wo, tiles_x, tiles_y, total_tiles;
     int dil, cin_chunks, cin_pad;
+    int split_chunk;        // chunks >= split_chunk are read through the second source map (== cin_chunks: none)
     int KW, KH, pad_l, pad_t;   // taps and how many of them lie left of / above the output pixel
     int BN;                 // == Cout (<= 64)
     int stages;
@@ -55,7 +56,8 @@ struct ColGeom {
 // EPI = 2 the sets alternate tiles, one per TMEM accumulator stage.
 template <int KC, bool HEAD, int KH, int EPI>
 __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
-    k_conv_col(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+    k_conv_col(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmO, const ColGeom g,
                const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out,
                const float *__restrict__ head_w, const float *__restrict__ head_b, float *__restrict__ head_out,
@@ -150,7 +152,10 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
                     ptx::mbar_arrive_expect_tx(&full[s], tx_bytes);
                     uint8_t *st = sA + (size_t)s * stage_bytes;
-                    ptx::tma_load_4d(st, &tmA, &full[s], cc * KC, x0 - g.pad_l, y0 - g.pad_t, img);
+                    if (cc < g.split_chunk)
+                        ptx::tma_load_4d(st, &tmA, &full[s], cc * KC, x0 - g.pad_l, y0 - g.pad_t, img);
+                    else
+                        ptx::tma_load_4d(st, &tmA2, &full[s], (cc - g.split_chunk) * KC, x0 - g.pad_l, y0 - g.pad_t, img);
                     if (!g.resident)
                         for (int t = 0; t < KH * KH; ++t)
                             ptx::tma_load_2d(st + a_bytes + (size_t)t * b_tile, &tmB, &full[s],
@@ -378,7 +383,7 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
 }
 
 struct ColPlan {
-    CUtensorMap tmA, tmB, tmH, tmO;
+    CUtensorMap tmA, tmA2, tmB, tmH, tmO;
     ColGeom g;
     int kc, head, epi;
     unsigned grid;
@@ -418,10 +423,11 @@ bool conv_col_eligible(const ConvDesc &d)
     // ksize 4 = the space-to-depth form of the 7x7/2 stem: taps at offsets {-2,-1,0,1}
     if ((d.ksize != 3 && d.ksize != 4) || d.stride != 1 || d.dilation != 1 || d.Cout > 64 || d.Cout % 32 != 0)
         return false;
-    const int kc = col_kc(d.Cin);
-    if (d.Cin % kc != 0) return false;
+    const int cin = d.Cin + d.Cin2;
+    const int kc = col_kc(cin);
+    if (d.Cin % kc != 0 || d.Cin2 % kc != 0) return false;
     if ((d.ksize == 4) != (kc == 16)) return false;   // instantiated: 4x4 taps with 16 channels, 3x3 otherwise
-    return col_smem(kc, d.ksize, (d.Cin + kc - 1) / kc, d.Cout, d.dilation, 2, HEAD_MAX, false) <= SMEM_LIMIT;
+    return col_smem(kc, d.ksize, (cin + kc - 1) / kc, d.Cout, d.dilation, 2, HEAD_MAX, false) <= SMEM_LIMIT;
 }
 
 size_t conv_col_plan_size() { return sizeof(ColPlan); }
@@ -434,10 +440,10 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     PV_CHECK_ARG(d.in_cs % 4 == 0 && d.in_co % 4 == 0 && d.out_cs % 4 == 0 && d.out_co % 4 == 0,
                  "conv(col): channel strides/offsets must be multiples of 4 floats");
     PV_CHECK_ARG(!d.res || (d.res_cs % 4 == 0 && d.res_co % 4 == 0), "conv(col): residual stride/offset alignment");
-    PV_CHECK_ARG(!head || (d.Cout == 32 && col_kc(d.Cin) != 16 && head->cout >= 1 && head->cout <= 32 && head->w && head->bias &&
+    PV_CHECK_ARG(!head || (d.Cout == 32 && col_kc(d.Cin + d.Cin2) != 16 && head->cout >= 1 && head->cout <= 32 && head->w && head->bias &&
                            head->out_nchw && (!head->mask || head->mask_esz == 1 || head->mask_esz == 8)),
                  "conv(col): bad fused-head description");
-    const int kc = col_kc(d.Cin);
+    const int kc = col_kc(d.Cin + d.Cin2);
     ColGeom &g = p->g;
     g.KW = g.KH = d.ksize;
     g.pad_l = g.pad_t = d.ksize == 4 ? 2 : 1;
@@ -447,8 +453,9 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     g.tiles_y = (d.H + COL_TH - 1) / COL_TH;
     g.total_tiles = g.tiles_x * g.tiles_y * d.b;
     g.dil = d.dilation;
-    g.cin_chunks = d.Cin / kc;
-    g.cin_pad = col_cin_pad(d.Cin);         // weights are packed [Cout][KH][KW][cin_pad], zero padded
+    g.cin_chunks = (d.Cin + d.Cin2) / kc;
+    g.split_chunk = d.in2 ? d.Cin / kc : g.cin_chunks;
+    g.cin_pad = col_cin_pad(d.Cin + d.Cin2);   // weights are packed [Cout][KH][KW][cin_pad], zero padded
     g.BN = d.Cout;
     g.out_cs = d.out_cs;
     g.out_co = d.out_co;
@@ -491,6 +498,17 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
         cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(COL_TW + (d.ksize - 1) * d.dilation),
                              (cuuint32_t)(COL_TH + (d.ksize - 1) * d.dilation), 1};
         int rc = tma_encode(&p->tmA, base, 4, dims, strides, box, kc * 4);
+        if (rc) return rc;
+    }
+    p->tmA2 = p->tmA;
+    if (d.in2) {
+        PV_CHECK_ARG(d.in2_cs % 4 == 0 && d.in2_co % 4 == 0 && d.Cin2 > 0, "conv(col): second source stride/offset alignment");
+        cuuint64_t dims[4] = {(cuuint64_t)d.Cin2, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.b};
+        cuuint64_t strides[3] = {(cuuint64_t)d.in2_cs * 4, (cuuint64_t)d.W * d.in2_cs * 4,
+                                 (cuuint64_t)d.H * d.W * d.in2_cs * 4};
+        cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(COL_TW + (d.ksize - 1) * d.dilation),
+                             (cuuint32_t)(COL_TH + (d.ksize - 1) * d.dilation), 1};
+        int rc = tma_encode(&p->tmA2, d.in2 + d.in2_co, 4, dims, strides, box, kc * 4);
         if (rc) return rc;
     }
     {
@@ -558,7 +576,7 @@ int conv_col_launch_at(const void *storage, cudaStream_t s)
     PV_CUDA(attr_err);
     const HeadDesc &h = p.hd;
 #define COL_LAUNCH(KC_, HEAD_, KH_, EPI_)                                                                         \
-    k_conv_col<KC_, HEAD_, KH_, EPI_><<<p.grid, 64 + 128 * EPI_, p.smem, s>>>(p.tmA, p.tmB, p.tmH, p.tmO, p.g, p.bias, p.res, p.out,           \
+    k_conv_col<KC_, HEAD_, KH_, EPI_><<<p.grid, 64 + 128 * EPI_, p.smem, s>>>(p.tmA, p.tmA2, p.tmB, p.tmH, p.tmO, p.g, p.bias, p.res, p.out,           \
                                                                 p.head ? h.w : nullptr, p.head ? h.bias : nullptr, \
                                                                 p.head ? h.out_nchw : nullptr, p.head ? h.mask : nullptr)
     if (p.kc == 32 && !p.head && p.epi == 2) COL_LAUNCH(32, false, 3, 2);

@@ -568,6 +568,7 @@ int conv_kc(int) { return 32; }   // ragged last channel chunk: TMA zero-fills, 
 int conv_plan(const ConvDesc &d, ConvPlan *p)
 {
     PV_CHECK_ARG(d.in && d.w && d.bias && d.out, "conv: null pointer");
+    PV_CHECK_ARG(!d.in2, "conv: a second input source is only supported by the column kernel");
     PV_CHECK_ARG(d.ksize == 1 || d.ksize == 3, "conv: kernel size %d unsupported", d.ksize);
     PV_CHECK_ARG(d.stride == 1 || d.stride == 2, "conv: stride %d unsupported", d.stride);
     PV_CHECK_ARG(d.stride == 1 || (d.dilation == 1 && d.H % 2 == 0 && d.W % 2 == 0),

@@ -22,6 +22,11 @@ struct ConvDesc {
     int b, H, W;
     int ksize, stride, dilation;
     int act, round_out;
+    // optional second source (column kernel only): channels [Cin, Cin+Cin2) of the convolution come
+    // from in2 [b,H,W,in2_cs] at in2_co -- a torch.cat on the READ side, so that both producers of a
+    // concatenated input write dense records of their own
+    const float *in2 = nullptr;
+    int in2_cs = 0, in2_co = 0, Cin2 = 0;
 };
 
 // Optional fused 1x1 head (convraw.3 + argmax) for the column kernel's epilogue.
