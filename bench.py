@@ -175,19 +175,23 @@ def conv_roofline(torch, net, x, peaks):
     ns = L.pvnet_backbone_num_stages()
     names = [L.pvnet_backbone_stage_name(i).decode() for i in range(ns)]
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    reps = 5
-    acc = np.zeros(ns)
-    for rep in range(reps + 1):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(ns + 1)]
-        ev[0].record()
+    # 5 untimed forwards, then 20 timed ones enqueued back to back (one synchronize at the end, so the
+    # GPU stays as busy -- and as power-capped -- as in the timed loop); per-stage median over the reps
+    warm, reps = 5, 20
+    evs = []
+    for rep in range(warm + reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(ns + 1)] if rep >= warm else None
+        if ev:
+            ev[0].record()
         for i in range(ns):
             _native.check(L.pvnet_backbone_run_stage(handle, i, x.data_ptr(), b, H, W, out.data_ptr(), mask.data_ptr(),
                                                      8, ws.data_ptr(), ws.numel(), stream), "run_stage")
-            ev[i + 1].record()
-        torch.cuda.synchronize()
-        if rep:
-            acc += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(ns)])
-    ms = acc / reps
+            if ev:
+                ev[i + 1].record()
+        if ev:
+            evs.append(ev)
+    torch.cuda.synchronize()
+    ms = np.median(np.array([[ev[i].elapsed_time(ev[i + 1]) for i in range(ns)] for ev in evs]), axis=0)
     is_conv = np.array([("layer" in nm or nm.startswith("fc") or nm.startswith("conv")) and "head" not in nm
                         for nm in names])
     conv_ms = float(ms[is_conv].sum())
