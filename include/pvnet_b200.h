@@ -20,6 +20,7 @@
  *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:333-406      estimate_voting_distribution_with_mean
  *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:763-858      ransac_voting_layer_v5
  *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:983-1034     generate_hypothesis (python level)
+ *   tools/train_linemod.py:119-130                                UncertaintyEvalWrapper.forward (v3 + with_mean)
  *   lib/networks/model_repository.py:64-80                        Resnet18_8s.forward
  * INTEGRATION.md shows the ctypes binding the reference's Python wrapper uses.
  */
@@ -156,6 +157,39 @@ PVNET_API int pvnet_vote_cov_with_mean(const void *mask, int mask_elem_size,
                                        float *out_cov, int32_t *out_counts, float *out_hyp, int32_t *out_tn,
                                        void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
 
+/* The uncertainty pipeline of tools/train_linemod.py:119-130 (`UncertaintyEvalWrapper.forward`):
+ *     mean      = ransac_voting_layer_v3(mask, vertex, hn, inlier_thresh)            (ransac_voting_gpu.py:514-598)
+ *     mean, cov = estimate_voting_distribution_with_mean(mask, vertex, mean, ...)     (ransac_voting_gpu.py:333-406)
+ * as ONE launch sequence: the mask is compacted and the vector field gathered once for both
+ * layers, and when both thresholds agree one kernel scores the v3 and the covariance hypotheses
+ * together.  out_cov == NULL runs the v3 part alone.
+ *
+ *   mask_mode  how BOTH layers read the mask.  The reference's v3 takes nonzero (:527) and
+ *              with_mean takes == 1 (:339); for the binary argmax mask of a 2-class network the
+ *              two agree and either mode gives the reference's result.  (Callers with other
+ *              masks use the two separate entry points.)
+ *   idxs       int32 [b,hn,vn,2] or NULL; cov_idxs int32 [b,cov_rounds*cov_hn,vn,2] or NULL;
+ *              selection f32 [b,h,w] or NULL (one field for both layers)
+ *   rng_state  DEVICE pointer to {uint64 seed, uint64 offset} or NULL.  Whatever sample set is
+ *              NULL is drawn on the device (Philox4x32-10; idxs = 32 random bits modulo tn like
+ *              torch's random_, selection = 24 bits * 2^-24 like uniform_); the call then advances
+ *              the offset, so a captured CUDA graph draws fresh samples on every replay.
+ *              With rng_state == NULL a NULL selection means "never subsample".
+ *   out_pts    f32 [b,vn,2]; out_cov f32 [b,vn,2,2] or NULL
+ *   out_counts/out_hyp [b,hn,vn(,2)], out_cov_counts/out_cov_hyp [b,cov_rounds*cov_hn,vn(,2)],
+ *   out_tn [b]: optional debug outputs.
+ *   Workspace: pvnet_vote_workspace_bytes(b, h, w, vn, hn + cov_rounds*cov_hn). */
+PVNET_API int pvnet_ransac_voting_pipeline(const void *mask, int mask_elem_size, int mask_mode,
+                                           const float *vertex, const int64_t vertex_strides[5],
+                                           const int32_t *idxs, const int32_t *cov_idxs, const float *selection,
+                                           const unsigned long long *rng_state,
+                                           int b, int h, int w, int vn, int hn, float inlier_thresh,
+                                           int cov_hn, int cov_rounds, int cov_min_hyp_num, float cov_inlier_thresh,
+                                           int min_num, int max_num, float *out_pts, float *out_cov,
+                                           int32_t *out_counts, float *out_hyp,
+                                           int32_t *out_cov_counts, float *out_cov_hyp, int32_t *out_tn,
+                                           void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
+
 /* 1:1 stand-ins for the reference extension's two functions, same layouts:
  * direct [tn,vn,2] f32, coords [tn,2] f32 (x,y), idxs [hn,vn,2] i32, hypo [hn,vn,2] f32.
  * pvnet_generate_hypothesis writes every element of hypo (degenerate pairs -> (0,0),
@@ -247,6 +281,15 @@ PVNET_API int pvnet_backbone_workspace_bytes(const pvnet_backbone_t *m, int b, i
 PVNET_API int pvnet_backbone_forward(pvnet_backbone_t *m, const float *image_nchw, int b, int h, int w,
                                      float *out_nchw, void *mask_out, int mask_elem_size,
                                      void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
+/* Same forward pass from a RAW image batch: image_hwc uint8 [b,h,w,3] (what an image decoder yields),
+ * normalised on the device inside the packing kernel with torchvision's ToTensor + Normalize
+ * arithmetic, (float(v)/255 - mean[c]) / std[c] in fp32 (tools/demo.py:89-95,
+ * lib/datasets/linemod_dataset.py:191-195): bit-identical to pvnet_backbone_forward on the
+ * torch-normalised float tensor, a quarter of the input bytes.  mean/std are HOST arrays. */
+PVNET_API int pvnet_backbone_forward_u8(pvnet_backbone_t *m, const uint8_t *image_hwc, const float mean[3],
+                                        const float std[3], int b, int h, int w,
+                                        float *out_nchw, void *mask_out, int mask_elem_size,
+                                        void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
 /* The forward pass is an ordered list of single-kernel stages; these run/describe one of
  * them with the same arguments (per-layer timing in bench.py, layer-wise parity tests). */
 PVNET_API int pvnet_backbone_num_stages(void);

@@ -42,6 +42,13 @@ struct pvnet_backbone {
     bool raw_split = false;              // convraw.0 reads the upsampled features and the image slice from two dense buffers
 };
 
+// where the image comes from: float32 NCHW (already normalised) or raw uint8 HWC + mean/std
+struct ImageSrc {
+    const void *ptr;
+    int is_u8;
+    float mean[3], std[3];
+};
+
 static size_t plan_stride()
 {
     const size_t a = conv_plan_size(), b = conv_col_plan_size();
@@ -279,10 +286,10 @@ const Stage kStages[] = {
 };
 constexpr int kNumStages = (int)(sizeof(kStages) / sizeof(kStages[0]));
 
-int prepare(pvnet_backbone *m, const float *image_nchw, int b, int h, int w, float *out_nchw, void *mask_out,
+int prepare(pvnet_backbone *m, const ImageSrc &img, int b, int h, int w, float *out_nchw, void *mask_out,
             int mask_elem_size, void *workspace, size_t workspace_bytes, Buffers *B)
 {
-    PV_CHECK_ARG(m && image_nchw && out_nchw && workspace, "null pointer");
+    PV_CHECK_ARG(m && img.ptr && out_nchw && workspace, "null pointer");
     PV_CHECK_ARG(b >= 1 && h >= 16 && w >= 16 && h % 8 == 0 && w % 8 == 0, "image size must be a multiple of 8");
     PV_CHECK_ARG(!mask_out || mask_elem_size == 1 || mask_elem_size == 8, "mask element size must be 1 or 8");
     for (int i = 0; i < CV_COUNT; ++i)
@@ -307,9 +314,14 @@ int prepare(pvnet_backbone *m, const float *image_nchw, int b, int h, int w, flo
     return PVNET_OK;
 }
 
-int run_stage(pvnet_backbone *m, const Stage &st, const Buffers &B, const float *image_nchw, int b, int h, int w,
+int run_stage(pvnet_backbone *m, const Stage &st, const Buffers &B, const ImageSrc &img, int b, int h, int w,
               float *out_nchw, void *mask_out, int mask_elem_size, cudaStream_t s)
 {
+    const float *image_nchw = static_cast<const float *>(img.ptr);
+    if (img.is_u8 && !(m->stem_tc)) {
+        set_error("uint8 image input needs the default convolution mode (tensor-core stem)");
+        return PVNET_E_INVALID;
+    }
     const int h2 = h / 2, w2 = w / 2, h4 = h / 4, w4 = w / 4, h8 = h / 8, w8 = w / 8;
     const int c4s = m->s8 + 64, c2s = m->s4 + 64, c1s = m->s2 + 8;
     switch (st.kind) {
@@ -318,8 +330,9 @@ int run_stage(pvnet_backbone *m, const Stage &st, const Buffers &B, const float 
         return launch_stem(image_nchw, m->w[CV_STEM], m->bias[CV_STEM], B.C2, b, h, w, c2s, m->s4, s);
     case ST_PACK:
         if (m->stem_tc && m->raw_split)
-            return launch_s2d_pack(image_nchw, B.S2D, B.C1 + (size_t)b * h * w * m->s2, b, h, w, 8, 0, s);
-        if (m->stem_tc) return launch_s2d_pack(image_nchw, B.S2D, B.C1, b, h, w, c1s, m->s2, s);
+            return launch_s2d_pack(img.ptr, img.is_u8, img.mean, img.std, B.S2D, B.C1 + (size_t)b * h * w * m->s2, b, h, w, 8,
+                                   0, s);
+        if (m->stem_tc) return launch_s2d_pack(img.ptr, img.is_u8, img.mean, img.std, B.S2D, B.C1, b, h, w, c1s, m->s2, s);
         return launch_pack_image(image_nchw, B.C1, b, h, w, c1s, m->s2, s);
     case ST_POOL: return launch_maxpool(B.C2, B.P, b, h2, w2, 64, c2s, m->s4, s);
     case ST_CONV: {
@@ -353,24 +366,41 @@ int pvnet_backbone_run_stage(pvnet_backbone_t *m, int stage, const float *image_
 {
     PV_CHECK_ARG(stage >= 0 && stage < kNumStages, "stage %d out of range", stage);
     Buffers B;
-    int rc = prepare(m, image_nchw, b, h, w, out_nchw, mask_out, mask_elem_size, workspace, workspace_bytes, &B);
+    const ImageSrc img{image_nchw, 0, {0, 0, 0}, {1, 1, 1}};
+    int rc = prepare(m, img, b, h, w, out_nchw, mask_out, mask_elem_size, workspace, workspace_bytes, &B);
     if (rc) return rc;
-    return run_stage(m, kStages[stage], B, image_nchw, b, h, w, out_nchw, mask_out, mask_elem_size,
-                     (cudaStream_t)stream);
+    return run_stage(m, kStages[stage], B, img, b, h, w, out_nchw, mask_out, mask_elem_size, (cudaStream_t)stream);
+}
+
+static int forward_impl(pvnet_backbone_t *m, const ImageSrc &img, int b, int h, int w, float *out_nchw, void *mask_out,
+                        int mask_elem_size, void *workspace, size_t workspace_bytes, pvnet_stream_t stream)
+{
+    Buffers B;
+    int rc = prepare(m, img, b, h, w, out_nchw, mask_out, mask_elem_size, workspace, workspace_bytes, &B);
+    if (rc) return rc;
+    for (int i = 0; i < kNumStages; ++i)
+        if ((rc = run_stage(m, kStages[i], B, img, b, h, w, out_nchw, mask_out, mask_elem_size, (cudaStream_t)stream)))
+            return rc;
+    return PVNET_OK;
+}
+
+int pvnet_backbone_forward_u8(pvnet_backbone_t *m, const uint8_t *image_hwc, const float mean[3], const float std[3],
+                              int b, int h, int w, float *out_nchw, void *mask_out, int mask_elem_size,
+                              void *workspace, size_t workspace_bytes, pvnet_stream_t stream)
+{
+    PV_CHECK_ARG(mean && std, "null mean/std");
+    PV_CHECK_ARG(std[0] != 0.f && std[1] != 0.f && std[2] != 0.f, "zero std");
+    PV_CHECK_ARG((reinterpret_cast<uintptr_t>(image_hwc) & 1) == 0 && w % 2 == 0, "uint8 image must be 2-byte aligned");
+    const ImageSrc img{image_hwc, 1, {mean[0], mean[1], mean[2]}, {std[0], std[1], std[2]}};
+    return forward_impl(m, img, b, h, w, out_nchw, mask_out, mask_elem_size, workspace, workspace_bytes, stream);
 }
 
 int pvnet_backbone_forward(pvnet_backbone_t *m, const float *image_nchw, int b, int h, int w, float *out_nchw,
                            void *mask_out, int mask_elem_size, void *workspace, size_t workspace_bytes,
                            pvnet_stream_t stream)
 {
-    Buffers B;
-    int rc = prepare(m, image_nchw, b, h, w, out_nchw, mask_out, mask_elem_size, workspace, workspace_bytes, &B);
-    if (rc) return rc;
-    for (int i = 0; i < kNumStages; ++i)
-        if ((rc = run_stage(m, kStages[i], B, image_nchw, b, h, w, out_nchw, mask_out, mask_elem_size,
-                            (cudaStream_t)stream)))
-            return rc;
-    return PVNET_OK;
+    const ImageSrc img{image_nchw, 0, {0, 0, 0}, {1, 1, 1}};
+    return forward_impl(m, img, b, h, w, out_nchw, mask_out, mask_elem_size, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -117,10 +117,20 @@ int launch_pack_image(const float *in, float *out, int b, int H, int W, int out_
 // channel (py*2+px)*3+c, 4 zero channels, for the tensor-core stem (a 7x7 stride-2 conv is a
 // 4x4 stride-1 conv on S), and (b) the image slice of the convraw.0 input buffer (3 channels +
 // 5 zeros at out_co).  Values rounded to tf32.
+// U8 = true: `in` is a raw uint8 HWC image [b,H,W,3] (what an image decoder yields) and the kernel
+// applies torchvision's ToTensor + Normalize in their own fp32 arithmetic (tools/demo.py:89-95,
+// lib/datasets/linemod_dataset.py:191-195): (float(v) / 255 - mean[c]) / std[c], three correctly
+// rounded ops -- bit-identical to feeding the float path with the torch-normalised tensor, at a
+// quarter of the input bytes.
+struct Norm3 {
+    float mean[3], std[3];
+};
+template <bool U8>
 __global__ void __launch_bounds__(128)
-    k_s2d_pack(const float *__restrict__ in, float *__restrict__ s2d, float *__restrict__ out, int H, int W, int out_cs,
-               int out_co)
+    k_s2d_pack(const void *__restrict__ in_v, Norm3 nrm, float *__restrict__ s2d, float *__restrict__ out, int H, int W,
+               int out_cs, int out_co)
 {
+    const float *in = static_cast<const float *>(in_v);
     // grid.y = image * H/2 + half-resolution row; a block covers 128 half-resolution columns.
     // Loads are coalesced float2 reads of the six (channel, row) lines; both outputs are staged in
     // shared memory so that the stores are coalesced too (a thread-per-pixel store touches 32
@@ -133,16 +143,39 @@ __global__ void __launch_bounds__(128)
     const int n = blockIdx.y / H2, y2 = blockIdx.y - n * H2;
     const size_t plane = (size_t)H * W;
     if (x2 < W2) {
-        const float *src = in + (size_t)n * 3 * plane + (size_t)(2 * y2) * W + 2 * x2;
         float v[16];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
+        if (U8) {
+            // two rows x (2 pixels x 3 bytes): three 16-bit loads per row, coalesced across the warp
+            const unsigned short *src8 = reinterpret_cast<const unsigned short *>(
+                static_cast<const unsigned char *>(in_v) + (((size_t)n * H + 2 * y2) * W + 2 * x2) * 3);
 #pragma unroll
             for (int py = 0; py < 2; ++py) {
-                const float2 q = __ldg(reinterpret_cast<const float2 *>(src + c * plane + py * W));
-                v[(py * 2 + 0) * 3 + c] = ptx::round_tf32(q.x);
-                v[(py * 2 + 1) * 3 + c] = ptx::round_tf32(q.y);
+                unsigned bytes[6];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const unsigned q = __ldg(src8 + (size_t)py * W * 3 / 2 + j);
+                    bytes[2 * j] = q & 0xffu;
+                    bytes[2 * j + 1] = q >> 8;
+                }
+#pragma unroll
+                for (int px = 0; px < 2; ++px)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float t = __fdiv_rn(__fsub_rn(__fdiv_rn((float)bytes[px * 3 + c], 255.f), nrm.mean[c]), nrm.std[c]);
+                        v[(py * 2 + px) * 3 + c] = ptx::round_tf32(t);
+                    }
             }
+        } else {
+            const float *src = in + (size_t)n * 3 * plane + (size_t)(2 * y2) * W + 2 * x2;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int py = 0; py < 2; ++py) {
+                    const float2 q = __ldg(reinterpret_cast<const float2 *>(src + c * plane + py * W));
+                    v[(py * 2 + 0) * 3 + c] = ptx::round_tf32(q.x);
+                    v[(py * 2 + 1) * 3 + c] = ptx::round_tf32(q.y);
+                }
+        }
         v[12] = v[13] = v[14] = v[15] = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -177,11 +210,20 @@ __global__ void __launch_bounds__(128)
     }
 }
 
-int launch_s2d_pack(const float *in, float *s2d, float *out, int b, int H, int W, int out_cs, int out_co,
-                    cudaStream_t s)
+int launch_s2d_pack(const void *in, int in_is_u8, const float *mean3, const float *std3, float *s2d, float *out, int b,
+                    int H, int W, int out_cs, int out_co, cudaStream_t s)
 {
     dim3 grid((unsigned)((W / 2 + 127) / 128), (unsigned)(b * (H / 2)));
-    k_s2d_pack<<<grid, 128, 0, s>>>(in, s2d, out, H, W, out_cs, out_co);
+    Norm3 nrm{};
+    if (in_is_u8) {
+        for (int c = 0; c < 3; ++c) {
+            nrm.mean[c] = mean3[c];
+            nrm.std[c] = std3[c];
+        }
+        k_s2d_pack<true><<<grid, 128, 0, s>>>(in, nrm, s2d, out, H, W, out_cs, out_co);
+    } else {
+        k_s2d_pack<false><<<grid, 128, 0, s>>>(in, nrm, s2d, out, H, W, out_cs, out_co);
+    }
     PV_LAUNCHED("k_s2d_pack");
     return PVNET_OK;
 }

@@ -58,8 +58,8 @@ int conv_launch_at(const void *plan_storage, cudaStream_t s);
 int launch_stem(const float *in, const float *w, const float *bias, float *out, int b, int H, int W, int out_cs,
                 int out_co, cudaStream_t s);
 int launch_pack_image(const float *in, float *out, int b, int H, int W, int out_cs, int out_co, cudaStream_t s);
-int launch_s2d_pack(const float *in, float *s2d, float *out, int b, int H, int W, int out_cs, int out_co,
-                    cudaStream_t s);
+int launch_s2d_pack(const void *in, int in_is_u8, const float *mean3, const float *std3, float *s2d, float *out, int b,
+                    int H, int W, int out_cs, int out_co, cudaStream_t s);
 int launch_maxpool(const float *in, float *out, int b, int H, int W, int C, int in_cs, int in_co, cudaStream_t s);
 int launch_upsample2x(const float *in, float *out, int b, int h, int w, int C, int out_cs, int out_co,
                       cudaStream_t s);

@@ -8,27 +8,33 @@
 //
 // Here the whole batch runs as one short launch sequence with no host sync:
 //   k_chunk_count   per-2048-pixel foreground counts
-//   k_chunk_kept    per-chunk kept counts (only differs when an image is subsampled)
+//   k_chunk_kept    per-chunk kept counts (only when an image may be subsampled)
 //   k_compact_write stable (row-major) list of foreground pixels, packed (y<<16|x)
+//   k_gather        ONE pass over the vector field: direct[b][k][t] (float2, compact, keypoint-
+//                   major) + a bounding box per 512-pixel tile; every later kernel streams
+//                   these coalesced lists instead of gathering sectors from the field again
 //   k_gen_hyp       ray-ray intersections, bit-exact op sequence of the reference
-//   k_vote          persistent kernel: pixel tiles staged in shared memory once per
-//                   (image, keypoint, hypothesis group), every lane keeps 4 hypotheses
-//                   in registers, inlier counts accumulate in registers; the [hn,vn,tn]
-//                   tensor never exists
+//   k_vote2         persistent kernel: pixel tiles staged in shared memory once per
+//                   (image, keypoint, hypothesis group) as the two edge functionals of the
+//                   inlier cone, every lane keeps 4/8 hypotheses in registers, inlier
+//                   counts accumulate in registers; the [hn,vn,tn] tensor never exists
 //   k_refit         argmax (lowest index on ties) + inlier sums of the winner in fp64
 //   k_refit_final   fixed-order reduction + 2x2 solve
 //   k_cov           estimate_voting_distribution_with_mean's weighted covariance
 //
 // Bit-exact inlier counts.  The reference predicate is
 //     num/(norm1*norm2) > thresh,  norm = sqrt.rn(fma(..)),  '/' = div.rn
-// (two correctly rounded sqrt, one correctly rounded division: ~30 issue slots).
-// k_vote evaluates a division/sqrt-free form  num'*|num'| - T^2*d2  with
-// num' = d . n/|n|, which differs from the reference's quotient test only by
-// rounding (relative error < 1.3e-6, bounded in DESIGN.md).  Every test whose
-// margin is inside a guard band of 6e-6 (or involves tiny/non-finite values) is
-// re-evaluated with the reference's exact instruction sequence (exact_inlier()
-// below).  Tests outside the band cannot change sign under either rounding, so
-// the counts are identical to the reference's, at ~13 issue slots per test.
+// (two correctly rounded sqrt, one correctly rounded division: ~30 issue slots).  With
+// theta the angle between the pixel's direction n and d = hypothesis - pixel, that is
+// |theta| < theta_T (cos theta_T = thresh), i.e.
+//     m = |d| sin(theta_T - |theta|) = sin(theta_T) (d.u) - cos(theta_T) |d.v| > 0,
+// u = n/|n|, v = (-u_y, u_x): two linear functionals of the hypothesis per pixel.  k_vote2
+// evaluates them in tile-centred coordinates (4 FFMA), m (1 FADD), and compares with a
+// per-hypothesis guard band B (DESIGN.md section 3 bounds both the reference's rounding,
+// <= (7 + 1/T) ulp on the cosine, and ours): m > B counts, |m| <= B (or NaN) is re-decided by
+// exact_inlier(), the reference's own instruction sequence.  Tests outside the band cannot
+// change sign under either rounding, so the counts are identical to the reference's, at
+// ~8 issue slots per test (13.6 in round 1's num*|num| - T^2 d^2 form, kept as k_vote for A/B).
 #include "common.cuh"
 
 #include <cfloat>
@@ -43,7 +49,7 @@ constexpr int CH_PX = 2048;       // pixels per compaction chunk
 constexpr int CH_THREADS = 256;   // 8 consecutive pixels per thread
 constexpr int VT_THREADS = 256;
 constexpr int VT_WARPS = VT_THREADS / 32;
-constexpr int VT_HPL = 4;         // hypotheses per lane of the packed variant (k_vote is templated on HPL and tile size)
+constexpr int VT_TILE = 512;      // pixels per staged tile (k_gather's bounding boxes use the same tiling)
 constexpr int VT_MAX_B = 1024;    // images per call (prefix table in shared memory)
 constexpr int RF_CHUNKS = 8;      // CTAs per (image, keypoint) in the refit pass
 constexpr int RF_THREADS = 256;
@@ -134,6 +140,40 @@ __device__ __forceinline__ float subsample_p(int fg, int max_num)
     return __fmul_rn(__frcp_rn((float)fg), (float)max_num);
 }
 
+// ------------------------------------------------------------------ device RNG
+// Philox4x32-10 (Salmon et al. 2011; the generator behind torch.cuda's random_/uniform_), used when
+// the caller passes no idxs / selection tensors: counter = (item, image | stream<<28, call offset),
+// key = seed.  rng_state is a DEVICE pointer {seed, offset}; the last kernel of a call bumps the
+// offset, so a captured CUDA graph draws fresh samples on every replay.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+enum { RNG_SELECTION = 0, RNG_IDXS_V3 = 1, RNG_IDXS_COV = 2 };
+__device__ __forceinline__ uint4 rng_draw(const unsigned long long *__restrict__ rng_state, unsigned item,
+                                          unsigned image, unsigned stream)
+{
+    const unsigned long long seed = rng_state[0], off = rng_state[1];
+    return philox4x32_10(make_uint4(item, image | (stream << 28), (unsigned)off, (unsigned)(off >> 32)),
+                         make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+}
+// the uniform field of ransac_voting_gpu.py:538: caller's tensor, or 24 random bits * 2^-24 (torch's uniform_)
+__device__ __forceinline__ float selection_value(const float *__restrict__ sel_field,
+                                                 const unsigned long long *__restrict__ rng_state, int b, int npx, int i)
+{
+    if (sel_field) return sel_field[(size_t)b * npx + i];
+    return (float)(rng_draw(rng_state, (unsigned)i, (unsigned)b, RNG_SELECTION).x & 0xffffffu) * 5.9604644775390625e-8f;
+}
+__global__ void k_rng_bump(unsigned long long *rng_state) { rng_state[1] += 1ull; }
+
 // ------------------------------------------------------------------ compaction
 // pass 1: foreground count of every 2048-pixel chunk
 template <typename T>
@@ -160,9 +200,9 @@ __global__ void __launch_bounds__(CH_THREADS) k_chunk_count(const T *__restrict_
 // selection[i] < p (ransac_voting_gpu.py:537-540).  Images below min_num keep nothing.
 template <typename T>
 __global__ void __launch_bounds__(CH_THREADS)
-    k_chunk_kept(const T *__restrict__ mask, int mode, const float *__restrict__ selection, int npx, int nchunk,
-                 int min_num, int max_num, const int *__restrict__ chunk_fg, int *__restrict__ chunk_kept,
-                 int *__restrict__ status)
+    k_chunk_kept(const T *__restrict__ mask, int mode, const float *__restrict__ selection,
+                 const unsigned long long *__restrict__ rng_state, int npx, int nchunk, int min_num, int max_num,
+                 const int *__restrict__ chunk_fg, int *__restrict__ chunk_kept, int *__restrict__ status)
 {
     __shared__ int scratch[96];
     const int c = blockIdx.x, b = blockIdx.y;
@@ -170,23 +210,23 @@ __global__ void __launch_bounds__(CH_THREADS)
     for (int i = threadIdx.x; i < nchunk; i += blockDim.x) tot += chunk_fg[b * nchunk + i];
     block_sum3(tot, z0, z1, scratch);
     const bool skip = tot < min_num;
+    const bool have_sel = selection != nullptr || rng_state != nullptr;
     const bool sub = tot > max_num;
-    if (!sub || selection == nullptr) {
+    if (!sub || !have_sel) {
         if (threadIdx.x == 0) {
             chunk_kept[b * nchunk + c] = skip ? 0 : chunk_fg[b * nchunk + c];
-            if (c == 0) status[b] = (skip ? 1 : 0) | ((sub && selection == nullptr) ? 4 : 0);
+            if (c == 0) status[b] = (skip ? 1 : 0) | ((sub && !have_sel) ? 4 : 0);
         }
         return;
     }
     const float p = subsample_p(tot, max_num);
     const T *m = mask + (size_t)b * npx;
-    const float *sel = selection + (size_t)b * npx;
     const int base = c * CH_PX + threadIdx.x * 8;
     int cnt = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int i = base + j;
-        if (i < npx) cnt += (is_foreground(m[i], mode) && sel[i] < p) ? 1 : 0;
+        if (i < npx) cnt += (is_foreground(m[i], mode) && selection_value(selection, rng_state, b, npx, i) < p) ? 1 : 0;
     }
     block_sum3(cnt, z0, z1, scratch);
     if (threadIdx.x == 0) {
@@ -199,13 +239,17 @@ __global__ void __launch_bounds__(CH_THREADS)
 // in row-major order == row r of torch.nonzero (ransac_voting_gpu.py:542).
 template <typename T>
 __global__ void __launch_bounds__(CH_THREADS)
-    k_compact_write(const T *__restrict__ mask, int mode, const float *__restrict__ selection, int npx, int width,
-                    int nchunk, int max_num, const int *__restrict__ chunk_fg, const int *__restrict__ chunk_kept,
+    k_compact_write(const T *__restrict__ mask, int mode, const float *__restrict__ selection,
+                    const unsigned long long *__restrict__ rng_state, int npx, int width, int nchunk, int min_num,
+                    int max_num, const int *__restrict__ chunk_fg, const int *__restrict__ chunk_kept_or_null,
                     unsigned *__restrict__ pix, int *__restrict__ tn_out, int *__restrict__ fg_out)
 {
     __shared__ int scratch[96];
     __shared__ int warp_off[CH_THREADS / 32];
     const int c = blockIdx.x, b = blockIdx.y;
+    // chunk_kept_or_null == nullptr: nothing can be subsampled (no selection source), so the kept
+    // counts are the foreground counts (or 0 for an image below min_num) and pass 2 is not launched
+    const int *chunk_kept = chunk_kept_or_null ? chunk_kept_or_null : chunk_fg;
     int tot_fg = 0, prefix = 0, tot_kept = 0;
     for (int i = threadIdx.x; i < nchunk; i += blockDim.x) {
         const int k = chunk_kept[b * nchunk + i];
@@ -214,15 +258,15 @@ __global__ void __launch_bounds__(CH_THREADS)
         if (i < c) prefix += k;
     }
     block_sum3(tot_fg, prefix, tot_kept, scratch);
+    if (!chunk_kept_or_null && tot_fg < min_num) tot_kept = 0;
     if (c == 0 && threadIdx.x == 0) {
         tn_out[b] = tot_kept;
         fg_out[b] = tot_fg;
     }
-    if (chunk_kept[b * nchunk + c] == 0) return;
-    const bool sub = (tot_fg > max_num) && selection != nullptr;
+    if (tot_kept == 0 || chunk_kept[b * nchunk + c] == 0) return;
+    const bool sub = (tot_fg > max_num) && chunk_kept_or_null && (selection != nullptr || rng_state != nullptr);
     const float p = sub ? subsample_p(tot_fg, max_num) : 0.f;
     const T *m = mask + (size_t)b * npx;
-    const float *sel = selection + (size_t)b * npx;
     const int base = c * CH_PX + threadIdx.x * 8;
     unsigned flags = 0;
 #pragma unroll
@@ -230,7 +274,7 @@ __global__ void __launch_bounds__(CH_THREADS)
         const int i = base + j;
         if (i < npx) {
             bool keep = is_foreground(m[i], mode);
-            if (sub && keep) keep = sel[i] < p;
+            if (sub && keep) keep = selection_value(selection, rng_state, b, npx, i) < p;
             flags |= (keep ? 1u : 0u) << j;
         }
     }
@@ -270,11 +314,67 @@ __global__ void k_sum_chunks(const int *__restrict__ chunk_fg, int nchunk, int *
     if (threadIdx.x == 0) fg_out[b] = tot;
 }
 
-// ------------------------------------------------------------------ hypotheses
-// idxs [b,hn,vn,2] -> hyp [b][vn][hn] (keypoint-major so a vote CTA reads one row)
+// ------------------------------------------------------------------ gather
+// One CTA per (512-pixel tile, image): direct[b][k][t] = vertex[b, y_t, x_t, k, :] for every keypoint,
+// read through the caller's strides (thread = pixel: coalesced along mask rows for the NCHW view,
+// L1-resident 8-byte pieces of one record for a pixel-major field), written coalesced.  Also the
+// tile's bounding box -> (centre, L1 radius) used by k_vote2's tile-centred arithmetic.
 __global__ void __launch_bounds__(256)
-    k_gen_hyp(const float *__restrict__ vertex, Strides st, const int *__restrict__ idxs,
-              const unsigned *__restrict__ pix, const int *__restrict__ tn_arr, int npx, int vn, int hn,
+    k_gather(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
+             const int *__restrict__ tn_arr, int npx, int cap, int ntile, int vn, float2 *__restrict__ direct,
+             float4 *__restrict__ tinfo)
+{
+    __shared__ int s_mm[8][2];
+    const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int tn = tn_arr[b];
+    const int t0 = g * VT_TILE;
+    if (t0 >= tn) return;
+    const int len = min(VT_TILE, tn - t0);
+    const bool vec2 = st.s[4] == 1 && ((st.s[0] | st.s[1] | st.s[2] | st.s[3]) & 1) == 0 &&
+                      (reinterpret_cast<uintptr_t>(vertex) & 7) == 0;
+    int xmin = 0x7fffffff, xmax = -1;
+    for (int i = tid; i < len; i += 256) {
+        const unsigned p = pix[(size_t)b * npx + t0 + i];
+        const int x = p & 0xffff, y = p >> 16;
+        xmin = min(xmin, x);
+        xmax = max(xmax, x);
+        const long long base = (long long)b * st.s[0] + (long long)y * st.s[1] + (long long)x * st.s[2];
+        float2 *o = direct + (size_t)b * vn * cap + t0 + i;
+        for (int k = 0; k < vn; ++k) {
+            const long long off = base + (long long)k * st.s[3];
+            float2 v;
+            if (vec2) v = __ldg(reinterpret_cast<const float2 *>(vertex + off));
+            else v = make_float2(__ldg(vertex + off), __ldg(vertex + off + st.s[4]));
+            o[(size_t)k * cap] = v;
+        }
+    }
+    xmin = __reduce_min_sync(0xffffffffu, xmin);
+    xmax = __reduce_max_sync(0xffffffffu, xmax);
+    if ((tid & 31) == 0) {
+        s_mm[tid >> 5][0] = xmin;
+        s_mm[tid >> 5][1] = xmax;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < 8; ++i) {
+            xmin = min(xmin, s_mm[i][0]);
+            xmax = max(xmax, s_mm[i][1]);
+        }
+        // the list is row-major: first / last pixel carry the extreme rows
+        const int ymin = pix[(size_t)b * npx + t0] >> 16, ymax = pix[(size_t)b * npx + t0 + len - 1] >> 16;
+        const int xc = (xmin + xmax) >> 1, yc = (ymin + ymax) >> 1;
+        const int r1 = max(xc - xmin, xmax - xc) + max(yc - ymin, ymax - yc);
+        tinfo[(size_t)b * ntile + g] = make_float4((float)xc, (float)yc, (float)r1, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------ hypotheses
+// idxs [b,hn,vn,2] (or the device RNG) -> hyp [b][vn][HT] at column h_off + h (keypoint-major so a
+// vote CTA reads one row).  Samples index the compact direct list.
+__global__ void __launch_bounds__(256)
+    k_gen_hyp(const float2 *__restrict__ direct, const int *__restrict__ idxs,
+              const unsigned long long *__restrict__ rng_state, int rng_stream, const unsigned *__restrict__ pix,
+              const int *__restrict__ tn_arr, int npx, int cap, int vn, int hn, int HT, int h_off,
               float2 *__restrict__ hyp)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,18 +384,22 @@ __global__ void __launch_bounds__(256)
     const int tn = tn_arr[b];
     float2 out = make_float2(0.f, 0.f);
     if (tn > 0) {
-        const size_t ib = (((size_t)b * hn + hi) * vn + vi) * 2;
-        const unsigned t0 = (unsigned)idxs[ib] % (unsigned)tn;
-        const unsigned t1 = (unsigned)idxs[ib + 1] % (unsigned)tn;
+        unsigned t0, t1;
+        if (idxs) {
+            const size_t ib = (((size_t)b * hn + hi) * vn + vi) * 2;
+            t0 = (unsigned)idxs[ib] % (unsigned)tn;
+            t1 = (unsigned)idxs[ib + 1] % (unsigned)tn;
+        } else {       // torch's random_(0, tn) is a 32-bit draw modulo tn as well
+            const uint4 r = rng_draw(rng_state, (unsigned)i, (unsigned)b, (unsigned)rng_stream);
+            t0 = r.x % (unsigned)tn;
+            t1 = r.y % (unsigned)tn;
+        }
         const unsigned p0 = pix[(size_t)b * npx + t0], p1 = pix[(size_t)b * npx + t1];
-        const int x0 = p0 & 0xffff, y0 = p0 >> 16, x1 = p1 & 0xffff, y1 = p1 >> 16;
-        const long long base = (long long)b * st.s[0] + (long long)vi * st.s[3];
-        const long long o0 = base + y0 * st.s[1] + x0 * st.s[2];
-        const long long o1 = base + y1 * st.s[1] + x1 * st.s[2];
-        out = exact_hypothesis(vertex[o0], vertex[o0 + st.s[4]], (float)x0, (float)y0, vertex[o1],
-                               vertex[o1 + st.s[4]], (float)x1, (float)y1);
+        const float2 d0 = direct[((size_t)b * vn + vi) * cap + t0], d1 = direct[((size_t)b * vn + vi) * cap + t1];
+        out = exact_hypothesis(d0.x, d0.y, (float)(p0 & 0xffff), (float)(p0 >> 16), d1.x, d1.y, (float)(p1 & 0xffff),
+                               (float)(p1 >> 16));
     }
-    hyp[((size_t)b * vn + vi) * hn + hi] = out;
+    hyp[((size_t)b * vn + vi) * HT + h_off + hi] = out;
 }
 
 // fast-path helpers of the vote kernels
@@ -305,6 +409,12 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr)
 {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
 // cnt += (a > b): one FSETP + one predicated IADD (the C form compiled to add + predicated move + move)
@@ -320,7 +430,7 @@ __device__ __forceinline__ void count_if_gt(int &cnt, float a, float b)
 template <int HPL, int TILE>
 __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 4)
     k_vote(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
-           const int *__restrict__ tn_arr, int npx, int nb, int vn, int hn, int wh,
+           const int *__restrict__ tn_arr, int npx, int nb, int vn, int hn, int HT, int h0, int wh,
            const float2 *__restrict__ hyp, int *__restrict__ counts, float thresh, float t2, float band)
 {
     __shared__ float4 tile[TILE];
@@ -383,7 +493,7 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 4)
         for (int j = 0; j < HPL; ++j) {
             const int h = hbase + j * 32 + lane;
             float2 hp = make_float2(3.0e8f, 3.0e8f);   // padding hypothesis, count discarded
-            if (h < hn) hp = __ldg(hyp + ((size_t)b * vn + k) * hn + h);
+            if (h < hn) hp = __ldg(hyp + ((size_t)b * vn + k) * HT + h0 + h);
             hx[j] = hp.x;
             hy[j] = hp.y;
             cnt[j] = 0;
@@ -446,57 +556,34 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 4)
         for (int i = tid; i < HC; i += VT_THREADS) {
             const int h = hc * HC + i;
             const int v = red[i];
-            if (h < hn && v) atomicAdd(counts + ((size_t)b * vn + k) * hn + h, v);
+            if (h < hn && v) atomicAdd(counts + ((size_t)b * vn + k) * HT + h0 + h, v);
         }
         __syncthreads();
     }
 }
 
-// ------------------------------------------------------------------ the vote, packed FP32x2
-// Same decomposition and the same guard-band argument as k_vote, but the arithmetic of two
-// hypotheses rides in one FFMA2/FADD2/FMUL2 (sm_100 packed fp32): the scalar version is bound by
-// the FMA pipe (36 FP32 instructions per 4 tests).  Tiles store each pixel pre-duplicated,
-// {x,x,y,y} and {ux,ux,uy,uy}, so the packed operands come straight out of two LDS.128.
-// The sign of num is tested separately (e = num^2 - T^2 d2 here), see DESIGN.md.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk(float a, float b)
+// ------------------------------------------------------------------ the vote (round 2)
+// Same decomposition as k_vote -- persistent CTAs over (pixel tile, keypoint, hypothesis group);
+// warps split wh (hypothesis groups of 32*HPL) x wp (pixel interleave); each lane owns HPL
+// hypotheses -- but the tile is staged from the COMPACT lists (coalesced 4-/8-byte streams) as the
+// two edge functionals of the inlier cone in tile-centred coordinates:
+//     recA = (sx, sy, -s.p', cx),  recB = (cy, -c.p'),   s = sin(theta_T) u,  c = cos(theta_T) v
+// so one test is  num = fma(hx', sx, fma(hy', sy, -s.p'));  perp = fma(hx', cx, fma(hy', cy, -c.p'));
+// m = num - |perp|;  count if m > B;  uncertain if !(|m| > B)   (4 FFMA + FADD + 2 FSETP + IADD).
+// B = beta (|hx'| + |hy'| + r1) + b0 per hypothesis and tile (|d| <= |h'|_1 + r1): beta carries the
+// reference's rounding band (7 + 1/T) ulp T / sin(theta_T) and ours, see DESIGN.md section 3.
+// Uncertain tests were not counted; a warp whose lanes flag any re-walks the 4-pixel group and
+// decides exactly those with exact_inlier() on the raw values.
+template <int HPL>
+__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 3 : 4)
+    k_vote2(const unsigned *__restrict__ pix, const float2 *__restrict__ direct, const float4 *__restrict__ tinfo,
+            const int *__restrict__ tn_arr, int npx, int cap, int ntile, int nb, int vn, int hn, int HT, int h0,
+            int wh, const float2 *__restrict__ hyp, int *__restrict__ counts, float thresh, float sn, float cs,
+            float beta, float b0)
 {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ void upk(f32x2 v, float &a, float &b)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
-{
-    f32x2 r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
-{
-    f32x2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
-{
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
-constexpr int VP_TILE = 1024;     // pixels per tile, 32 B each
-
-__global__ void __launch_bounds__(VT_THREADS, 3)
-    k_vote_packed(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
-                  const int *__restrict__ tn_arr, int npx, int nb, int vn, int hn, int wh,
-                  const float2 *__restrict__ hyp, int *__restrict__ counts, float thresh, float t2, float band)
-{
-    __shared__ float4 tile[2 * VP_TILE];
-    __shared__ int red[VT_WARPS * 32 * VT_HPL];
+    __shared__ float4 recA[VT_TILE];
+    __shared__ float2 recB[VT_TILE];
+    __shared__ int red[VT_WARPS * 32 * HPL];
     __shared__ int tile_prefix[VT_MAX_B + 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -504,113 +591,131 @@ __global__ void __launch_bounds__(VT_THREADS, 3)
         int acc = 0;
         for (int i = 0; i < nb; ++i) {
             tile_prefix[i] = acc;
-            acc += (tn_arr[i] + VP_TILE - 1) / VP_TILE;
+            acc += (tn_arr[i] + VT_TILE - 1) / VT_TILE;
         }
         tile_prefix[nb] = acc;
     }
     __syncthreads();
     const int total_tiles = tile_prefix[nb];
-    const int HC = wh * 32 * VT_HPL;
+    const int HC = wh * 32 * HPL;               // hypotheses per item
     const int hcn = (hn + HC - 1) / HC;
     const long long n_items = (long long)total_tiles * vn * hcn;
     const int wp_count = VT_WARPS / wh;
     const int my_wh = warp % wh, my_wp = warp / wh;
-    const f32x2 nt2 = pk(-t2, -t2), band2 = pk(band, band), c2 = pk(4e-12f, 4e-12f);
+    const float qnan = __int_as_float(0x7fc00000);
 
     for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int hc = (int)(it % hcn);
         const long long r = it / hcn;
         const int k = (int)(r % vn);
         const int g = (int)(r / vn);
-        int lo = 0, hi = nb;
+        int lo = 0, hi = nb;                         // b with tile_prefix[b] <= g < tile_prefix[b+1]
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (tile_prefix[mid] <= g) lo = mid; else hi = mid;
         }
         const int b = lo;
         const int tn = tn_arr[b];
-        const int t0 = (g - tile_prefix[b]) * VP_TILE;
-        const int len = min(VP_TILE, tn - t0);
-        const long long vbase = (long long)b * st.s[0] + (long long)k * st.s[3];
+        const int gt = g - tile_prefix[b];
+        const int t0 = gt * VT_TILE;
+        const int len = min(VT_TILE, tn - t0);
+        const float4 ti = __ldg(tinfo + (size_t)b * ntile + gt);          // (xc, yc, r1)
+        const unsigned *pix_t = pix + (size_t)b * npx + t0;
+        const float2 *dir_t = direct + ((size_t)b * vn + k) * cap + t0;
 
+        // ---- stage: coalesced streams -> cone functionals
         for (int i = tid; i < len; i += VT_THREADS) {
-            const unsigned p = __ldg(pix + (size_t)b * npx + t0 + i);
-            const int x = p & 0xffff, y = p >> 16;
-            const long long off = vbase + y * st.s[1] + x * st.s[2];
-            const float nx = __ldg(vertex + off), ny = __ldg(vertex + off + st.s[4]);
-            const float n2 = fmaf(nx, nx, ny * ny);
+            const unsigned p = __ldg(pix_t + i);
+            const float2 n = __ldg(dir_t + i);
+            const float xr = (float)(int)(p & 0xffff) - ti.x, yr = (float)(int)(p >> 16) - ti.y;
+            const float n2 = fmaf(n.x, n.x, n.y * n.y);
             const float rinv = rsqrtf(n2);
-            float ux = nx * rinv, uy = ny * rinv;
-            if (!(n2 > 1e-11f && n2 < 1e30f)) ux = uy = __int_as_float(0x7fc00000);
-            tile[2 * i] = make_float4((float)x, (float)x, (float)y, (float)y);
-            tile[2 * i + 1] = make_float4(ux, ux, uy, uy);
+            const float ux = n.x * rinv, uy = n.y * rinv;
+            float sx = sn * ux, sy = sn * uy, cx = -cs * uy, cy = cs * ux;
+            float ns = -fmaf(sx, xr, sy * yr), nc = -fmaf(cx, xr, cy * yr);
+            if (!(n2 > 1e-11f && n2 < 1e30f)) sx = sy = cx = cy = ns = nc = qnan;   // -> exact path
+            recA[i] = make_float4(sx, sy, ns, cx);
+            recB[i] = make_float2(cy, nc);
         }
         for (int i = tid; i < HC; i += VT_THREADS) red[i] = 0;
         __syncthreads();
 
-        const int hbase = hc * HC + my_wh * (32 * VT_HPL);
-        float hx[VT_HPL], hy[VT_HPL];
-        int cnt[VT_HPL];
+        // ---- this lane's hypotheses, tile-centred, and their guard bands
+        const int hbase = hc * HC + my_wh * (32 * HPL);
+        const float2 *hyp_row = hyp + ((size_t)b * vn + k) * HT + h0;
+        float hx[HPL], hy[HPL], bd[HPL];
+        int cnt[HPL];
 #pragma unroll
-        for (int j = 0; j < VT_HPL; ++j) {
+        for (int j = 0; j < HPL; ++j) {
             const int h = hbase + j * 32 + lane;
-            float2 hp = make_float2(3.0e8f, 3.0e8f);
-            if (h < hn) hp = __ldg(hyp + ((size_t)b * vn + k) * hn + h);
-            hx[j] = hp.x;
-            hy[j] = hp.y;
+            hx[j] = hy[j] = 0.f;
+            bd[j] = -1.f;                            // padding: never uncertain, count discarded
+            if (h < hn) {
+                const float2 hp = __ldg(hyp_row + h);
+                hx[j] = hp.x - ti.x;
+                hy[j] = hp.y - ti.y;
+                bd[j] = fmaf(beta, fabsf(hx[j]) + fabsf(hy[j]) + ti.z, b0);
+            }
             cnt[j] = 0;
         }
-        f32x2 hx2[VT_HPL / 2], hy2[VT_HPL / 2];
-#pragma unroll
-        for (int j = 0; j < VT_HPL / 2; ++j) {
-            hx2[j] = pk(hx[2 * j], hx[2 * j + 1]);
-            hy2[j] = pk(hy[2 * j], hy[2 * j + 1]);
-        }
-        const ulonglong2 *tile2 = reinterpret_cast<const ulonglong2 *>(tile);
 
-#pragma unroll 2
-        for (int i = my_wp; i < len; i += wp_count) {
-            const ulonglong2 pc = tile2[2 * i];        // {x,x} {y,y}
-            const ulonglong2 pu = tile2[2 * i + 1];    // {ux,ux} {uy,uy}
-            unsigned unc = 0;
+        const uint32_t ra_u = ptx_smem_u32(recA), rb_u = ptx_smem_u32(recB);
+        auto sweep = [&](int i0, int n) {           // pixels i0, i0 + wp_count, ... (n of them, n <= VT_GROUP)
+            bool unc = false;
 #pragma unroll
-            for (int j = 0; j < VT_HPL / 2; ++j) {
-                const f32x2 dx = sub2(hx2[j], pc.x), dy = sub2(hy2[j], pc.y);
-                const f32x2 d2 = fma2(dx, dx, mul2(dy, dy));
-                const f32x2 num = fma2(dx, pu.x, mul2(dy, pu.y));
-                const f32x2 e = fma2(nt2, d2, mul2(num, num));
-                const f32x2 bd = fma2(band2, d2, c2);
-                float e0, e1, b0, b1, n0, n1;
-                upk(e, e0, e1);
-                upk(bd, b0, b1);
-                upk(num, n0, n1);
-                cnt[2 * j] += (e0 > b0 && n0 > 0.f) ? 1 : 0;
-                cnt[2 * j + 1] += (e1 > b1 && n1 > 0.f) ? 1 : 0;
-                unc |= (fabsf(e0) > b0) ? 0u : (1u << (2 * j));
-                unc |= (fabsf(e1) > b1) ? 0u : (2u << (2 * j));
-            }
-            if (__any_sync(0xffffffffu, unc != 0)) {
-                if (unc) {
-                    float px, py, dummy;
-                    upk(pc.x, px, dummy);
-                    upk(pc.y, py, dummy);
-                    const long long off = vbase + (long long)py * st.s[1] + (long long)px * st.s[2];
-                    const float nx = __ldg(vertex + off), ny = __ldg(vertex + off + st.s[4]);
+            for (int u = 0; u < VT_GROUP; ++u) {
+                if (u < n) {
+                    const uint32_t pi = (uint32_t)(i0 + u * wp_count);
+                    const float4 a = lds_f4(ra_u + pi * 16u);
+                    const float2 c = lds_f2(rb_u + pi * 8u);
 #pragma unroll
-                    for (int j = 0; j < VT_HPL; ++j)
-                        if (unc & (1u << j)) cnt[j] += exact_inlier(nx, ny, px, py, hx[j], hy[j], thresh) ? 1 : 0;
+                    for (int j = 0; j < HPL; ++j) {
+                        const float num = fmaf(hx[j], a.x, fmaf(hy[j], a.y, a.z));
+                        const float perp = fmaf(hx[j], a.w, fmaf(hy[j], c.x, c.y));
+                        const float m = num - fabsf(perp);
+                        count_if_gt(cnt[j], m, bd[j]);
+                        unc |= !(fabsf(m) > bd[j]);
+                    }
                 }
             }
-        }
-
+            if (__any_sync(0xffffffffu, unc)) {
+                if (unc) {
+                    for (int u = 0; u < n; ++u) {
+                        const int pi = i0 + u * wp_count;
+                        const float4 a = recA[pi];
+                        const float2 c = recB[pi];
 #pragma unroll
-        for (int j = 0; j < VT_HPL; ++j)
-            if (cnt[j]) atomicAdd(&red[my_wh * (32 * VT_HPL) + j * 32 + lane], cnt[j]);
+                        for (int j = 0; j < HPL; ++j) {
+                            const float num = fmaf(hx[j], a.x, fmaf(hy[j], a.y, a.z));
+                            const float perp = fmaf(hx[j], a.w, fmaf(hy[j], c.x, c.y));
+                            const float m = num - fabsf(perp);
+                            if (hbase + j * 32 + lane < hn && !(fabsf(m) > bd[j])) {
+                                const unsigned p = pix_t[pi];
+                                const float2 nraw = dir_t[pi];
+                                const float2 hp = hyp_row[hbase + j * 32 + lane];
+                                cnt[j] += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hp.x, hp.y,
+                                                       thresh)
+                                              ? 1
+                                              : 0;
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        int i = my_wp;
+        for (; i + (VT_GROUP - 1) * wp_count < len; i += VT_GROUP * wp_count) sweep(i, VT_GROUP);
+        if (i < len) sweep(i, (len - i + wp_count - 1) / wp_count);
+
+        // ---- combine the pixel-interleaved warps, then one atomic per hypothesis
+#pragma unroll
+        for (int j = 0; j < HPL; ++j)
+            if (cnt[j]) atomicAdd(&red[my_wh * (32 * HPL) + j * 32 + lane], cnt[j]);
         __syncthreads();
-        for (int i = tid; i < HC; i += VT_THREADS) {
-            const int h = hc * HC + i;
-            const int v = red[i];
-            if (h < hn && v) atomicAdd(counts + ((size_t)b * vn + k) * hn + h, v);
+        for (int i2 = tid; i2 < HC; i2 += VT_THREADS) {
+            const int h = hc * HC + i2;
+            const int v = red[i2];
+            if (h < hn && v) atomicAdd(counts + ((size_t)b * vn + k) * HT + h0 + h, v);
         }
         __syncthreads();
     }
@@ -629,8 +734,8 @@ __device__ __forceinline__ double warp_sum_d(double v)
 // inliers of the winner (:582-584) feed  sum n n^T  and  sum n (n.c),  n = (d_y,-d_x)
 // (:579-593), accumulated in fp64.
 __global__ void __launch_bounds__(RF_THREADS)
-    k_refit(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
-            const int *__restrict__ tn_arr, int npx, int vn, int hn, const float2 *__restrict__ hyp,
+    k_refit(const float2 *__restrict__ direct, int cap, const unsigned *__restrict__ pix,
+            const int *__restrict__ tn_arr, int npx, int vn, int hn, int HT, const float2 *__restrict__ hyp,
             const int *__restrict__ counts, float thresh, double *__restrict__ part, float2 *__restrict__ win)
 {
     __shared__ unsigned long long s_key[RF_THREADS / 32];
@@ -647,7 +752,7 @@ __global__ void __launch_bounds__(RF_THREADS)
     unsigned long long key = 0;
     for (int h = tid; h < hn; h += RF_THREADS) {
         const unsigned long long kk =
-            ((unsigned long long)(unsigned)counts[(size_t)bk * hn + h] << 32) | (unsigned long long)(0xffffffffu - (unsigned)h);
+            ((unsigned long long)(unsigned)counts[(size_t)bk * HT + h] << 32) | (unsigned long long)(0xffffffffu - (unsigned)h);
         key = kk > key ? kk : key;
     }
 #pragma unroll
@@ -662,18 +767,19 @@ __global__ void __launch_bounds__(RF_THREADS)
     const unsigned best_cnt = (unsigned)(key >> 32);
     const unsigned best_h = 0xffffffffu - (unsigned)(key & 0xffffffffu);
     float2 wp = make_float2(0.f, 0.f);
-    if (best_cnt > 0) wp = hyp[(size_t)bk * hn + best_h];
+    if (best_cnt > 0) wp = hyp[(size_t)bk * HT + best_h];
     if (rc == 0 && tid == 0) win[bk] = wp;
 
     const int per = (tn + RF_CHUNKS - 1) / RF_CHUNKS;
     const int lo = rc * per, hi = min(tn, lo + per);
-    const long long vbase = (long long)b * st.s[0] + (long long)k * st.s[3];
+    const float2 *dir_k = direct + (size_t)bk * cap;
+    (void)k;
     double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
     for (int t = lo + tid; t < hi; t += RF_THREADS) {
         const unsigned p = pix[(size_t)b * npx + t];
         const int x = p & 0xffff, y = p >> 16;
-        const long long off = vbase + y * st.s[1] + x * st.s[2];
-        const float dxv = vertex[off], dyv = vertex[off + st.s[4]];
+        const float2 dv = dir_k[t];
+        const float dxv = dv.x, dyv = dv.y;
         if (exact_inlier(dxv, dyv, (float)x, (float)y, wp.x, wp.y, thresh)) {
             const double n0 = (double)dyv, n1 = -(double)dxv;
             const double bb = n0 * (double)x + n1 * (double)y;
@@ -727,24 +833,24 @@ __global__ void k_refit_final(const double *__restrict__ part, const int *__rest
 // ransac_voting_layer_v5's confidence (ransac_voting_gpu.py:850-852): inliers of the REFITTED
 // point at a fixed threshold, divided by the pixel count.  grid (RF_CHUNKS, b*vn), integer atomics.
 __global__ void __launch_bounds__(RF_THREADS)
-    k_conf_count(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
+    k_conf_count(const float2 *__restrict__ direct, int cap, const unsigned *__restrict__ pix,
                  const int *__restrict__ tn_arr, int npx, int vn, const float *__restrict__ pts, float thresh,
                  int *__restrict__ conf_cnt)
 {
     __shared__ int scratch[96];
-    const int rc = blockIdx.x, bk = blockIdx.y, b = bk / vn, k = bk - b * vn;
+    const int rc = blockIdx.x, bk = blockIdx.y, b = bk / vn;
     const int tn = tn_arr[b];
     if (tn == 0) return;
     const float hx = pts[bk * 2], hy = pts[bk * 2 + 1];
     const int per = (tn + RF_CHUNKS - 1) / RF_CHUNKS;
     const int lo = rc * per, hi = min(tn, lo + per);
-    const long long vbase = (long long)b * st.s[0] + (long long)k * st.s[3];
+    const float2 *dir_k = direct + (size_t)bk * cap;
     int c = 0, z0 = 0, z1 = 0;
     for (int t = lo + threadIdx.x; t < hi; t += RF_THREADS) {
         const unsigned p = pix[(size_t)b * npx + t];
         const int x = p & 0xffff, y = p >> 16;
-        const long long off = vbase + y * st.s[1] + x * st.s[2];
-        c += exact_inlier(vertex[off], vertex[off + st.s[4]], (float)x, (float)y, hx, hy, thresh) ? 1 : 0;
+        const float2 dv = dir_k[t];
+        c += exact_inlier(dv.x, dv.y, (float)x, (float)y, hx, hy, thresh) ? 1 : 0;
     }
     block_sum3(c, z0, z1, scratch);
     if (threadIdx.x == 0 && c) atomicAdd(conf_cnt + bk, c);
@@ -784,12 +890,12 @@ __device__ __forceinline__ void block_sum2_d(double &a, double &b, double (*s_ac
 // (the set the refit used), residual r = n.p - n.c with n = (d_y,-d_x) and p the refitted point;
 // partial sums of r^2 and of the inlier count in fp64.  grid (RF_CHUNKS, b*vn).
 __global__ void __launch_bounds__(RF_THREADS)
-    k_resid_sum(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
+    k_resid_sum(const float2 *__restrict__ direct, int cap, const unsigned *__restrict__ pix,
                 const int *__restrict__ tn_arr, int npx, int vn, const float2 *__restrict__ win,
                 const float *__restrict__ pts, float thresh, double *__restrict__ part)
 {
     __shared__ double s_acc[RF_THREADS / 32][2];
-    const int rc = blockIdx.x, bk = blockIdx.y, b = bk / vn, k = bk - b * vn;
+    const int rc = blockIdx.x, bk = blockIdx.y, b = bk / vn;
     const int tn = tn_arr[b];
     double *my_part = part + ((size_t)bk * RF_CHUNKS + rc) * 2;
     double r2 = 0.0, cnt = 0.0;
@@ -798,12 +904,12 @@ __global__ void __launch_bounds__(RF_THREADS)
         const double px = (double)pts[bk * 2], py = (double)pts[bk * 2 + 1];
         const int per = (tn + RF_CHUNKS - 1) / RF_CHUNKS;
         const int lo = rc * per, hi = min(tn, lo + per);
-        const long long vbase = (long long)b * st.s[0] + (long long)k * st.s[3];
+        const float2 *dir_k = direct + (size_t)bk * cap;
         for (int t = lo + threadIdx.x; t < hi; t += RF_THREADS) {
             const unsigned p = pix[(size_t)b * npx + t];
             const int x = p & 0xffff, y = p >> 16;
-            const long long off = vbase + y * st.s[1] + x * st.s[2];
-            const float dxv = vertex[off], dyv = vertex[off + st.s[4]];
+            const float2 dv = dir_k[t];
+            const float dxv = dv.x, dyv = dv.y;
             if (exact_inlier(dxv, dyv, (float)x, (float)y, wp.x, wp.y, thresh)) {
                 const double n0 = (double)dyv, n1 = -(double)dxv;
                 const double r = n0 * px + n1 * py - (n0 * (double)x + n1 * (double)y);
@@ -840,23 +946,23 @@ __global__ void k_resid_final(const double *__restrict__ part, const int *__rest
 // ransac_motion_voting (ransac_voting_gpu.py:960-981): sum over the foreground pixels of
 // vertex + (x, y), fp64 partials.  grid (RF_CHUNKS, b*vn).
 __global__ void __launch_bounds__(RF_THREADS)
-    k_motion_sum(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
+    k_motion_sum(const float2 *__restrict__ direct, int cap, const unsigned *__restrict__ pix,
                  const int *__restrict__ tn_arr, int npx, int vn, double *__restrict__ part)
 {
     __shared__ double s_acc[RF_THREADS / 32][2];
-    const int rc = blockIdx.x, bk = blockIdx.y, b = bk / vn, k = bk - b * vn;
+    const int rc = blockIdx.x, bk = blockIdx.y, b = bk / vn;
     const int tn = tn_arr[b];
     double sx = 0.0, sy = 0.0;
     const int per = (tn + RF_CHUNKS - 1) / RF_CHUNKS;
     const int lo = rc * per, hi = min(tn, lo + per);
-    const long long vbase = (long long)b * st.s[0] + (long long)k * st.s[3];
+    const float2 *dir_k = direct + (size_t)bk * cap;
     for (int t = lo + threadIdx.x; t < hi; t += RF_THREADS) {
         const unsigned p = pix[(size_t)b * npx + t];
         const int x = p & 0xffff, y = p >> 16;
-        const long long off = vbase + y * st.s[1] + x * st.s[2];
+        const float2 dv = dir_k[t];
         // the reference adds in fp32 before averaging: cur_vert[cur_mask] + coords (:978)
-        sx += (double)__fadd_rn(vertex[off], (float)x);
-        sy += (double)__fadd_rn(vertex[off + st.s[4]], (float)y);
+        sx += (double)__fadd_rn(dv.x, (float)x);
+        sy += (double)__fadd_rn(dv.y, (float)y);
     }
     block_sum2_d(sx, sy, s_acc);
     if (threadIdx.x == 0) {
@@ -888,8 +994,8 @@ __global__ void k_motion_final(const double *__restrict__ part, const int *__res
 
 // internal [b][vn][hn] -> API layouts [b,hn,vn(,2)]
 __global__ void k_export(const float2 *__restrict__ hyp, const int *__restrict__ counts,
-                         const int *__restrict__ tn_arr, int nb, int vn, int hn, float *__restrict__ out_hyp,
-                         int *__restrict__ out_counts, int *__restrict__ out_tn)
+                         const int *__restrict__ tn_arr, int nb, int vn, int hn, int HT, int h_off,
+                         float *__restrict__ out_hyp, int *__restrict__ out_counts, int *__restrict__ out_tn)
 {
     const long long n = (long long)nb * vn * hn;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -898,7 +1004,7 @@ __global__ void k_export(const float2 *__restrict__ hyp, const int *__restrict__
         const long long r = i / vn;
         const int h = (int)(r % hn);
         const int b = (int)(r / hn);
-        const size_t src = ((size_t)b * vn + k) * hn + h;
+        const size_t src = ((size_t)b * vn + k) * HT + h_off + h;
         if (out_counts) out_counts[i] = counts[src];
         if (out_hyp) {
             const float2 v = hyp[src];
@@ -913,9 +1019,13 @@ __global__ void k_export(const float2 *__restrict__ hyp, const int *__restrict__
 // ------------------------------------------------------------------ covariance
 // block per (image, keypoint); ransac_voting_gpu.py:392-401
 __global__ void __launch_bounds__(256)
-    k_cov(const float2 *__restrict__ hyp, const int *__restrict__ counts, const int *__restrict__ tn_arr,
-          const float *__restrict__ mean, int vn, int hn, int min_hyp_num, float *__restrict__ out_cov)
+    k_cov(const float2 *__restrict__ hyp_all, const int *__restrict__ counts_all, const int *__restrict__ tn_arr,
+          const float *__restrict__ mean, int vn, int hn, int HT, int h_off, int min_hyp_num,
+          float *__restrict__ out_cov)
 {
+    // this (image, keypoint)'s row of hn hypotheses inside the [b][vn][HT] tables
+    const float2 *hyp = hyp_all + (size_t)blockIdx.x * HT + h_off;
+    const int *counts = counts_all + (size_t)blockIdx.x * HT + h_off;
     __shared__ int s_max[8];
     __shared__ double s_acc[8][5];
     const int bk = blockIdx.x, b = bk / vn;
@@ -926,7 +1036,7 @@ __global__ void __launch_bounds__(256)
     const int rows = skipped ? min_hyp_num : hn;       // :343-348 vs :363-384
     int cmax = 0;
     if (!skipped)
-        for (int h = tid; h < hn; h += 256) cmax = max(cmax, counts[(size_t)bk * hn + h]);
+        for (int h = tid; h < hn; h += 256) cmax = max(cmax, counts[h]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
     if (lane == 0) s_max[warp] = cmax;
@@ -944,8 +1054,8 @@ __global__ void __launch_bounds__(256)
             hxv = 0.f;
             hyv = 0.f;
         } else {
-            w = __fdiv_rn((float)counts[(size_t)bk * hn + h], ftn);
-            const float2 hp = hyp[(size_t)bk * hn + h];
+            w = __fdiv_rn((float)counts[h], ftn);
+            const float2 hp = hyp[h];
             hxv = hp.x;
             hyv = hp.y;
         }
@@ -1034,8 +1144,10 @@ __global__ void __launch_bounds__(256)
 struct VoteWs {
     unsigned *pix;
     int *chunk_fg, *chunk_kept, *tn, *fg, *status, *counts;
-    float2 *hyp, *win;
+    float2 *hyp, *win, *direct;
+    float4 *tinfo;
     double *part;
+    int cap, ntile;      // per-image capacity of the compact lists (pixels, multiple of VT_TILE) and tiles
     size_t bytes;
 };
 
@@ -1045,6 +1157,8 @@ VoteWs carve(void *ws, int b, int h, int w, int vn, int hn_total)
     const int nchunk = (int)((npx + CH_PX - 1) / CH_PX);
     Carver c(ws);
     VoteWs v;
+    v.ntile = (int)((npx + VT_TILE - 1) / VT_TILE);
+    v.cap = v.ntile * VT_TILE;
     v.pix = c.take<unsigned>((size_t)b * npx);
     v.chunk_fg = c.take<int>((size_t)b * nchunk);
     v.chunk_kept = c.take<int>((size_t)b * nchunk);
@@ -1055,14 +1169,16 @@ VoteWs carve(void *ws, int b, int h, int w, int vn, int hn_total)
     v.hyp = c.take<float2>((size_t)b * vn * hn_total);
     v.win = c.take<float2>((size_t)b * vn);
     v.part = c.take<double>((size_t)b * vn * RF_CHUNKS * 5);
+    v.tinfo = c.take<float4>((size_t)b * v.ntile);
+    v.direct = c.take<float2>((size_t)b * vn * v.cap);
     v.bytes = pvnet::align_up(c.off, 256);
     return v;
 }
 
-int check_common(const void *mask, int mask_elem_size, const float *vertex, const long long *strides,
-                 const int32_t *idxs, int b, int h, int w, int vn, int hn)
+int check_common(const void *mask, int mask_elem_size, const float *vertex, const long long *strides, int b, int h,
+                 int w, int vn, int hn)
 {
-    PV_CHECK_ARG(mask && vertex && strides && idxs, "null mask/vertex/strides/idxs pointer");
+    PV_CHECK_ARG(mask && vertex && strides, "null mask/vertex/strides pointer");
     PV_CHECK_ARG(mask_elem_size == 1 || mask_elem_size == 2 || mask_elem_size == 4 || mask_elem_size == 8,
                  "mask element size %d not in {1,2,4,8}", mask_elem_size);
     PV_CHECK_ARG(b >= 1 && b <= VT_MAX_B, "batch %d outside [1,%d]", b, VT_MAX_B);
@@ -1072,105 +1188,191 @@ int check_common(const void *mask, int mask_elem_size, const float *vertex, cons
     return PVNET_OK;
 }
 
+// Where the samples come from: the caller's tensors (parity tests, rng="reference") or the device
+// generator.  idxs == nullptr needs rng_state; selection == nullptr && rng_state == nullptr means
+// "never subsample".
+struct Samples {
+    const int32_t *idxs;
+    const float *selection;
+    const unsigned long long *rng_state;
+};
+
 template <typename T>
-int launch_compaction_t(const T *mask, int mode, const float *selection, int b, int h, int w, int min_num,
-                        int max_num, const VoteWs &ws, cudaStream_t s)
+int launch_compaction_t(const T *mask, int mode, const Samples &sm, int b, int h, int w, int min_num, int max_num,
+                        const VoteWs &ws, cudaStream_t s)
 {
     const int npx = h * w;
     const int nchunk = (npx + CH_PX - 1) / CH_PX;
     dim3 grid(nchunk, b);
     k_chunk_count<T><<<grid, CH_THREADS, 0, s>>>(mask, mode, npx, nchunk, ws.chunk_fg);
     PV_LAUNCHED("k_chunk_count");
-    k_chunk_kept<T><<<grid, CH_THREADS, 0, s>>>(mask, mode, selection, npx, nchunk, min_num, max_num, ws.chunk_fg,
-                                                ws.chunk_kept, ws.status);
-    PV_LAUNCHED("k_chunk_kept");
-    k_compact_write<T><<<grid, CH_THREADS, 0, s>>>(mask, mode, selection, npx, w, nchunk, max_num, ws.chunk_fg,
-                                                   ws.chunk_kept, ws.pix, ws.tn, ws.fg);
+    // the kept-count pass is only needed when an image could be subsampled
+    const bool may_sub = (sm.selection != nullptr || sm.rng_state != nullptr) && max_num < npx;
+    if (may_sub) {
+        k_chunk_kept<T><<<grid, CH_THREADS, 0, s>>>(mask, mode, sm.selection, sm.rng_state, npx, nchunk, min_num, max_num,
+                                                    ws.chunk_fg, ws.chunk_kept, ws.status);
+        PV_LAUNCHED("k_chunk_kept");
+    }
+    k_compact_write<T><<<grid, CH_THREADS, 0, s>>>(mask, mode, sm.selection, sm.rng_state, npx, w, nchunk, min_num,
+                                                   max_num, ws.chunk_fg, may_sub ? ws.chunk_kept : nullptr, ws.pix,
+                                                   ws.tn, ws.fg);
     PV_LAUNCHED("k_compact_write");
     return PVNET_OK;
 }
 
-int launch_compaction(const void *mask, int esz, int mode, const float *selection, int b, int h, int w,
-                      int min_num, int max_num, const VoteWs &ws, cudaStream_t s)
+// mask -> stable pixel list -> compact direct lists + tile boxes (everything the scoring passes read)
+int launch_pixels(const void *mask, int esz, int mode, const float *vertex, const Strides &st, const Samples &sm,
+                  int b, int h, int w, int vn, int min_num, int max_num, const VoteWs &ws, cudaStream_t s)
 {
+    int rc;
     switch (esz) {
-    case 1: return launch_compaction_t((const unsigned char *)mask, mode, selection, b, h, w, min_num, max_num, ws, s);
-    case 2: return launch_compaction_t((const short *)mask, mode, selection, b, h, w, min_num, max_num, ws, s);
-    case 4: return launch_compaction_t((const int *)mask, mode, selection, b, h, w, min_num, max_num, ws, s);
-    default: return launch_compaction_t((const long long *)mask, mode, selection, b, h, w, min_num, max_num, ws, s);
+    case 1: rc = launch_compaction_t((const unsigned char *)mask, mode, sm, b, h, w, min_num, max_num, ws, s); break;
+    case 2: rc = launch_compaction_t((const short *)mask, mode, sm, b, h, w, min_num, max_num, ws, s); break;
+    case 4: rc = launch_compaction_t((const int *)mask, mode, sm, b, h, w, min_num, max_num, ws, s); break;
+    default: rc = launch_compaction_t((const long long *)mask, mode, sm, b, h, w, min_num, max_num, ws, s); break;
     }
-}
-
-// hypotheses + scoring shared by v3 and with_mean
-int launch_hyp_and_vote(const float *vertex, const Strides &st, const int32_t *idxs, int b, int h, int w, int vn,
-                        int hn, float thresh, const VoteWs &ws, cudaStream_t s)
-{
-    const int npx = h * w;
-    PV_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (size_t)b * vn * hn, s));
-    dim3 ghyp((hn * vn + 255) / 256, b);
-    k_gen_hyp<<<ghyp, 256, 0, s>>>(vertex, st, idxs, ws.pix, ws.tn, npx, vn, hn, ws.hyp);
-    PV_LAUNCHED("k_gen_hyp");
-    // (hypotheses per lane, pixels per tile): items are (tile, keypoint, hypothesis group) on a static
-    // round-robin over 4 CTAs per SM (63 registers; +2..4 % over 3 CTAs in the sweep), so small tiles
-    // keep the last round short (2048-pixel tiles: 1440 items on 444 CTAs = 4 rounds for 3.2 rounds of
-    // work at 16 x 20k px, K=9, 256 hyp).
-    static const int cfg = [] {
-        const char *e = getenv("PVNET_VOTE_CFG");      // tuning knob: 0 = 4x2048, 1 = 4x512, 2 = 8x512, 3 = 8x1024
-        return e ? atoi(e) : 1;
-    }();
-    const int HPL = cfg >= 2 ? 8 : 4, TILE = cfg == 0 ? 2048 : (cfg == 3 ? 1024 : 512);
-    // hypothesis warps per CTA: 32*HPL hypotheses per warp
-    int wh = 1;
-    while (wh < VT_WARPS && wh * 32 * HPL < hn) wh <<= 1;
-    const int HC = wh * 32 * HPL;
-    const long long max_items = (long long)b * ((npx + TILE - 1) / TILE) * vn * ((hn + HC - 1) / HC);
-    static const int ctas_per_sm = [] {
-        const char *e = getenv("PVNET_VOTE_CTAS");     // tuning knob: resident vote CTAs per SM (HPL 4), default 4
-        return e ? atoi(e) : 4;
-    }();
-    long long grid = (long long)pvnet::sm_count() * (HPL > 4 ? 2 : ctas_per_sm);
-    if (grid > max_items) grid = max_items;
-    // thresh <= 0 (or NaN) has no squared form: NaN makes every test take the exact path
-    const float t2 = (thresh > 0.f && thresh < 1e18f) ? thresh * thresh : nanf("");
-    const float band = GUARD_EPS * (thresh > 0.f ? thresh * thresh : 1.f);
-    static const int packed = [] {
-        // tuning knob: 1 = FFMA2/FADD2/FMUL2 variant.  Measured identical (1686 vs 1683 Gtests/s at
-        // 150k px x 2048 hyp): packed FP32 issues at half rate on this part, so scalar stays default.
-        const char *e = getenv("PVNET_VOTE_PACKED");
-        return e ? atoi(e) : 0;
-    }();
-    if (packed) {
-        const long long max_items_p = (long long)b * ((npx + VP_TILE - 1) / VP_TILE) * vn * ((hn + HC - 1) / HC);
-        long long grid_p = (long long)pvnet::sm_count() * 3;
-        if (grid_p > max_items_p) grid_p = max_items_p;
-        k_vote_packed<<<(unsigned)grid_p, VT_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, npx, b, vn, hn, wh, ws.hyp,
-                                                             ws.counts, thresh, t2, band);
-        PV_LAUNCHED("k_vote_packed");
-        return PVNET_OK;
-    }
-#define VOTE_LAUNCH(H_, T_)                                                                                    \
-    k_vote<H_, T_><<<(unsigned)grid, VT_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, npx, b, vn, hn, wh, ws.hyp, \
-                                                         ws.counts, thresh, t2, band)
-    if (cfg == 0) VOTE_LAUNCH(4, 2048);
-    else if (cfg == 2) VOTE_LAUNCH(8, 512);
-    else if (cfg == 3) VOTE_LAUNCH(8, 1024);
-    else VOTE_LAUNCH(4, 512);
-#undef VOTE_LAUNCH
-    PV_LAUNCHED("k_vote");
+    if (rc) return rc;
+    dim3 grid(ws.ntile, b);
+    k_gather<<<grid, 256, 0, s>>>(vertex, st, ws.pix, ws.tn, h * w, ws.cap, ws.ntile, vn, ws.direct, ws.tinfo);
+    PV_LAUNCHED("k_gather");
     return PVNET_OK;
 }
 
-int launch_export(const VoteWs &ws, int b, int vn, int hn, float *out_hyp, int32_t *out_counts, int32_t *out_tn,
-                  cudaStream_t s)
+// hypotheses of one sample set into columns [h_off, h_off + hn) of the [b][vn][HT] tables
+int launch_gen_hyp(const Samples &sm, int rng_stream, int b, int h, int w, int vn, int hn, int HT, int h_off,
+                   const VoteWs &ws, cudaStream_t s)
+{
+    PV_CHECK_ARG(sm.idxs || sm.rng_state, "neither idxs nor an rng state given");
+    dim3 ghyp((hn * vn + 255) / 256, b);
+    k_gen_hyp<<<ghyp, 256, 0, s>>>(ws.direct, sm.idxs, sm.rng_state, rng_stream, ws.pix, ws.tn, h * w, ws.cap, vn, hn, HT,
+                                   h_off, ws.hyp);
+    PV_LAUNCHED("k_gen_hyp");
+    return PVNET_OK;
+}
+
+// Guard-band constants of k_vote2 for a threshold T.  With u = 2^-24:
+//   reference: fl(cos) = cos (1 + delta), |delta| <= eta = (7 + 1/T) u  (two sqrt of an fma, the fma of
+//   the numerator with its inner product, one multiply, one division) plus u rad from rounding d;
+//   in m = |d| sin(theta_T - |theta|) that is a band of (eta T / sin(theta_T) + u) |d|;
+//   ours: unit vector, functionals, centring and the two fma chains: < 8 u (|h'|_1 + r1).
+// beta = 1.25 (1.1 eta T / s + u) + 16 u; b0 = 1e-5 covers |d| < 1e-6 (norm test of the reference).
+// Outside T in [0.05, 1 - 1e-6] (and for NaN) beta is NaN: every test takes the exact path.
+struct VoteConsts {
+    float sn, cs, beta, b0;
+};
+VoteConsts vote_consts(float thresh)
+{
+    VoteConsts c;
+    const double T = (double)thresh, u = 5.9604644775390625e-8;
+    if (T >= 0.05 && T <= 1.0 - 1e-6) {
+        const double sn = sqrt(1.0 - T * T);
+        const double eta = (7.0 + 1.0 / T) * u * 1.05;
+        c.sn = (float)sn;
+        c.cs = (float)T;
+        c.beta = (float)(1.25 * (1.1 * eta * T / sn + u) + 16.0 * u);
+    } else {
+        c.sn = 0.f;
+        c.cs = 1.f;
+        c.beta = nanf("");
+    }
+    c.b0 = 1e-5f;
+    return c;
+}
+
+// score columns [h0, h0 + hn) of the hypothesis tables (counts must be zero there)
+int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int vn, int hn, int HT, int h0, float thresh,
+                const VoteWs &ws, cudaStream_t s)
+{
+    const int npx = h * w;
+    static const int impl = [] {
+        const char *e = getenv("PVNET_VOTE_IMPL");     // tuning knob: 0 = round-1 kernel (k_vote), 2 = k_vote2 (default)
+        return e ? atoi(e) : 2;
+    }();
+    static const int hpl_env = [] {
+        const char *e = getenv("PVNET_VOTE_HPL");      // tuning knob: hypotheses per lane of k_vote2 (4 or 8)
+        return e ? atoi(e) : 8;
+    }();
+    const int HPL = (impl == 2 && hpl_env == 8 && hn > 128) ? 8 : 4;
+    int wh = 1;                                        // hypothesis warps per CTA: 32*HPL hypotheses per warp
+    while (wh < VT_WARPS && wh * 32 * HPL < hn) wh <<= 1;
+    const int HC = wh * 32 * HPL;
+    const long long max_items = (long long)b * ((npx + VT_TILE - 1) / VT_TILE) * vn * ((hn + HC - 1) / HC);
+    static const int ctas_per_sm = [] {
+        const char *e = getenv("PVNET_VOTE_CTAS");     // tuning knob: resident vote CTAs per SM
+        return e ? atoi(e) : 0;
+    }();
+    const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : (HPL > 4 ? 3 : 4);
+    long long grid = (long long)pvnet::sm_count() * per_sm;
+    if (grid > max_items) grid = max_items;
+    if (grid < 1) grid = 1;
+    if (impl == 0) {
+        // thresh <= 0 (or NaN) has no squared form: NaN makes every test take the exact path
+        const float t2 = (thresh > 0.f && thresh < 1e18f) ? thresh * thresh : nanf("");
+        const float band = GUARD_EPS * (thresh > 0.f ? thresh * thresh : 1.f);
+        k_vote<4, VT_TILE><<<(unsigned)grid, VT_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, npx, b, vn, hn, HT, h0, wh,
+                                                                 ws.hyp, ws.counts, thresh, t2, band);
+        PV_LAUNCHED("k_vote");
+        return PVNET_OK;
+    }
+    const VoteConsts vc = vote_consts(thresh);
+    if (HPL == 8)
+        k_vote2<8><<<(unsigned)grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tinfo, ws.tn, npx, ws.cap, ws.ntile, b, vn, hn,
+                                                         HT, h0, wh, ws.hyp, ws.counts, thresh, vc.sn, vc.cs, vc.beta, vc.b0);
+    else
+        k_vote2<4><<<(unsigned)grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tinfo, ws.tn, npx, ws.cap, ws.ntile, b, vn, hn,
+                                                         HT, h0, wh, ws.hyp, ws.counts, thresh, vc.sn, vc.cs, vc.beta, vc.b0);
+    PV_LAUNCHED("k_vote2");
+    return PVNET_OK;
+}
+
+int launch_refit(int b, int h, int w, int vn, int hn, int HT, float thresh, const VoteWs &ws, float *out_pts,
+                 cudaStream_t s)
+{
+    dim3 grf(RF_CHUNKS, b * vn);
+    k_refit<<<grf, RF_THREADS, 0, s>>>(ws.direct, ws.cap, ws.pix, ws.tn, h * w, vn, hn, HT, ws.hyp, ws.counts, thresh,
+                                       ws.part, ws.win);
+    PV_LAUNCHED("k_refit");
+    k_refit_final<<<(b * vn + 127) / 128, 128, 0, s>>>(ws.part, ws.tn, b, vn, out_pts);
+    PV_LAUNCHED("k_refit_final");
+    return PVNET_OK;
+}
+
+int launch_export(const VoteWs &ws, int b, int vn, int hn, int HT, int h_off, float *out_hyp, int32_t *out_counts,
+                  int32_t *out_tn, cudaStream_t s)
 {
     if (!out_hyp && !out_counts && !out_tn) return PVNET_OK;
     const long long n = (long long)b * vn * hn;
     int grid = (int)((n + 255) / 256);
     if (grid > 4096) grid = 4096;
     if (grid < 1) grid = 1;
-    k_export<<<grid, 256, 0, s>>>(ws.hyp, ws.counts, ws.tn, b, vn, hn, out_hyp, out_counts, out_tn);
+    k_export<<<grid, 256, 0, s>>>(ws.hyp, ws.counts, ws.tn, b, vn, hn, HT, h_off, out_hyp, out_counts, out_tn);
     PV_LAUNCHED("k_export");
     return PVNET_OK;
+}
+
+int finish_rng(const Samples &sm, cudaStream_t s)
+{
+    if (!sm.rng_state) return PVNET_OK;
+    k_rng_bump<<<1, 1, 0, s>>>(const_cast<unsigned long long *>(sm.rng_state));
+    PV_LAUNCHED("k_rng_bump");
+    return PVNET_OK;
+}
+
+int ws_check(const VoteWs &ws, void *workspace, size_t workspace_bytes)
+{
+    PV_CHECK_ARG(workspace, "null workspace");
+    if (workspace_bytes < ws.bytes) {
+        pvnet::set_error("workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+        return PVNET_E_WORKSPACE;
+    }
+    return PVNET_OK;
+}
+
+Strides to_strides(const int64_t *vs)
+{
+    Strides st;
+    for (int i = 0; i < 5; ++i) st.s[i] = vs ? vs[i] : 0;
+    return st;
 }
 
 }  // namespace
@@ -1218,29 +1420,21 @@ int pvnet_ransac_voting_v3(const void *mask, int mask_elem_size, const float *ve
                            float *out_pts, int32_t *out_counts, float *out_hyp, int32_t *out_tn, void *workspace,
                            size_t workspace_bytes, pvnet_stream_t stream)
 {
-    Strides st;
-    if (vertex_strides)
-        for (int i = 0; i < 5; ++i) st.s[i] = vertex_strides[i];
-    int rc = check_common(mask, mask_elem_size, vertex, (const long long *)vertex_strides, idxs, b, h, w, vn, hn);
+    PV_CHECK_ARG(idxs, "null idxs (use pvnet_ransac_voting_pipeline for device-side sampling)");
+    int rc = check_common(mask, mask_elem_size, vertex, (const long long *)vertex_strides, b, h, w, vn, hn);
     if (rc) return rc;
-    PV_CHECK_ARG(out_pts && workspace, "null out_pts/workspace");
+    PV_CHECK_ARG(out_pts, "null out_pts");
+    const Strides st = to_strides(vertex_strides);
     VoteWs ws = carve(workspace, b, h, w, vn, hn);
-    if (workspace_bytes < ws.bytes) {
-        pvnet::set_error("workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
-        return PVNET_E_WORKSPACE;
-    }
+    if ((rc = ws_check(ws, workspace, workspace_bytes))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    rc = launch_compaction(mask, mask_elem_size, PVNET_MASK_NONZERO_BYTE, selection, b, h, w, min_num, max_num, ws, s);
-    if (rc) return rc;
-    rc = launch_hyp_and_vote(vertex, st, idxs, b, h, w, vn, hn, inlier_thresh, ws, s);
-    if (rc) return rc;
-    dim3 grf(RF_CHUNKS, b * vn);
-    k_refit<<<grf, RF_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, h * w, vn, hn, ws.hyp, ws.counts, inlier_thresh,
-                                       ws.part, ws.win);
-    PV_LAUNCHED("k_refit");
-    k_refit_final<<<(b * vn + 127) / 128, 128, 0, s>>>(ws.part, ws.tn, b, vn, out_pts);
-    PV_LAUNCHED("k_refit_final");
-    return launch_export(ws, b, vn, hn, out_hyp, out_counts, out_tn, s);
+    const Samples sm{idxs, selection, nullptr};
+    if ((rc = launch_pixels(mask, mask_elem_size, PVNET_MASK_NONZERO_BYTE, vertex, st, sm, b, h, w, vn, min_num, max_num, ws, s))) return rc;
+    PV_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (size_t)b * vn * hn, s));
+    if ((rc = launch_gen_hyp(sm, RNG_IDXS_V3, b, h, w, vn, hn, hn, 0, ws, s))) return rc;
+    if ((rc = launch_vote(vertex, st, b, h, w, vn, hn, hn, 0, inlier_thresh, ws, s))) return rc;
+    if ((rc = launch_refit(b, h, w, vn, hn, hn, inlier_thresh, ws, out_pts, s))) return rc;
+    return launch_export(ws, b, vn, hn, hn, 0, out_hyp, out_counts, out_tn, s);
 }
 
 int pvnet_ransac_voting_v5(const void *mask, int mask_elem_size, const float *vertex,
@@ -1254,14 +1448,12 @@ int pvnet_ransac_voting_v5(const void *mask, int mask_elem_size, const float *ve
                                     inlier_thresh, min_num, max_num, out_pts, out_counts, out_hyp, out_tn, workspace,
                                     workspace_bytes, stream);
     if (rc) return rc;
-    Strides st;
-    for (int i = 0; i < 5; ++i) st.s[i] = vertex_strides[i];
     VoteWs ws = carve(workspace, b, h, w, vn, hn);
     cudaStream_t s = (cudaStream_t)stream;
     int *conf_cnt = reinterpret_cast<int *>(ws.part);      // the refit partials are consumed by now
     PV_CUDA(cudaMemsetAsync(conf_cnt, 0, sizeof(int) * (size_t)b * vn, s));
     dim3 grid(RF_CHUNKS, b * vn);
-    k_conf_count<<<grid, RF_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, h * w, vn, out_pts, conf_thresh, conf_cnt);
+    k_conf_count<<<grid, RF_THREADS, 0, s>>>(ws.direct, ws.cap, ws.pix, ws.tn, h * w, vn, out_pts, conf_thresh, conf_cnt);
     PV_LAUNCHED("k_conf_count");
     k_conf_final<<<(b * vn + 127) / 128, 128, 0, s>>>(conf_cnt, ws.tn, b, vn, out_conf);
     PV_LAUNCHED("k_conf_final");
@@ -1279,12 +1471,10 @@ int pvnet_ransac_voting_v4(const void *mask, int mask_elem_size, const float *ve
                                     inlier_thresh, min_num, max_num, out_pts, out_counts, out_hyp, out_tn, workspace,
                                     workspace_bytes, stream);
     if (rc) return rc;
-    Strides st;
-    for (int i = 0; i < 5; ++i) st.s[i] = vertex_strides[i];
     VoteWs ws = carve(workspace, b, h, w, vn, hn);
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(RF_CHUNKS, b * vn);                          // the refit partials are consumed by now
-    k_resid_sum<<<grid, RF_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, h * w, vn, ws.win, out_pts, inlier_thresh,
+    k_resid_sum<<<grid, RF_THREADS, 0, s>>>(ws.direct, ws.cap, ws.pix, ws.tn, h * w, vn, ws.win, out_pts, inlier_thresh,
                                             ws.part);
     PV_LAUNCHED("k_resid_sum");
     k_resid_final<<<(b * vn + 127) / 128, 128, 0, s>>>(ws.part, ws.tn, b, vn, out_var);
@@ -1296,25 +1486,18 @@ int pvnet_ransac_motion_voting(const void *mask, int mask_elem_size, const float
                                const int64_t vertex_strides[5], int b, int h, int w, int vn, float *out_pts,
                                void *workspace, size_t workspace_bytes, pvnet_stream_t stream)
 {
-    PV_CHECK_ARG(mask && vertex && vertex_strides && out_pts && workspace, "null pointer");
-    PV_CHECK_ARG(mask_elem_size == 1 || mask_elem_size == 2 || mask_elem_size == 4 || mask_elem_size == 8,
-                 "mask element size %d not in {1,2,4,8}", mask_elem_size);
-    PV_CHECK_ARG(b >= 1 && b <= VT_MAX_B, "batch %d outside [1,%d]", b, VT_MAX_B);
-    PV_CHECK_ARG(h >= 1 && w >= 1 && h <= 65535 && w <= 65535, "image size %dx%d unsupported", h, w);
-    PV_CHECK_ARG(vn >= 1 && vn <= 65535, "keypoint count %d unsupported", vn);
-    Strides st;
-    for (int i = 0; i < 5; ++i) st.s[i] = vertex_strides[i];
+    int rc = check_common(mask, mask_elem_size, vertex, (const long long *)vertex_strides, b, h, w, vn, 1);
+    if (rc) return rc;
+    PV_CHECK_ARG(out_pts, "null out_pts");
+    const Strides st = to_strides(vertex_strides);
     VoteWs ws = carve(workspace, b, h, w, vn, 1);
-    if (workspace_bytes < ws.bytes) {
-        pvnet::set_error("workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
-        return PVNET_E_WORKSPACE;
-    }
+    if ((rc = ws_check(ws, workspace, workspace_bytes))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     // every foreground pixel takes part: min_num 1, no subsampling
-    int rc = launch_compaction(mask, mask_elem_size, PVNET_MASK_NONZERO_BYTE, nullptr, b, h, w, 1, 0x7fffffff, ws, s);
-    if (rc) return rc;
+    const Samples sm{nullptr, nullptr, nullptr};
+    if ((rc = launch_pixels(mask, mask_elem_size, PVNET_MASK_NONZERO_BYTE, vertex, st, sm, b, h, w, vn, 1, 0x7fffffff, ws, s))) return rc;
     dim3 grid(RF_CHUNKS, b * vn);
-    k_motion_sum<<<grid, RF_THREADS, 0, s>>>(vertex, st, ws.pix, ws.tn, h * w, vn, ws.part);
+    k_motion_sum<<<grid, RF_THREADS, 0, s>>>(ws.direct, ws.cap, ws.pix, ws.tn, h * w, vn, ws.part);
     PV_LAUNCHED("k_motion_sum");
     k_motion_final<<<(b * vn + 127) / 128, 128, 0, s>>>(ws.part, ws.tn, b, vn, out_pts);
     PV_LAUNCHED("k_motion_final");
@@ -1328,29 +1511,79 @@ int pvnet_vote_cov_with_mean(const void *mask, int mask_elem_size, const float *
                              float *out_hyp, int32_t *out_tn, void *workspace, size_t workspace_bytes,
                              pvnet_stream_t stream)
 {
-    Strides st;
-    if (vertex_strides)
-        for (int i = 0; i < 5; ++i) st.s[i] = vertex_strides[i];
+    PV_CHECK_ARG(idxs, "null idxs (use pvnet_ransac_voting_pipeline for device-side sampling)");
     PV_CHECK_ARG(rounds >= 1 && min_hyp_num >= 1, "rounds/min_hyp_num must be positive");
     const long long hnt_ll = (long long)hn * rounds;
     PV_CHECK_ARG(hnt_ll <= (1 << 24), "too many hypotheses");
     const int hnt = (int)hnt_ll;
-    int rc = check_common(mask, mask_elem_size, vertex, (const long long *)vertex_strides, idxs, b, h, w, vn, hnt);
+    int rc = check_common(mask, mask_elem_size, vertex, (const long long *)vertex_strides, b, h, w, vn, hnt);
     if (rc) return rc;
-    PV_CHECK_ARG(out_cov && mean && workspace, "null out_cov/mean/workspace");
+    PV_CHECK_ARG(out_cov && mean, "null out_cov/mean");
+    const Strides st = to_strides(vertex_strides);
     VoteWs ws = carve(workspace, b, h, w, vn, hnt);
-    if (workspace_bytes < ws.bytes) {
-        pvnet::set_error("workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
-        return PVNET_E_WORKSPACE;
-    }
+    if ((rc = ws_check(ws, workspace, workspace_bytes))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    rc = launch_compaction(mask, mask_elem_size, PVNET_MASK_EQUALS_ONE, selection, b, h, w, min_num, max_num, ws, s);
-    if (rc) return rc;
-    rc = launch_hyp_and_vote(vertex, st, idxs, b, h, w, vn, hnt, inlier_thresh, ws, s);
-    if (rc) return rc;
-    k_cov<<<b * vn, 256, 0, s>>>(ws.hyp, ws.counts, ws.tn, mean, vn, hnt, min_hyp_num, out_cov);
+    const Samples sm{idxs, selection, nullptr};
+    if ((rc = launch_pixels(mask, mask_elem_size, PVNET_MASK_EQUALS_ONE, vertex, st, sm, b, h, w, vn, min_num, max_num, ws, s))) return rc;
+    PV_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (size_t)b * vn * hnt, s));
+    if ((rc = launch_gen_hyp(sm, RNG_IDXS_COV, b, h, w, vn, hnt, hnt, 0, ws, s))) return rc;
+    if ((rc = launch_vote(vertex, st, b, h, w, vn, hnt, hnt, 0, inlier_thresh, ws, s))) return rc;
+    k_cov<<<b * vn, 256, 0, s>>>(ws.hyp, ws.counts, ws.tn, mean, vn, hnt, hnt, 0, min_hyp_num, out_cov);
     PV_LAUNCHED("k_cov");
-    return launch_export(ws, b, vn, hnt, out_hyp, out_counts, out_tn, s);
+    return launch_export(ws, b, vn, hnt, hnt, 0, out_hyp, out_counts, out_tn, s);
+}
+
+// ransac_voting_layer_v3 followed by estimate_voting_distribution_with_mean on its result, the
+// sequence of tools/train_linemod.py:119-130 (UncertaintyEvalWrapper), as ONE launch sequence: the
+// mask is compacted and the field gathered once, and when both thresholds agree one k_vote2 launch
+// scores the v3 and the covariance hypotheses together.  See include/pvnet_b200.h.
+int pvnet_ransac_voting_pipeline(const void *mask, int mask_elem_size, int mask_mode, const float *vertex,
+                                 const int64_t vertex_strides[5], const int32_t *idxs, const int32_t *cov_idxs,
+                                 const float *selection, const unsigned long long *rng_state, int b, int h, int w,
+                                 int vn, int hn, float inlier_thresh, int cov_hn, int cov_rounds, int cov_min_hyp_num,
+                                 float cov_inlier_thresh, int min_num, int max_num, float *out_pts, float *out_cov,
+                                 int32_t *out_counts, float *out_hyp, int32_t *out_cov_counts, float *out_cov_hyp,
+                                 int32_t *out_tn, void *workspace, size_t workspace_bytes, pvnet_stream_t stream)
+{
+    const bool with_cov = out_cov != nullptr;
+    PV_CHECK_ARG(mask_mode == PVNET_MASK_NONZERO_BYTE || mask_mode == PVNET_MASK_EQUALS_ONE, "bad mask mode");
+    PV_CHECK_ARG(idxs || rng_state, "neither idxs nor rng_state given");
+    PV_CHECK_ARG(!with_cov || cov_idxs || rng_state, "neither cov_idxs nor rng_state given");
+    PV_CHECK_ARG(!with_cov || (cov_hn >= 1 && cov_rounds >= 1 && cov_min_hyp_num >= 1), "bad covariance sizes");
+    const long long hnt_ll = with_cov ? (long long)cov_hn * cov_rounds : 0;
+    PV_CHECK_ARG(hnt_ll + hn <= (1 << 24), "too many hypotheses");
+    const int hnt = (int)hnt_ll, HT = hn + hnt;
+    int rc = check_common(mask, mask_elem_size, vertex, (const long long *)vertex_strides, b, h, w, vn, hn);
+    if (rc) return rc;
+    PV_CHECK_ARG(out_pts, "null out_pts");
+    const Strides st = to_strides(vertex_strides);
+    VoteWs ws = carve(workspace, b, h, w, vn, HT);
+    if ((rc = ws_check(ws, workspace, workspace_bytes))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Samples sm{idxs, selection, idxs ? nullptr : rng_state};
+    const Samples sel_src{nullptr, selection, selection ? nullptr : rng_state};
+    if ((rc = launch_pixels(mask, mask_elem_size, mask_mode, vertex, st, sel_src, b, h, w, vn, min_num, max_num, ws, s))) return rc;
+    PV_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (size_t)b * vn * HT, s));
+    if ((rc = launch_gen_hyp(sm, RNG_IDXS_V3, b, h, w, vn, hn, HT, 0, ws, s))) return rc;
+    if (with_cov) {
+        const Samples smc{cov_idxs, selection, cov_idxs ? nullptr : rng_state};
+        if ((rc = launch_gen_hyp(smc, RNG_IDXS_COV, b, h, w, vn, hnt, HT, hn, ws, s))) return rc;
+    }
+    if (with_cov && cov_inlier_thresh == inlier_thresh) {
+        if ((rc = launch_vote(vertex, st, b, h, w, vn, HT, HT, 0, inlier_thresh, ws, s))) return rc;
+    } else {
+        if ((rc = launch_vote(vertex, st, b, h, w, vn, hn, HT, 0, inlier_thresh, ws, s))) return rc;
+        if (with_cov && (rc = launch_vote(vertex, st, b, h, w, vn, hnt, HT, hn, cov_inlier_thresh, ws, s))) return rc;
+    }
+    if ((rc = launch_refit(b, h, w, vn, hn, HT, inlier_thresh, ws, out_pts, s))) return rc;
+    if (with_cov) {
+        k_cov<<<b * vn, 256, 0, s>>>(ws.hyp, ws.counts, ws.tn, out_pts, vn, hnt, HT, hn, cov_min_hyp_num, out_cov);
+        PV_LAUNCHED("k_cov");
+    }
+    if ((rc = launch_export(ws, b, vn, hn, HT, 0, out_hyp, out_counts, out_tn, s))) return rc;
+    if (with_cov && (rc = launch_export(ws, b, vn, hnt, HT, hn, out_cov_hyp, out_cov_counts, nullptr, s))) return rc;
+    if (rng_state && (!idxs || (with_cov && !cov_idxs) || !selection)) return finish_rng(Samples{nullptr, nullptr, rng_state}, s);
+    return PVNET_OK;
 }
 
 int pvnet_generate_hypothesis(const float *direct, const float *coords, const int32_t *idxs, float *hypo, int tn,

@@ -36,6 +36,11 @@ def gather_results(local: torch.Tensor, n_items: int | None = None) -> torch.Ten
         counts = [int(s.item()) for s in sizes]
     else:
         counts = [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)]
+    if min(counts) == max(counts) == local.shape[0] and hasattr(dist, "all_gather_into_tensor"):
+        # equal shards (the usual case): one collective into one preallocated tensor, no list / cat
+        out = torch.empty((world * counts[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
     width = max(counts)
     padded = local
     if local.shape[0] < width:

@@ -9,8 +9,16 @@ sm_100a backbone (tcgen05 implicit-GEMM convs behind include/pvnet_b200.h).
 
 * eval mode on CUDA -> `pvnet_backbone_forward`: BatchNorm folded into TF32 conv weights
   (the reference's cuDNN path also runs TF32 on this hardware: torch's
-  `cudnn.allow_tf32` default), fp32 accumulation, fp32 stem and 1x1 head, fused argmax.
-  There is no PyTorch fallback in this mode: if the library is missing it raises.
+  `cudnn.allow_tf32` default), fp32 accumulation.  Every convolution runs on tcgen05 with TF32
+  operands: the 7x7/2 stem as a 4x4 conv over the 2x2 space-to-depth image, and convraw.3 (1x1 +
+  bias) as a TS-mode MMA inside convraw.0's epilogue, fused with torch.argmax over the
+  segmentation logits (head weights are rounded to TF32; the fp32 `k_head`/`k_stem` kernels remain as
+  the `pvnet_conv_set_mode(1)` test path).  There is no PyTorch fallback in this mode: if the library
+  is missing it raises.
+* `nn.DataParallel(net, device_ids=[...])` (the reference's own multi-GPU wrapper,
+  tools/train_linemod.py:258, tools/demo.py:160) works: replicas share ONE per-device cache of
+  native handles and packed weights (keyed by the source module's weight versions), so weights are
+  packed once per device, never per forward, and a handle is destroyed exactly once.
 * train mode (BatchNorm batch statistics, autograd; also what tools/demo.py runs because it
   never calls .eval()) -> the plain PyTorch graph below, as SURVEY.md §7
   prescribes; training is out of scope for the native path.
@@ -18,6 +26,8 @@ sm_100a backbone (tcgen05 implicit-GEMM convs behind include/pvnet_b200.h).
 from __future__ import annotations
 
 import ctypes
+import threading
+import weakref
 
 import torch
 from torch import nn
@@ -46,6 +56,33 @@ _SLOTS = [
 ]
 
 
+class _NativeEntry:
+    """One device's native backbone: the C handle, the packed weight tensors it points into, and the
+    weight-version key it was built from.  The handle is destroyed exactly once, when the entry dies."""
+
+    def __init__(self, handle, keep, key):
+        self.handle, self.keep, self.key = handle, keep, key
+        self.packs = 1
+        self._fin = weakref.finalize(self, _NativeEntry._destroy, handle.value)
+
+    @staticmethod
+    def _destroy(handle_value):
+        try:
+            _native.lib().pvnet_backbone_destroy(ctypes.c_void_p(handle_value))
+        except Exception:
+            pass
+
+
+class _NativeState:
+    """Shared (by reference) between a module and its DataParallel replicas / shallow copies."""
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.entries = {}          # device index -> _NativeEntry
+        self.workspaces = {}       # (device index, stream) -> uint8 tensor
+        self.pack_count = 0        # how many times weights were folded + packed (tests assert on it)
+
+
 class Resnet18_8s(nn.Module):
     def __init__(self, ver_dim, seg_dim, fcdim=256, s8dim=128, s4dim=64, s2dim=32, raw_dim=32):
         super().__init__()
@@ -67,7 +104,9 @@ class Resnet18_8s(nn.Module):
         self.up2storaw = nn.UpsamplingBilinear2d(scale_factor=2)
         self.convraw = nn.Sequential(nn.Conv2d(3 + s2dim, raw_dim, 3, 1, 1, bias=False), nn.BatchNorm2d(raw_dim),
                                      nn.LeakyReLU(0.1, True), nn.Conv2d(raw_dim, seg_dim + ver_dim, 1, 1))
-        self._native = None          # (handle, packed tensors kept alive, version key)
+        self._nat = _NativeState()
+        self._src_key = None         # set on DataParallel replicas: the source module's weight-version key
+        self._frozen = False
 
     # ------------------------------------------------------------------ PyTorch graph
     def _forward_torch(self, x):
@@ -79,28 +118,66 @@ class Resnet18_8s(nn.Module):
         return out[:, :self.seg_dim], out[:, self.seg_dim:]
 
     # ------------------------------------------------------------------ native path
-    def _weights_key(self, device):
-        return (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
+    def _weights_key(self):
+        """Identity + version of every parameter and buffer: changes when weights are loaded, moved or
+        modified in place.  A DataParallel replica reports its SOURCE module's key (its own tensors are
+        fresh broadcast copies on every forward)."""
+        if self._src_key is not None:
+            return self._src_key
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
                tuple((b.data_ptr(), b._version) for b in self.buffers())
 
-    def _release_native(self):
-        if self._native is not None:
-            _native.lib().pvnet_backbone_destroy(self._native[0])
-            self._native = None
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica._src_key = self._weights_key()       # _nat is shared by reference (shallow __dict__ copy)
+        return replica
 
-    def __del__(self):
-        try:
-            self._release_native()
-        except Exception:
-            pass
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_nat", None)                      # C handles and device workspaces do not pickle / deep-copy
+        state["_src_key"] = None
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._nat = _NativeState()
+        self._src_key = None
+        self.__dict__.setdefault("_frozen", False)
+
+    def freeze_native(self, frozen=True):
+        """Latency knob: with frozen=True the per-forward staleness check of the packed weights (a walk
+        over the 152 state tensors, ~40 us) is skipped; call freeze_native(False) after changing weights."""
+        self._frozen = bool(frozen)
+        return self
+
+    def native_pack_count(self):
+        return self._nat.pack_count
 
     def _prepare_native(self, device):
         """Fold BatchNorm (eval statistics) into the conv weights, pack them K-major, round
-        to TF32, hand the pointers to the C handle.  Redone when any parameter changes."""
-        key = self._weights_key(device)
-        if self._native is not None and self._native[2] == key:
-            return self._native[0]
-        self._release_native()
+        to TF32, hand the pointers to the C handle.  Redone when any parameter changes; cached per
+        device and shared with DataParallel replicas."""
+        device = torch.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        nat = self._nat
+        ent = nat.entries.get(idx)
+        if ent is not None and self._frozen:
+            return ent.handle
+        key = self._weights_key()
+        if ent is not None and ent.key == key:
+            return ent.handle
+        with nat.lock:
+            ent = nat.entries.get(idx)
+            if ent is not None and ent.key == key:
+                return ent.handle
+            ent = self._pack_native(device, key)
+            nat.entries[idx] = ent               # the previous entry (if any) is destroyed by its finalizer
+            nat.pack_count += 1
+            # cached tensor maps of older plans point at the old weights: workspaces keep their address,
+            # the new handle plans afresh
+            return ent.handle
+
+    def _pack_native(self, device, key):
         L = _native.lib()
         mods = dict(self.named_modules())
         fcdim, s8dim, s4dim, s2dim, raw_dim = self._dims
@@ -137,17 +214,26 @@ class Resnet18_8s(nn.Module):
             keep += [w4, b]
             _native.check(L.pvnet_backbone_set_conv(handle, len(_SLOTS), w4.data_ptr(), b.data_ptr()),
                           "pvnet_backbone_set_conv(stem s2d)")
-        self._native = (handle, keep, key)
-        return handle
+        return _NativeEntry(handle, keep, key)
 
-    def forward_native(self, x, with_mask=False, mask_dtype=torch.int64):
-        """x [b,3,H,W] float32 CUDA -> out [b,seg+ver,H,W] (and the fused argmax mask)."""
+    def forward_native(self, x, with_mask=False, mask_dtype=torch.int64, mean=None, std=None):
+        """x [b,3,H,W] float32 CUDA (normalised) -- or uint8 [b,H,W,3] raw images with `mean`/`std`
+        (normalised on the device) -> out [b,seg+ver,H,W] (and the fused argmax mask)."""
         if not x.is_cuda:
             raise RuntimeError("pvnet_b200: the native backbone needs a CUDA tensor (there is no CPU path)")
-        x = x.contiguous().float()
-        b, c, h, w = x.shape
-        if c != 3 or h % 8 or w % 8:
-            raise ValueError(f"input must be [b,3,H,W] with H,W multiples of 8, got {tuple(x.shape)}")
+        raw_u8 = x.dtype == torch.uint8
+        if raw_u8:
+            if x.dim() != 4 or x.shape[3] != 3 or mean is None or std is None:
+                raise ValueError("uint8 input must be [b,H,W,3] with mean= and std= (ToTensor + Normalize constants)")
+            x = x.contiguous()
+            b, h, w, _ = x.shape
+        else:
+            x = x.contiguous().float()
+            b, c, h, w = x.shape
+            if c != 3:
+                raise ValueError(f"input must be [b,3,H,W], got {tuple(x.shape)}")
+        if h % 8 or w % 8:
+            raise ValueError(f"H,W must be multiples of 8, got {tuple(x.shape)}")
         dev = x.device
         with torch.cuda.device(dev):
             handle = self._prepare_native(dev)
@@ -158,19 +244,29 @@ class Resnet18_8s(nn.Module):
             ws = self._workspace(n.value, dev)
             out = torch.empty([b, self.seg_dim + self.ver_dim, h, w], dtype=torch.float32, device=dev)
             mask = torch.empty([b, h, w], dtype=mask_dtype, device=dev) if with_mask else None
-            _native.check(L.pvnet_backbone_forward(
-                handle, x.data_ptr(), b, h, w, out.data_ptr(), None if mask is None else mask.data_ptr(),
-                0 if mask is None else mask.element_size(), ws.data_ptr(), ws.numel(),
-                ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "pvnet_backbone_forward")
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            mptr, msz = (None, 0) if mask is None else (mask.data_ptr(), mask.element_size())
+            if raw_u8:
+                mean3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+                std3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+                _native.check(L.pvnet_backbone_forward_u8(handle, x.data_ptr(), mean3, std3, b, h, w, out.data_ptr(), mptr,
+                                                          msz, ws.data_ptr(), ws.numel(), stream),
+                              "pvnet_backbone_forward_u8")
+            else:
+                _native.check(L.pvnet_backbone_forward(handle, x.data_ptr(), b, h, w, out.data_ptr(), mptr, msz,
+                                                       ws.data_ptr(), ws.numel(), stream), "pvnet_backbone_forward")
         return (out, mask) if with_mask else out
 
     def _workspace(self, nbytes, dev):
-        # one persistent workspace per module (activations of the largest batch seen); reusing
+        # one persistent workspace per (device, stream) (activations of the largest batch seen); reusing
         # the same address also lets the C handle keep its encoded tensor maps
-        ws = getattr(self, "_ws", None)
-        if ws is None or ws.numel() < nbytes or ws.device != dev:
+        dev = torch.device(dev)
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._nat.workspaces.get(key)
+        if ws is None or ws.numel() < nbytes:
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            self._ws = ws
+            self._nat.workspaces[key] = ws
         return ws
 
     def forward(self, x, feature_alignment=False):

@@ -1,9 +1,18 @@
 """End-to-end inference from host memory: image batches in pinned host buffers -> keypoints
 (and optionally covariances) back on the host, the way tools/train_linemod.py:190-205
-(`[d.cuda() for d in data]` -> net -> EvalWrapper -> `.cpu()`) runs the hot path, but with the
-host->device copy of batch i+1 overlapped with the compute of batch i (two device input
-buffers, a side stream for copies, CUDA events for ordering; no host synchronisation inside
-the loop except the final one).
+(`[d.cuda() for d in data]` -> net -> EvalWrapper / UncertaintyEvalWrapper -> `.cpu()`) runs the
+hot path, but with the host->device copy of batch i+1 overlapped with the compute of batch i
+(two device input buffers, a side stream for copies, CUDA events for ordering; no host
+synchronisation inside the loop; `run` synchronises once on the last device->host copy before it
+returns, so the host buffers are valid when it does).
+
+Per batch the device work is: `pvnet_backbone_forward` (fused argmax -> uint8 mask) and ONE
+`pvnet_ransac_voting_pipeline` call (v3, plus estimate_voting_distribution_with_mean when
+`with_covariance`), sampling on the device (rng="device": no torch RNG launches).
+
+Inputs may be float32 [b,3,H,W] (already normalised, what `ToTensor` + `Normalize` produce,
+tools/demo.py:89-95) or uint8 [b,H,W,3] raw images: the latter are normalised on the device inside
+the packing kernel (4x fewer host->device bytes).
 """
 from __future__ import annotations
 
@@ -11,10 +20,13 @@ import torch
 
 from . import ransac_voting_gpu as rv
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)      # tools/demo.py:91-94, lib/datasets/linemod_dataset.py:191-195
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
 
 class PoseKeypointPipeline:
-    def __init__(self, net, round_hyp_num=256, inlier_thresh=0.99, rng="batched", with_covariance=False,
-                 cov_round_hyp_num=256, cov_min_hyp_num=4096):
+    def __init__(self, net, round_hyp_num=256, inlier_thresh=0.99, rng="device", with_covariance=False,
+                 cov_round_hyp_num=256, cov_min_hyp_num=4096, max_num=30000, mean=IMAGENET_MEAN, std=IMAGENET_STD):
         self.net = net
         self.hn = round_hyp_num
         self.thresh = inlier_thresh
@@ -22,36 +34,48 @@ class PoseKeypointPipeline:
         self.with_cov = with_covariance
         self.cov_hn = cov_round_hyp_num
         self.cov_min = cov_min_hyp_num
+        self.max_num = max_num
+        self.mean, self.std = tuple(mean), tuple(std)
         self._bufs = None
         self._copy_stream = None
 
     def _setup(self, host_batch, dev):
-        if self._bufs is None or self._bufs[0].shape != host_batch.shape or self._bufs[0].device != dev:
-            self._bufs = [torch.empty(host_batch.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        if (self._bufs is None or self._bufs[0].shape != host_batch.shape or self._bufs[0].dtype != host_batch.dtype
+                or self._bufs[0].device != dev):
+            self._bufs = [torch.empty(host_batch.shape, dtype=host_batch.dtype, device=dev) for _ in range(2)]
             self._ready = [torch.cuda.Event() for _ in range(2)]      # H2D of buffer i finished
             self._free = [torch.cuda.Event() for _ in range(2)]       # compute no longer reads buffer i
+            self._done = torch.cuda.Event()                           # last D2H of a run() finished
             self._copy_stream = torch.cuda.Stream(device=dev)
             for e in self._free:
                 e.record(torch.cuda.current_stream(dev))
 
     def step(self, x):
-        """x [b,3,H,W] on the device -> keypoints [b,K,2] (and covariances [b,K,2,2])."""
-        out, mask = self.net.forward_native(x, with_mask=True)
+        """x on the device: float32 [b,3,H,W] or uint8 [b,H,W,3] -> keypoints [b,K,2]
+        (and covariances [b,K,2,2])."""
+        if x.dtype == torch.uint8:
+            out, mask = self.net.forward_native(x, with_mask=True, mask_dtype=torch.uint8, mean=self.mean, std=self.std)
+        else:
+            out, mask = self.net.forward_native(x, with_mask=True, mask_dtype=torch.uint8)
         b, c, h, w = out.shape
         k = (c - self.net.seg_dim) // 2
         vertex = out[:, self.net.seg_dim:].permute(0, 2, 3, 1).view(b, h, w, k, 2)      # tools/demo.py:48-50
-        kp = rv.ransac_voting_layer_v3(mask, vertex, self.hn, inlier_thresh=self.thresh, rng=self.rng)
-        if not self.with_cov:
-            return kp
+        # a 2-class argmax mask is binary: v3's `nonzero` and with_mean's `== 1` readings coincide
+        if self.net.seg_dim == 2 or not self.with_cov:
+            return rv.ransac_voting_pipeline(mask, vertex, self.hn, self.thresh, self.with_cov, self.cov_hn, self.cov_min,
+                                             self.thresh, max_num=self.max_num, rng=self.rng)
+        kp = rv.ransac_voting_layer_v3(mask, vertex, self.hn, inlier_thresh=self.thresh, max_num=self.max_num,
+                                       rng="batched")
         _, cov = rv.estimate_voting_distribution_with_mean(mask, vertex, kp, round_hyp_num=self.cov_hn,
                                                            min_hyp_num=self.cov_min, inlier_thresh=self.thresh,
-                                                           rng=self.rng)
+                                                           max_num=self.max_num, rng="batched")
         return kp, cov
 
     @torch.no_grad()
-    def run(self, host_batches, out_host=None, on_result=None):
-        """host_batches: sequence of pinned float32 [b,3,H,W] tensors.  Results are copied
-        device->host into out_host[i] (pinned) when given.  Returns the last device result."""
+    def run(self, host_batches, out_host=None, cov_host=None, on_result=None):
+        """host_batches: sequence of pinned [b,3,H,W] float32 (or [b,H,W,3] uint8) tensors.  Results are
+        copied device->host into out_host[i] (and cov_host[i]) -- pinned tensors -- when given; the call
+        returns after the last of those copies has completed.  Returns the last device result."""
         dev = next(self.net.parameters()).device
         batches = list(host_batches)
         if not batches:
@@ -78,6 +102,11 @@ class PoseKeypointPipeline:
             if out_host is not None:
                 kp = result[0] if isinstance(result, tuple) else result
                 out_host[i].copy_(kp, non_blocking=True)
+            if cov_host is not None and isinstance(result, tuple):
+                cov_host[i].copy_(result[1], non_blocking=True)
             if on_result is not None:
                 on_result(i, result)
+        if out_host is not None or cov_host is not None:
+            self._done.record(main)
+            self._done.synchronize()
         return result

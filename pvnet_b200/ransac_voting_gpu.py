@@ -30,7 +30,17 @@ Randomness (``rng=``):
   "batched"  one ``random_`` (and, if subsampling is possible, one ``uniform_``) call
         for the whole batch, no host sync at all; statistically equivalent, different
         stream.
-  explicit ``idxs=`` / ``selection=`` tensors override both (used by the parity tests).
+  "device"   (``ransac_voting_layer_v3`` and ``ransac_voting_pipeline`` only) nothing is drawn by
+        torch at all: the kernels sample with a counter-based Philox generator whose
+        {seed, offset} live in a small device tensor (seeded from ``torch.initial_seed()``),
+        so the call has no RNG launches, no host sync, and a captured CUDA graph draws fresh
+        samples on every replay.
+  explicit ``idxs=`` / ``selection=`` tensors override all of them (used by the parity tests).
+
+``ransac_voting_pipeline`` is the fused form of what ``UncertaintyEvalWrapper``
+(tools/train_linemod.py:119-130) runs per batch -- v3, then
+estimate_voting_distribution_with_mean on its result -- with one compaction / gather of the
+mask and field for both layers.
 """
 from __future__ import annotations
 
@@ -75,11 +85,53 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+_WS_CACHE = {}       # (device, stream) -> grow-only uint8 workspace; stream-ordered reuse is safe
+_RNG_STATE = {}      # device -> (seed the state was made from, int64[2] device tensor {seed, offset})
+
+
 def _workspace(b, h, w, vn, hn_total, device):
+    """The caller-owned workspace of the C ABI.  One grow-only buffer per (device, stream): calls on a
+    stream are ordered, so reusing the address is safe, costs no allocation per call and keeps the
+    launch sequence capturable in a CUDA graph (the reference allocates per call, :557)."""
     n = ctypes.c_size_t()
     _native.check(_native.lib().pvnet_vote_workspace_bytes(b, h, w, vn, hn_total, ctypes.byref(n)),
                   "pvnet_vote_workspace_bytes")
-    return torch.empty(n.value, dtype=torch.uint8, device=device), n.value
+    device = torch.device(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < n.value:
+        ws = torch.empty(n.value, dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = ws
+    return ws, ws.numel()
+
+
+def reset_device_rng(device=None):
+    """Rewind the device-side sampler of `device` to {torch.initial_seed(), offset 0}, in place."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+    cur = _RNG_STATE.get(key)
+    if cur is None:
+        _rng_state(device)
+    else:
+        cur[1].copy_(torch.tensor([seed, 0], dtype=torch.int64))
+        cur[0] = seed
+
+
+def _rng_state(device):
+    """{seed, offset} of the device-side Philox generator; re-made when torch.manual_seed changed."""
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+    cur = _RNG_STATE.get(key)
+    if cur is None:
+        cur = [seed, torch.tensor([seed, 0], dtype=torch.int64, device=device)]
+        _RNG_STATE[key] = cur
+    elif cur[0] != seed:       # re-seed IN PLACE: captured CUDA graphs hold this tensor's address
+        cur[1].copy_(torch.tensor([seed, 0], dtype=torch.int64))
+        cur[0] = seed
+    return cur[1]
 
 
 def _stream(device):
@@ -179,6 +231,9 @@ def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, con
             idxs, selection, _ = _draw_reference(m, _MASK_NONZERO_BYTE, b, h, w, vn, hn, 1, min_num, max_num)
         elif rng == "batched":
             idxs, selection = _draw_batched(b, h, w, vn, hn, max_num, dev)
+        elif rng == "device":
+            return ransac_voting_pipeline(mask, vertex, hn, inlier_thresh, with_covariance=False, min_num=min_num,
+                                          max_num=max_num, rng="device", return_debug=return_debug)
         else:
             raise ValueError(f"unknown rng mode {rng!r}")
         out = torch.empty([b, vn, 2], dtype=torch.float32, device=dev)
@@ -196,6 +251,69 @@ def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, con
     if return_debug:
         return out, dict(counts=counts, hyp=hyp, tn=tn, idxs=idxs, selection=selection)
     return out
+
+
+def ransac_voting_pipeline(mask, vertex, round_hyp_num, inlier_thresh=0.99, with_covariance=True, cov_round_hyp_num=256,
+                           cov_min_hyp_num=4096, cov_inlier_thresh=0.99, min_num=5, max_num=30000, *,
+                           mask_mode="nonzero", idxs=None, cov_idxs=None, selection=None, rng="device",
+                           return_debug=False):
+    """``ransac_voting_layer_v3`` followed by ``estimate_voting_distribution_with_mean`` on its result
+    (tools/train_linemod.py:119-130) as one launch sequence over `pvnet_ransac_voting_pipeline`.
+
+    :param mask_mode: "nonzero" (v3's reading, :527) or "equals_one" (with_mean's, :339) for BOTH layers;
+                      identical for the binary argmax mask of a 2-class network
+    :param rng:       "device" (in-kernel Philox, no torch RNG launches, graph-capturable) or "batched"
+                      (torch draws once per batch); injected idxs / cov_idxs / selection override
+    :return: keypoints [b,vn,2] (and cov [b,vn,2,2] when with_covariance); with return_debug also a dict
+    """
+    _require_cuda(mask, "mask")
+    _require_cuda(vertex, "vertex")
+    b, h, w, vn, _ = vertex.shape
+    hn = int(round_hyp_num)
+    rounds = int(math.ceil(cov_min_hyp_num / cov_round_hyp_num)) if with_covariance else 0
+    hnt = int(cov_round_hyp_num) * rounds
+    dev = mask.device
+    mode = {"nonzero": _MASK_NONZERO_BYTE, "equals_one": _MASK_EQUALS_ONE}[mask_mode]
+    m, esz = _prep_mask(mask, mode)
+    v, strides = _prep_vertex(vertex)
+    with torch.cuda.device(dev):
+        state = None
+        if idxs is not None:
+            idxs, selection = _check_injected(idxs, selection, b, h, w, vn, hn, dev)
+        if with_covariance and cov_idxs is not None:
+            cov_idxs, _ = _check_injected(cov_idxs, None, b, h, w, vn, hnt, dev)
+        if rng == "batched":
+            if idxs is None:
+                idxs, sel2 = _draw_batched(b, h, w, vn, hn, max_num, dev)
+                selection = sel2 if selection is None else selection
+            if with_covariance and cov_idxs is None:
+                cov_idxs = torch.empty([b, hnt, vn, 2], dtype=torch.int32, device=dev).random_(0, 2 ** 31 - 1)
+        elif rng == "device":
+            state = _rng_state(dev)
+        elif idxs is None or (with_covariance and cov_idxs is None):
+            raise ValueError(f"rng mode {rng!r} needs injected idxs (and cov_idxs)")
+        out = torch.empty([b, vn, 2], dtype=torch.float32, device=dev)
+        cov = torch.empty([b, vn, 2, 2], dtype=torch.float32, device=dev) if with_covariance else None
+        dbg = {}
+        if return_debug:
+            dbg = dict(counts=torch.empty([b, hn, vn], dtype=torch.int32, device=dev),
+                       hyp=torch.empty([b, hn, vn, 2], dtype=torch.float32, device=dev),
+                       tn=torch.empty([b], dtype=torch.int32, device=dev))
+            if with_covariance:
+                dbg.update(cov_counts=torch.empty([b, hnt, vn], dtype=torch.int32, device=dev),
+                           cov_hyp=torch.empty([b, hnt, vn, 2], dtype=torch.float32, device=dev))
+        ws, ws_bytes = _workspace(b, h, w, vn, hn + hnt, dev)
+        _native.check(_native.lib().pvnet_ransac_voting_pipeline(
+            _ptr(m), esz, mode, _ptr(v), strides, _ptr(idxs), _ptr(cov_idxs), _ptr(selection), _ptr(state),
+            b, h, w, vn, hn, float(inlier_thresh), int(cov_round_hyp_num), max(rounds, 1), int(cov_min_hyp_num),
+            float(cov_inlier_thresh), int(min_num), int(min(max_num, 2 ** 31 - 1)), _ptr(out), _ptr(cov),
+            _ptr(dbg.get("counts")), _ptr(dbg.get("hyp")), _ptr(dbg.get("cov_counts")), _ptr(dbg.get("cov_hyp")),
+            _ptr(dbg.get("tn")), _ptr(ws), ws_bytes, _stream(dev)), "pvnet_ransac_voting_pipeline")
+    res = (out, cov) if with_covariance else out
+    if return_debug:
+        dbg.update(idxs=idxs, cov_idxs=cov_idxs, selection=selection)
+        return (out, cov, dbg) if with_covariance else (out, dbg)
+    return res
 
 
 def ransac_voting_layer_v5(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
