@@ -21,6 +21,7 @@
  *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:763-858      ransac_voting_layer_v5
  *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:983-1034     generate_hypothesis (python level)
  *   tools/train_linemod.py:119-130                                UncertaintyEvalWrapper.forward (v3 + with_mean)
+ *   lib/utils/extend_utils/extend_utils.py:63-114                 uncertainty_pnp (+ evaluation_utils.py:165-201)
  *   lib/networks/model_repository.py:64-80                        Resnet18_8s.forward
  * INTEGRATION.md shows the ctypes binding the reference's Python wrapper uses.
  */
@@ -204,6 +205,31 @@ PVNET_API int pvnet_voting_for_hypothesis(const float *direct, const float *coor
 PVNET_API int pvnet_vote_counts(const float *direct, const float *coords, const float *hypo,
                                 int32_t *counts, int tn, int vn, int hn, float inlier_thresh,
                                 pvnet_stream_t stream);
+
+/* ------------------------------------------------------------------ uncertainty-driven PnP
+ * The consumer of the keypoints + covariances above; reference, per image on the
+ * host: lib/utils/evaluation_utils.py:165-201 (`Evaluator.evaluate_uncertainty`) ->
+ * lib/utils/extend_utils/extend_utils.py:63-114 (`uncertainty_pnp`) ->
+ * lib/utils/extend_utils/src/uncertainty_pnp.cpp:61-92 (Ceres LM over 2 pn residuals x 6 parameters).
+ *
+ * pvnet_covariance_to_weights: cov f32 [n,2,2] -> weights f32 [n,3] = (wxx, wxy, wyy) of inv(sqrtm(cov)),
+ *   zeros where cov[0,0] < 1e-6 or any element is NaN (evaluation_utils.py:170-181) or the matrix is not
+ *   positive definite (where scipy's sqrtm + inv would fail).
+ * pvnet_uncertainty_pnp: batched form of extend_utils.py:63 `uncertainty_pnp(points_2d, weights_2d,
+ *   points_3d, camera_matrix)`: points_2d f32 [b,pn,2]; EITHER weights_2d f32 [b,pn,3] OR cov f32
+ *   [b,pn,2,2] (converted as above; pass NULL for the other); points_3d f32 [pn,3] (one object);
+ *   camera_matrix: HOST array of 9 doubles (row-major K).  4 <= pn <= 32.  One warp per image, fp64:
+ *   P3P (Grunert) on the first three of the four points with the largest wxx + wxy (extend_utils.py:84;
+ *   the fourth disambiguates, as OpenCV's SOLVEPNP_P3P), then Levenberg-Marquardt on
+ *   sum_i |W_i (proj(R X_i + t) - x_i)|^2 (uncertainty_pnp.cpp:20-37) to the stationary point (pn == 4
+ *   returns the P3P pose, :90-94).
+ *   out_pose f64 [b,3,4] = (R | t) like the reference's return value; out_info int32 [b,2] or NULL =
+ *   (status bits: 1 = P3P found no solution and the identity start was used, 2 = iteration cap hit;
+ *   LM iterations). */
+PVNET_API int pvnet_covariance_to_weights(const float *cov, int n, float *weights, pvnet_stream_t stream);
+PVNET_API int pvnet_uncertainty_pnp(const float *points_2d, const float *cov, const float *weights_2d,
+                                    const float *points_3d, const double camera_matrix[9], int b, int pn,
+                                    double *out_pose, int32_t *out_info, pvnet_stream_t stream);
 
 /* Number of kernels this library has launched on the calling thread since the last
  * reset (bench.py's "gpu_launches"). */

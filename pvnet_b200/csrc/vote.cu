@@ -564,25 +564,63 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 4)
 
 // ------------------------------------------------------------------ the vote (round 2)
 // Same decomposition as k_vote -- persistent CTAs over (pixel tile, keypoint, hypothesis group);
-// warps split wh (hypothesis groups of 32*HPL) x wp (pixel interleave); each lane owns HPL
+// warps split wh (hypothesis groups of 32*HPL) x wp (contiguous pixel chunks); each lane owns HPL
 // hypotheses -- but the tile is staged from the COMPACT lists (coalesced 4-/8-byte streams) as the
-// two edge functionals of the inlier cone in tile-centred coordinates:
-//     recA = (sx, sy, -s.p', cx),  recB = (cy, -c.p'),   s = sin(theta_T) u,  c = cos(theta_T) v
+// two edge functionals of the inlier cone in tile-centred coordinates,
+//     s = sin(theta_T) u,  c = cos(theta_T) v:   num = h'.s - p'.s,   perp = h'.c - p'.c,
 // so one test is  num = fma(hx', sx, fma(hy', sy, -s.p'));  perp = fma(hx', cx, fma(hy', cy, -c.p'));
-// m = num - |perp|;  count if m > B;  uncertain if !(|m| > B)   (4 FFMA + FADD + 2 FSETP + IADD).
+// m = num - |perp|;  inlier if m > B;  uncertain if !(|m| > B).
 // B = beta (|hx'| + |hy'| + r1) + b0 per hypothesis and tile (|d| <= |h'|_1 + r1): beta carries the
 // reference's rounding band (7 + 1/T) ulp T / sin(theta_T) and ours, see DESIGN.md section 3.
-// Uncertain tests were not counted; a warp whose lanes flag any re-walks the 4-pixel group and
-// decides exactly those with exact_inlier() on the raw values.
+// Uncertain tests are not counted by the fast path; a warp whose lanes flag any re-walks the 4-pixel
+// group and decides exactly those with exact_inlier() on the raw values.
+//
+// Instruction mix (ncu on the first version -- 4 FFMA + FADD + 2 FSETP + IADD per test -- showed the
+// half-rate ALU pipe busier than the FMA pipe and 29 % of the issue slots lost to its bursts):
+//   * two hypotheses ride in one FFMA2 (fma.rn.f32x2): same FMA-pipe time, half the issue slots;
+//     the pixel operands are stored pre-duplicated so a pair comes straight out of LDS.128;
+//   * the count is taken on the FMA pipe:  cnt += fma.sat(m, 2^64, -B 2^64)  is exactly 1 when
+//     m > B and exactly 0 otherwise (the product is exact, |m - B| >= ulp(B) >= 2^-23 b0 when they
+//     differ, NaN saturates to 0), so the ALU pipe only sees the one FSETP of the guard band.
+// Per test: 2 issue slots of FFMA2 + FADD + FFMA.SAT + FADD + FSETP = 6 slots, 7 FMA-pipe cycles.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c)
+{
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ void lds_2x64(uint32_t addr, f32x2 &a, f32x2 &b)
+{
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+constexpr float VT_SCALE = 18446744073709551616.f;     // 2^64
+
 template <int HPL>
-__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 3 : 4)
+__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
     k_vote2(const unsigned *__restrict__ pix, const float2 *__restrict__ direct, const float4 *__restrict__ tinfo,
             const int *__restrict__ tn_arr, int npx, int cap, int ntile, int nb, int vn, int hn, int HT, int h0,
             int wh, const float2 *__restrict__ hyp, int *__restrict__ counts, float thresh, float sn, float cs,
             float beta, float b0)
 {
-    __shared__ float4 recA[VT_TILE];
-    __shared__ float2 recB[VT_TILE];
+    // per pixel 48 bytes: {sx,sx,sy,sy} {ns,ns,cx,cx} {cy,cy,nc,nc}
+    __shared__ float4 rec[3 * VT_TILE];
     __shared__ int red[VT_WARPS * 32 * HPL];
     __shared__ int tile_prefix[VT_MAX_B + 1];
 
@@ -603,6 +641,7 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 3 : 4)
     const int wp_count = VT_WARPS / wh;
     const int my_wh = warp % wh, my_wp = warp / wh;
     const float qnan = __int_as_float(0x7fc00000);
+    const uint32_t rec_u = ptx_smem_u32(rec);
 
     for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int hc = (int)(it % hcn);
@@ -623,7 +662,7 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 3 : 4)
         const unsigned *pix_t = pix + (size_t)b * npx + t0;
         const float2 *dir_t = direct + ((size_t)b * vn + k) * cap + t0;
 
-        // ---- stage: coalesced streams -> cone functionals
+        // ---- stage: coalesced streams -> cone functionals, duplicated for the packed FMAs
         for (int i = tid; i < len; i += VT_THREADS) {
             const unsigned p = __ldg(pix_t + i);
             const float2 n = __ldg(dir_t + i);
@@ -634,8 +673,9 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 3 : 4)
             float sx = sn * ux, sy = sn * uy, cx = -cs * uy, cy = cs * ux;
             float ns = -fmaf(sx, xr, sy * yr), nc = -fmaf(cx, xr, cy * yr);
             if (!(n2 > 1e-11f && n2 < 1e30f)) sx = sy = cx = cy = ns = nc = qnan;   // -> exact path
-            recA[i] = make_float4(sx, sy, ns, cx);
-            recB[i] = make_float2(cy, nc);
+            rec[3 * i] = make_float4(sx, sx, sy, sy);
+            rec[3 * i + 1] = make_float4(ns, ns, cx, cx);
+            rec[3 * i + 2] = make_float4(cy, cy, nc, nc);
         }
         for (int i = tid; i < HC; i += VT_THREADS) red[i] = 0;
         __syncthreads();
@@ -643,51 +683,72 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 3 : 4)
         // ---- this lane's hypotheses, tile-centred, and their guard bands
         const int hbase = hc * HC + my_wh * (32 * HPL);
         const float2 *hyp_row = hyp + ((size_t)b * vn + k) * HT + h0;
-        float hx[HPL], hy[HPL], bd[HPL];
-        int cnt[HPL];
+        f32x2 hx2[HPL / 2], hy2[HPL / 2];
+        float bd[HPL], nb2[HPL], cnt[HPL];          // band, -band * 2^64, count (exact small integers in fp32)
 #pragma unroll
-        for (int j = 0; j < HPL; ++j) {
-            const int h = hbase + j * 32 + lane;
-            hx[j] = hy[j] = 0.f;
-            bd[j] = -1.f;                            // padding: never uncertain, count discarded
-            if (h < hn) {
-                const float2 hp = __ldg(hyp_row + h);
-                hx[j] = hp.x - ti.x;
-                hy[j] = hp.y - ti.y;
-                bd[j] = fmaf(beta, fabsf(hx[j]) + fabsf(hy[j]) + ti.z, b0);
+        for (int j = 0; j < HPL; j += 2) {
+            float hxv[2], hyv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int h = hbase + (j + e) * 32 + lane;
+                hxv[e] = hyv[e] = 0.f;
+                bd[j + e] = -1.f;                   // padding: never uncertain, count discarded
+                if (h < hn) {
+                    const float2 hp = __ldg(hyp_row + h);
+                    hxv[e] = hp.x - ti.x;
+                    hyv[e] = hp.y - ti.y;
+                    bd[j + e] = fmaf(beta, fabsf(hxv[e]) + fabsf(hyv[e]) + ti.z, b0);
+                    if (!(bd[j + e] < 1e18f)) bd[j + e] = qnan;     // absurdly far / non-finite: exact path
+                }
+                nb2[j + e] = -bd[j + e] * VT_SCALE;
+                cnt[j + e] = 0.f;
             }
-            cnt[j] = 0;
+            hx2[j / 2] = pk2(hxv[0], hxv[1]);
+            hy2[j / 2] = pk2(hyv[0], hyv[1]);
         }
 
-        const uint32_t ra_u = ptx_smem_u32(recA), rb_u = ptx_smem_u32(recB);
-        auto sweep = [&](int i0, int n) {           // pixels i0, i0 + wp_count, ... (n of them, n <= VT_GROUP)
+        // this warp's contiguous pixel chunk (multiple of VT_GROUP)
+        const int chunk = ((len + wp_count - 1) / wp_count + VT_GROUP - 1) / VT_GROUP * VT_GROUP;
+        const int p_lo = min(len, my_wp * chunk), p_hi = min(len, p_lo + chunk);
+
+        auto sweep = [&](int i0, int n) {           // pixels i0 .. i0 + n - 1 (n <= VT_GROUP)
             bool unc = false;
+            const uint32_t base = rec_u + (uint32_t)i0 * 48u;
 #pragma unroll
             for (int u = 0; u < VT_GROUP; ++u) {
                 if (u < n) {
-                    const uint32_t pi = (uint32_t)(i0 + u * wp_count);
-                    const float4 a = lds_f4(ra_u + pi * 16u);
-                    const float2 c = lds_f2(rb_u + pi * 8u);
+                    f32x2 SX, SY, NS, CX, CY, NC;
+                    lds_2x64(base + (uint32_t)u * 48u, SX, SY);
+                    lds_2x64(base + (uint32_t)u * 48u + 16u, NS, CX);
+                    lds_2x64(base + (uint32_t)u * 48u + 32u, CY, NC);
 #pragma unroll
-                    for (int j = 0; j < HPL; ++j) {
-                        const float num = fmaf(hx[j], a.x, fmaf(hy[j], a.y, a.z));
-                        const float perp = fmaf(hx[j], a.w, fmaf(hy[j], c.x, c.y));
-                        const float m = num - fabsf(perp);
-                        count_if_gt(cnt[j], m, bd[j]);
-                        unc |= !(fabsf(m) > bd[j]);
+                    for (int j = 0; j < HPL / 2; ++j) {
+                        const f32x2 num2 = fma2(hx2[j], SX, fma2(hy2[j], SY, NS));
+                        const f32x2 per2 = fma2(hx2[j], CX, fma2(hy2[j], CY, NC));
+                        float n0, n1, q0, q1;
+                        upk2(num2, n0, n1);
+                        upk2(per2, q0, q1);
+                        const float m0 = n0 - fabsf(q0), m1 = n1 - fabsf(q1);
+                        cnt[2 * j] += fma_sat(m0, VT_SCALE, nb2[2 * j]);
+                        cnt[2 * j + 1] += fma_sat(m1, VT_SCALE, nb2[2 * j + 1]);
+                        unc |= !(fabsf(m0) > bd[2 * j]);
+                        unc |= !(fabsf(m1) > bd[2 * j + 1]);
                     }
                 }
             }
             if (__any_sync(0xffffffffu, unc)) {
                 if (unc) {
                     for (int u = 0; u < n; ++u) {
-                        const int pi = i0 + u * wp_count;
-                        const float4 a = recA[pi];
-                        const float2 c = recB[pi];
+                        const int pi = i0 + u;
+                        const float4 ra = rec[3 * pi], rb = rec[3 * pi + 1], rc = rec[3 * pi + 2];
 #pragma unroll
                         for (int j = 0; j < HPL; ++j) {
-                            const float num = fmaf(hx[j], a.x, fmaf(hy[j], a.y, a.z));
-                            const float perp = fmaf(hx[j], a.w, fmaf(hy[j], c.x, c.y));
+                            float hxa, hxb, hya, hyb;
+                            upk2(hx2[j / 2], hxa, hxb);
+                            upk2(hy2[j / 2], hya, hyb);
+                            const float hxs = (j & 1) ? hxb : hxa, hys = (j & 1) ? hyb : hya;
+                            const float num = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
+                            const float perp = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
                             const float m = num - fabsf(perp);
                             if (hbase + j * 32 + lane < hn && !(fabsf(m) > bd[j])) {
                                 const unsigned p = pix_t[pi];
@@ -695,22 +756,24 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 3 : 4)
                                 const float2 hp = hyp_row[hbase + j * 32 + lane];
                                 cnt[j] += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hp.x, hp.y,
                                                        thresh)
-                                              ? 1
-                                              : 0;
+                                              ? 1.f
+                                              : 0.f;
                             }
                         }
                     }
                 }
             }
         };
-        int i = my_wp;
-        for (; i + (VT_GROUP - 1) * wp_count < len; i += VT_GROUP * wp_count) sweep(i, VT_GROUP);
-        if (i < len) sweep(i, (len - i + wp_count - 1) / wp_count);
+        int i = p_lo;
+        for (; i + VT_GROUP <= p_hi; i += VT_GROUP) sweep(i, VT_GROUP);
+        if (i < p_hi) sweep(i, p_hi - i);
 
-        // ---- combine the pixel-interleaved warps, then one atomic per hypothesis
+        // ---- combine the pixel-chunk warps, then one atomic per hypothesis
 #pragma unroll
-        for (int j = 0; j < HPL; ++j)
-            if (cnt[j]) atomicAdd(&red[my_wh * (32 * HPL) + j * 32 + lane], cnt[j]);
+        for (int j = 0; j < HPL; ++j) {
+            const int c = (int)cnt[j];
+            if (c) atomicAdd(&red[my_wh * (32 * HPL) + j * 32 + lane], c);
+        }
         __syncthreads();
         for (int i2 = tid; i2 < HC; i2 += VT_THREADS) {
             const int h = hc * HC + i2;
@@ -1301,7 +1364,7 @@ int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int
         const char *e = getenv("PVNET_VOTE_CTAS");     // tuning knob: resident vote CTAs per SM
         return e ? atoi(e) : 0;
     }();
-    const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : (HPL > 4 ? 3 : 4);
+    const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : (HPL > 4 ? 2 : 3);
     long long grid = (long long)pvnet::sm_count() * per_sm;
     if (grid > max_items) grid = max_items;
     if (grid < 1) grid = 1;
