@@ -231,6 +231,16 @@ PVNET_API int pvnet_uncertainty_pnp(const float *points_2d, const float *cov, co
                                     const float *points_3d, const double camera_matrix[9], int b, int pn,
                                     double *out_pose, int32_t *out_info, pvnet_stream_t stream);
 
+/* The vanishing-point pair of the reference extension (ransac_voting.cpp:61-99 ->
+ * ransac_voting_kernel.cu:170-260, :263-351; used by ransac_voting_vanish_point_layer,
+ * ransac_voting_gpu.py:408-501): hypotheses are homogeneous points hypo [hn,vn,3]; the vote sets
+ * inliers [hn,vn,tn] u8 (caller zero-fills; may be NULL) and/or writes the row sums counts [hn,vn]. */
+PVNET_API int pvnet_generate_hypothesis_vanishing_point(const float *direct, const float *coords, const int32_t *idxs,
+                                                        float *hypo, int tn, int vn, int hn, pvnet_stream_t stream);
+PVNET_API int pvnet_voting_for_hypothesis_vanishing_point(const float *direct, const float *coords, const float *hypo,
+                                                          uint8_t *inliers, int32_t *counts, int tn, int vn, int hn,
+                                                          float inlier_thresh, pvnet_stream_t stream);
+
 /* Number of kernels this library has launched on the calling thread since the last
  * reset (bench.py's "gpu_launches"). */
 PVNET_API long long pvnet_launch_count(void);

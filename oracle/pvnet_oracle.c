@@ -9,6 +9,8 @@
  * What is restated (paths relative to /root/reference):
  *   pvo_generate_hypothesis   lib/ransac_voting_gpu_layer/src/ransac_voting_kernel.cu:11-49
  *   pvo_voting_for_hypothesis lib/ransac_voting_gpu_layer/src/ransac_voting_kernel.cu:88-126
+ *   pvo_generate_hypothesis_vp / pvo_voting_for_hypothesis_vp
+ *                             lib/ransac_voting_gpu_layer/src/ransac_voting_kernel.cu:170-230, :263-305
  *   pvo_vote_counts           same predicate, summed over pixels the way
  *                             lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:561 does
  *                             (torch.sum(cur_inlier, 2)) without storing the u8 tensor
@@ -129,6 +131,63 @@ PVO_API void pvo_vote_counts(const float *direct, const float *coords,
                                    hx, hy, thresh);
             }
             counts[hi * vn + vi] = c;
+        }
+    }
+}
+
+/* ransac_voting_kernel.cu:170-230.  hypo [hn,vn,3] homogeneous intersection of the two pixels' lines;
+ * rounding sequence as nvcc compiles the reference (SASS, sm_100a): see exact_vp_hypothesis in
+ * pvnet_b200/csrc/vote.cu for the line-by-line mapping. */
+PVO_API void pvo_generate_hypothesis_vp(const float *direct, const float *coords, const int32_t *idxs,
+                                        float *hypo, int tn, int vn, int hn)
+{
+    (void)tn;
+    for (int hi = 0; hi < hn; ++hi) {
+        for (int vi = 0; vi < vn; ++vi) {
+            const int t0 = idxs[(hi * vn + vi) * 2], t1 = idxs[(hi * vn + vi) * 2 + 1];
+            const float dx0 = direct[((size_t)t0 * vn + vi) * 2], dy0 = direct[((size_t)t0 * vn + vi) * 2 + 1];
+            const float dx1 = direct[((size_t)t1 * vn + vi) * 2], dy1 = direct[((size_t)t1 * vn + vi) * 2 + 1];
+            const float cx0 = coords[(size_t)t0 * 2], cy0 = coords[(size_t)t0 * 2 + 1];
+            const float cx1 = coords[(size_t)t1 * 2], cy1 = coords[(size_t)t1 * 2 + 1];
+            const float lz0 = fmaf(dx0, cy0, -(dy0 * cx0));
+            const float lz1 = fmaf(dx1, cy1, -(dy1 * cx1));
+            float z = fmaf(dx0, dy1, -(dy0 * dx1));
+            float x = fmaf(dx1, lz0, -(dx0 * lz1));
+            float y = fmaf(dy1, lz0, -(dy0 * lz1));
+            const float vx0 = dx0 * fmaf(-cx0, z, x), vx1 = dx1 * fmaf(-cx1, z, x);
+            const float vy0 = dy0 * fmaf(-cy0, z, y), vy1 = dy1 * fmaf(-cy1, z, y);
+            if (vx0 < 0.f && vx1 < 0.f && vy0 < 0.f && vy1 < 0.f) {
+                x = -x;
+                y = -y;
+                z = -z;
+            }
+            if (fminf(vx0 * vx1, vy0 * vy1) < 0.f) x = y = z = 0.f;
+            hypo[(hi * vn + vi) * 3] = x;
+            hypo[(hi * vn + vi) * 3 + 1] = y;
+            hypo[(hi * vn + vi) * 3 + 2] = z;
+        }
+    }
+}
+
+/* ransac_voting_kernel.cu:263-305; inliers [hn,vn,tn] u8 only SET */
+PVO_API void pvo_voting_for_hypothesis_vp(const float *direct, const float *coords, const float *hypo,
+                                          uint8_t *inliers, int tn, int vn, int hn, float thresh)
+{
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int hi = 0; hi < hn; ++hi) {
+        for (int vi = 0; vi < vn; ++vi) {
+            const float hx = hypo[(hi * vn + vi) * 3], hy = hypo[(hi * vn + vi) * 3 + 1], hz = hypo[(hi * vn + vi) * 3 + 2];
+            uint8_t *row = inliers + ((size_t)hi * vn + vi) * tn;
+            for (int ti = 0; ti < tn; ++ti) {
+                const float dx = direct[((size_t)ti * vn + vi) * 2], dy = direct[((size_t)ti * vn + vi) * 2 + 1];
+                const float fx = fmaf(-coords[(size_t)ti * 2], hz, hx), fy = fmaf(-coords[(size_t)ti * 2 + 1], hz, hy);
+                const float norm1 = sqrtf(fmaf(dx, dx, dy * dy)), norm2 = sqrtf(fmaf(fx, fx, fy * fy));
+                if ((double)norm1 < 1e-6 || (double)norm2 < 1e-6) continue;
+                const float vx = fx * dx, vy = fy * dy;
+                const float ang = (vx + vy) / (norm2 * norm1);
+                if (fminf(vx, vy) < 0.f) continue;
+                if (fabsf(ang) > thresh) row[ti] = 1;
+            }
         }
     }
 }

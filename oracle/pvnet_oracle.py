@@ -66,6 +66,11 @@ def lib():
         L.pvo_vote_counts.argtypes = [_F32P, _F32P, _F32P, _I32P, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_float]
         L.pvo_vote_counts.restype = None
+        L.pvo_generate_hypothesis_vp.argtypes = [_F32P, _F32P, _I32P, _F32P, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.pvo_generate_hypothesis_vp.restype = None
+        L.pvo_voting_for_hypothesis_vp.argtypes = [_F32P, _F32P, _F32P, _U8P, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                   ctypes.c_float]
+        L.pvo_voting_for_hypothesis_vp.restype = None
         L.pvo_num_threads.restype = ctypes.c_int
         L.pvo_set_num_threads.argtypes = [ctypes.c_int]
         _lib = L
@@ -122,6 +127,29 @@ def vote_counts(direct, coords, hypo, thresh):
 
 
 # ----------------------------------------------------------------- mask / compaction
+def generate_hypothesis_vanishing_point_kernel(direct, coords, idxs):
+    """ransac_voting_kernel.cu:170-230 -> hypo [hn,vn,3] f32 (homogeneous)."""
+    direct, coords = _f32(direct), _f32(coords)
+    idxs = np.ascontiguousarray(idxs, dtype=np.int32)
+    tn, vn, _ = direct.shape
+    hn = idxs.shape[0]
+    hypo = np.empty((hn, vn, 3), np.float32)
+    lib().pvo_generate_hypothesis_vp(_ptr(direct, _F32P), _ptr(coords, _F32P), _ptr(idxs, _I32P), _ptr(hypo, _F32P),
+                                     tn, vn, hn)
+    return hypo
+
+
+def voting_for_hypothesis_vanishing_point_kernel(direct, coords, hypo, thresh):
+    """ransac_voting_kernel.cu:263-305 -> inliers [hn,vn,tn] u8."""
+    direct, coords, hypo = _f32(direct), _f32(coords), _f32(hypo)
+    tn, vn, _ = direct.shape
+    hn = hypo.shape[0]
+    inl = np.zeros((hn, vn, tn), np.uint8)
+    lib().pvo_voting_for_hypothesis_vp(_ptr(direct, _F32P), _ptr(coords, _F32P), _ptr(hypo, _F32P), _ptr(inl, _U8P),
+                                       tn, vn, hn, float(thresh))
+    return inl
+
+
 def _byte_mask(mask_img):
     """`.byte()` of ransac_voting_gpu.py:527: integer masks keep their low 8 bits."""
     m = np.asarray(mask_img)

@@ -40,6 +40,11 @@ def lib():
         L.pvref_generate_hypothesis.restype = ci
         L.pvref_voting_for_hypothesis.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci]
         L.pvref_voting_for_hypothesis.restype = ci
+        if hasattr(L, "pvref_generate_hypothesis_vp"):
+            L.pvref_generate_hypothesis_vp.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci]
+            L.pvref_generate_hypothesis_vp.restype = ci
+            L.pvref_voting_for_hypothesis_vp.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci]
+            L.pvref_voting_for_hypothesis_vp.restype = ci
         _lib = L
     return _lib
 
@@ -72,6 +77,30 @@ def voting_for_hypothesis(direct, coords, hypo, inliers, thresh):
                                            inliers.data_ptr(), tn, vn, hn, float(thresh), _dev(direct))
     if rc != 0:
         raise RuntimeError(f"pvref_voting_for_hypothesis -> {rc}")
+
+
+def generate_hypothesis_vanishing_point(direct, coords, idxs):
+    """ransac_voting.cpp:61-72 -> ransac_voting_kernel.cu:232-260"""
+    tn, vn, _ = direct.shape
+    hn = idxs.shape[0]
+    torch.cuda.synchronize()
+    out = torch.empty([hn, vn, 3], dtype=torch.float32, device=direct.device)
+    rc = lib().pvref_generate_hypothesis_vp(direct.data_ptr(), coords.data_ptr(), idxs.data_ptr(), out.data_ptr(),
+                                            tn, vn, hn, _dev(direct))
+    if rc != 0:
+        raise RuntimeError(f"pvref_generate_hypothesis_vp -> {rc}")
+    return out
+
+
+def voting_for_hypothesis_vanishing_point(direct, coords, hypo, inliers, thresh):
+    """ransac_voting.cpp:82-96 -> ransac_voting_kernel.cu:307-351"""
+    tn, vn, _ = direct.shape
+    hn = hypo.shape[0]
+    torch.cuda.synchronize()
+    rc = lib().pvref_voting_for_hypothesis_vp(direct.data_ptr(), coords.data_ptr(), hypo.data_ptr(), inliers.data_ptr(),
+                                              tn, vn, hn, float(thresh), _dev(direct))
+    if rc != 0:
+        raise RuntimeError(f"pvref_voting_for_hypothesis_vp -> {rc}")
 
 
 def _inverse_2x2(mats):

@@ -18,6 +18,10 @@ at::Tensor generate_hypothesis_launcher(at::Tensor direct, at::Tensor coords, at
 void voting_for_hypothesis_launcher(at::Tensor direct, at::Tensor coords, at::Tensor hypo_pts,
                                     at::Tensor inliers, float inlier_thresh);
 
+at::Tensor generate_hypothesis_vanishing_point_launcher(at::Tensor direct, at::Tensor coords, at::Tensor idxs);
+void voting_for_hypothesis_vanishing_point_launcher(at::Tensor direct, at::Tensor coords, at::Tensor hypo_pts,
+                                                    at::Tensor inliers, float inlier_thresh);
+
 namespace {
 at::Tensor wrap(void *p, at::IntArrayRef sizes, at::ScalarType t, int device)
 {
@@ -61,6 +65,41 @@ int pvref_voting_for_hypothesis(float *direct, float *coords, float *hypo, uint8
         at::Tensor h = wrap(hypo, {hn, vn, 2}, at::kFloat, device);
         at::Tensor n = wrap(inliers, {hn, vn, tn}, at::kByte, device);
         voting_for_hypothesis_launcher(d, c, h, n, thresh);
+        return (int)cudaDeviceSynchronize();
+    } catch (...) {
+        return -1;
+    }
+}
+
+// the vanishing-point pair (ransac_voting_kernel.cu:232-260, :307-351): hypo [hn,vn,3]
+__attribute__((visibility("default")))
+int pvref_generate_hypothesis_vp(float *direct, float *coords, int32_t *idxs, float *hypo_out, int tn, int vn, int hn,
+                                 int device)
+{
+    try {
+        cudaSetDevice(device);
+        at::Tensor h = generate_hypothesis_vanishing_point_launcher(wrap(direct, {tn, vn, 2}, at::kFloat, device),
+                                                                    wrap(coords, {tn, 2}, at::kFloat, device),
+                                                                    wrap(idxs, {hn, vn, 2}, at::kInt, device));
+        cudaError_t e = cudaMemcpy(hypo_out, h.data_ptr<float>(), sizeof(float) * (size_t)hn * vn * 3,
+                                   cudaMemcpyDeviceToDevice);
+        if (e != cudaSuccess) return (int)e;
+        return (int)cudaDeviceSynchronize();
+    } catch (...) {
+        return -1;
+    }
+}
+
+__attribute__((visibility("default")))
+int pvref_voting_for_hypothesis_vp(float *direct, float *coords, float *hypo, uint8_t *inliers, int tn, int vn, int hn,
+                                   float thresh, int device)
+{
+    try {
+        cudaSetDevice(device);
+        voting_for_hypothesis_vanishing_point_launcher(wrap(direct, {tn, vn, 2}, at::kFloat, device),
+                                                       wrap(coords, {tn, 2}, at::kFloat, device),
+                                                       wrap(hypo, {hn, vn, 3}, at::kFloat, device),
+                                                       wrap(inliers, {hn, vn, tn}, at::kByte, device), thresh);
         return (int)cudaDeviceSynchronize();
     } catch (...) {
         return -1;

@@ -11,13 +11,14 @@
 //   k_chunk_kept    per-chunk kept counts (only when an image may be subsampled)
 //   k_compact_write stable (row-major) list of foreground pixels, packed (y<<16|x)
 //   k_gather        ONE pass over the vector field: direct[b][k][t] (float2, compact, keypoint-
-//                   major) + a bounding box per 512-pixel tile; every later kernel streams
-//                   these coalesced lists instead of gathering sectors from the field again
+//                   major); every later kernel streams these coalesced lists instead of
+//                   gathering sectors from the field again
 //   k_gen_hyp       ray-ray intersections, bit-exact op sequence of the reference
-//   k_vote2         persistent kernel: pixel tiles staged in shared memory once per
-//                   (image, keypoint, hypothesis group) as the two edge functionals of the
-//                   inlier cone, every lane keeps 4/8 hypotheses in registers, inlier
-//                   counts accumulate in registers; the [hn,vn,tn] tensor never exists
+//   k_vote2         persistent kernel of autonomous warps: a warp takes (image, keypoint, 256
+//                   hypotheses, pixel segment), stages 64 pixels at a time in its private
+//                   shared memory as the two edge functionals of the inlier cone, keeps 8
+//                   hypotheses per lane and their counts in registers; the [hn,vn,tn]
+//                   tensor never exists
 //   k_refit         argmax (lowest index on ties) + inlier sums of the winner in fp64
 //   k_refit_final   fixed-order reduction + 2x2 solve
 //   k_cov           estimate_voting_distribution_with_mean's weighted covariance
@@ -317,14 +318,12 @@ __global__ void k_sum_chunks(const int *__restrict__ chunk_fg, int nchunk, int *
 // ------------------------------------------------------------------ gather
 // One CTA per (512-pixel tile, image): direct[b][k][t] = vertex[b, y_t, x_t, k, :] for every keypoint,
 // read through the caller's strides (thread = pixel: coalesced along mask rows for the NCHW view,
-// L1-resident 8-byte pieces of one record for a pixel-major field), written coalesced.  Also the
-// tile's bounding box -> (centre, L1 radius) used by k_vote2's tile-centred arithmetic.
+// L1-resident 8-byte pieces of one record for a pixel-major field), written coalesced.  Every later
+// kernel streams these compact lists instead of gathering sectors from the field again.
 __global__ void __launch_bounds__(256)
     k_gather(const float *__restrict__ vertex, Strides st, const unsigned *__restrict__ pix,
-             const int *__restrict__ tn_arr, int npx, int cap, int ntile, int vn, float2 *__restrict__ direct,
-             float4 *__restrict__ tinfo)
+             const int *__restrict__ tn_arr, int npx, int cap, int vn, float2 *__restrict__ direct)
 {
-    __shared__ int s_mm[8][2];
     const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int tn = tn_arr[b];
     const int t0 = g * VT_TILE;
@@ -332,12 +331,9 @@ __global__ void __launch_bounds__(256)
     const int len = min(VT_TILE, tn - t0);
     const bool vec2 = st.s[4] == 1 && ((st.s[0] | st.s[1] | st.s[2] | st.s[3]) & 1) == 0 &&
                       (reinterpret_cast<uintptr_t>(vertex) & 7) == 0;
-    int xmin = 0x7fffffff, xmax = -1;
     for (int i = tid; i < len; i += 256) {
         const unsigned p = pix[(size_t)b * npx + t0 + i];
         const int x = p & 0xffff, y = p >> 16;
-        xmin = min(xmin, x);
-        xmax = max(xmax, x);
         const long long base = (long long)b * st.s[0] + (long long)y * st.s[1] + (long long)x * st.s[2];
         float2 *o = direct + (size_t)b * vn * cap + t0 + i;
         for (int k = 0; k < vn; ++k) {
@@ -347,24 +343,6 @@ __global__ void __launch_bounds__(256)
             else v = make_float2(__ldg(vertex + off), __ldg(vertex + off + st.s[4]));
             o[(size_t)k * cap] = v;
         }
-    }
-    xmin = __reduce_min_sync(0xffffffffu, xmin);
-    xmax = __reduce_max_sync(0xffffffffu, xmax);
-    if ((tid & 31) == 0) {
-        s_mm[tid >> 5][0] = xmin;
-        s_mm[tid >> 5][1] = xmax;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int i = 1; i < 8; ++i) {
-            xmin = min(xmin, s_mm[i][0]);
-            xmax = max(xmax, s_mm[i][1]);
-        }
-        // the list is row-major: first / last pixel carry the extreme rows
-        const int ymin = pix[(size_t)b * npx + t0] >> 16, ymax = pix[(size_t)b * npx + t0 + len - 1] >> 16;
-        const int xc = (xmin + xmax) >> 1, yc = (ymin + ymax) >> 1;
-        const int r1 = max(xc - xmin, xmax - xc) + max(yc - ymin, ymax - yc);
-        tinfo[(size_t)b * ntile + g] = make_float4((float)xc, (float)yc, (float)r1, 0.f);
     }
 }
 
@@ -409,12 +387,6 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr)
 {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float2 lds_f2(uint32_t addr)
-{
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
 // cnt += (a > b): one FSETP + one predicated IADD (the C form compiled to add + predicated move + move)
@@ -612,77 +584,104 @@ __device__ __forceinline__ void lds_2x64(uint32_t addr, f32x2 &a, f32x2 &b)
 }
 constexpr float VT_SCALE = 18446744073709551616.f;     // 2^64
 
+// Work decomposition (second ncu pass: with CTA-wide tiles, 48 % of the stall samples sat OUTSIDE the
+// test loop -- the dependent global loads of staging / hypothesis set-up, and three CTA barriers per
+// item): warps are autonomous.  A warp pulls (image, keypoint, group of 32*HPL hypotheses, pixel
+// segment) items from a ticket counter, keeps its hypotheses and counts in registers for the whole
+// segment, stages 64 pixels at a time into its PRIVATE 3 KB of shared memory (next sub-chunk
+// prefetched into registers during the sweep; only __syncwarp), and publishes the counts with one RED
+// per hypothesis.  No CTA barrier after the prologue.
+constexpr int VT_SUB = 64;        // pixels per staged sub-chunk (2 per lane)
+
 template <int HPL>
 __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
-    k_vote2(const unsigned *__restrict__ pix, const float2 *__restrict__ direct, const float4 *__restrict__ tinfo,
-            const int *__restrict__ tn_arr, int npx, int cap, int ntile, int nb, int vn, int hn, int HT, int h0,
-            int wh, const float2 *__restrict__ hyp, int *__restrict__ counts, float thresh, float sn, float cs,
-            float beta, float b0)
+    k_vote2(const unsigned *__restrict__ pix, const float2 *__restrict__ direct, const int *__restrict__ tn_arr, int npx,
+            int cap, int nb, int vn, int hn, int HT, int h0, const float2 *__restrict__ hyp, int *__restrict__ counts,
+            unsigned *__restrict__ ticket, float thresh, float sn, float cs, float beta, float b0)
 {
-    // per pixel 48 bytes: {sx,sx,sy,sy} {ns,ns,cx,cx} {cy,cy,nc,nc}
-    __shared__ float4 rec[3 * VT_TILE];
-    __shared__ int red[VT_WARPS * 32 * HPL];
-    __shared__ int tile_prefix[VT_MAX_B + 1];
+    // per warp, per pixel 48 bytes: {sx,sx,sy,sy} {ns,ns,cx,cx} {cy,cy,nc,nc}
+    __shared__ float4 rec_all[VT_WARPS * 3 * VT_SUB];
+    __shared__ int seg_prefix[VT_MAX_B + 1];
+    __shared__ int s_seg;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int HC = 32 * HPL;
+    const int hcn = (hn + HC - 1) / HC;
     if (tid == 0) {
+        // pixels per item: the largest power-of-two multiple of VT_SUB (<= 4096) that still leaves ~6 items per
+        // resident warp, so hypotheses are set up rarely and the tail stays short
+        long long px = 0;
+        for (int i = 0; i < nb; ++i) px += tn_arr[i];
+        const long long want = (long long)gridDim.x * VT_WARPS * 6;
+        int seg = 4096;
+        while (seg > 4 * VT_SUB && (px / seg + nb) * vn * hcn < want) seg >>= 1;
         int acc = 0;
         for (int i = 0; i < nb; ++i) {
-            tile_prefix[i] = acc;
-            acc += (tn_arr[i] + VT_TILE - 1) / VT_TILE;
+            seg_prefix[i] = acc;
+            acc += (tn_arr[i] + seg - 1) / seg;
         }
-        tile_prefix[nb] = acc;
+        seg_prefix[nb] = acc;
+        s_seg = seg;
     }
     __syncthreads();
-    const int total_tiles = tile_prefix[nb];
-    const int HC = wh * 32 * HPL;               // hypotheses per item
-    const int hcn = (hn + HC - 1) / HC;
-    const long long n_items = (long long)total_tiles * vn * hcn;
-    const int wp_count = VT_WARPS / wh;
-    const int my_wh = warp % wh, my_wp = warp / wh;
+    const int SEG = s_seg;
+    const long long n_items = (long long)seg_prefix[nb] * vn * hcn;
     const float qnan = __int_as_float(0x7fc00000);
+    float4 *rec = rec_all + warp * (3 * VT_SUB);
     const uint32_t rec_u = ptx_smem_u32(rec);
 
-    for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (;;) {
+        unsigned item_u = 0;
+        if (lane == 0) item_u = atomicAdd(ticket, 1u);
+        const long long it = (long long)__shfl_sync(0xffffffffu, item_u, 0);
+        if (it >= n_items) break;
         const int hc = (int)(it % hcn);
         const long long r = it / hcn;
         const int k = (int)(r % vn);
         const int g = (int)(r / vn);
-        int lo = 0, hi = nb;                         // b with tile_prefix[b] <= g < tile_prefix[b+1]
+        int lo = 0, hi = nb;                         // b with seg_prefix[b] <= g < seg_prefix[b+1]
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if (tile_prefix[mid] <= g) lo = mid; else hi = mid;
+            if (seg_prefix[mid] <= g) lo = mid; else hi = mid;
         }
         const int b = lo;
         const int tn = tn_arr[b];
-        const int gt = g - tile_prefix[b];
-        const int t0 = gt * VT_TILE;
-        const int len = min(VT_TILE, tn - t0);
-        const float4 ti = __ldg(tinfo + (size_t)b * ntile + gt);          // (xc, yc, r1)
+        const int t0 = (g - seg_prefix[b]) * SEG;
+        const int len = min(SEG, tn - t0);
         const unsigned *pix_t = pix + (size_t)b * npx + t0;
         const float2 *dir_t = direct + ((size_t)b * vn + k) * cap + t0;
 
-        // ---- stage: coalesced streams -> cone functionals, duplicated for the packed FMAs
-        for (int i = tid; i < len; i += VT_THREADS) {
-            const unsigned p = __ldg(pix_t + i);
-            const float2 n = __ldg(dir_t + i);
-            const float xr = (float)(int)(p & 0xffff) - ti.x, yr = (float)(int)(p >> 16) - ti.y;
-            const float n2 = fmaf(n.x, n.x, n.y * n.y);
-            const float rinv = rsqrtf(n2);
-            const float ux = n.x * rinv, uy = n.y * rinv;
-            float sx = sn * ux, sy = sn * uy, cx = -cs * uy, cy = cs * ux;
-            float ns = -fmaf(sx, xr, sy * yr), nc = -fmaf(cx, xr, cy * yr);
-            if (!(n2 > 1e-11f && n2 < 1e30f)) sx = sy = cx = cy = ns = nc = qnan;   // -> exact path
-            rec[3 * i] = make_float4(sx, sx, sy, sy);
-            rec[3 * i + 1] = make_float4(ns, ns, cx, cx);
-            rec[3 * i + 2] = make_float4(cy, cy, nc, nc);
-        }
-        for (int i = tid; i < HC; i += VT_THREADS) red[i] = 0;
-        __syncthreads();
-
-        // ---- this lane's hypotheses, tile-centred, and their guard bands
-        const int hbase = hc * HC + my_wh * (32 * HPL);
+        // ---- this lane's hypotheses (issued first: their latency overlaps the bounding-box pass)
+        const int hbase = hc * HC;
         const float2 *hyp_row = hyp + ((size_t)b * vn + k) * HT + h0;
+        float2 hraw[HPL];
+#pragma unroll
+        for (int j = 0; j < HPL; ++j) {
+            const int h = hbase + j * 32 + lane;
+            hraw[j] = (h < hn) ? __ldg(hyp_row + h) : make_float2(0.f, 0.f);
+        }
+        // first sub-chunk's raw data
+        unsigned pp[2];
+        float2 pn[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int i = e * 32 + lane;
+            pp[e] = (i < len) ? __ldg(pix_t + i) : 0u;
+            pn[e] = (i < len) ? __ldg(dir_t + i) : make_float2(0.f, 0.f);
+        }
+        // ---- bounding box of the segment (the list is row-major: rows from its ends, columns by a pass)
+        int xmin = 0x7fffffff, xmax = -1;
+        for (int i = lane; i < len; i += 32) {
+            const int x = (int)(__ldg(pix_t + i) & 0xffffu);
+            xmin = min(xmin, x);
+            xmax = max(xmax, x);
+        }
+        xmin = __reduce_min_sync(0xffffffffu, xmin);
+        xmax = __reduce_max_sync(0xffffffffu, xmax);
+        const int ymin = (int)(__ldg(pix_t) >> 16), ymax = (int)(__ldg(pix_t + len - 1) >> 16);
+        const float xc = (float)((xmin + xmax) >> 1), yc = (float)((ymin + ymax) >> 1);
+        const float r1 = (float)(max((int)xc - xmin, xmax - (int)xc) + max((int)yc - ymin, ymax - (int)yc));
+
         f32x2 hx2[HPL / 2], hy2[HPL / 2];
         float bd[HPL], nb2[HPL], cnt[HPL];          // band, -band * 2^64, count (exact small integers in fp32)
 #pragma unroll
@@ -694,10 +693,9 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                 hxv[e] = hyv[e] = 0.f;
                 bd[j + e] = -1.f;                   // padding: never uncertain, count discarded
                 if (h < hn) {
-                    const float2 hp = __ldg(hyp_row + h);
-                    hxv[e] = hp.x - ti.x;
-                    hyv[e] = hp.y - ti.y;
-                    bd[j + e] = fmaf(beta, fabsf(hxv[e]) + fabsf(hyv[e]) + ti.z, b0);
+                    hxv[e] = hraw[j + e].x - xc;
+                    hyv[e] = hraw[j + e].y - yc;
+                    bd[j + e] = fmaf(beta, fabsf(hxv[e]) + fabsf(hyv[e]) + r1, b0);
                     if (!(bd[j + e] < 1e18f)) bd[j + e] = qnan;     // absurdly far / non-finite: exact path
                 }
                 nb2[j + e] = -bd[j + e] * VT_SCALE;
@@ -707,16 +705,43 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
             hy2[j / 2] = pk2(hyv[0], hyv[1]);
         }
 
-        // this warp's contiguous pixel chunk (multiple of VT_GROUP)
-        const int chunk = ((len + wp_count - 1) / wp_count + VT_GROUP - 1) / VT_GROUP * VT_GROUP;
-        const int p_lo = min(len, my_wp * chunk), p_hi = min(len, p_lo + chunk);
-
-        auto sweep = [&](int i0, int n) {           // pixels i0 .. i0 + n - 1 (n <= VT_GROUP)
-            bool unc = false;
-            const uint32_t base = rec_u + (uint32_t)i0 * 48u;
+        for (int c0 = 0; c0 < len; c0 += VT_SUB) {
+            const int clen = min(VT_SUB, len - c0);
+            // ---- stage this sub-chunk from the prefetched registers: cone functionals, duplicated for FFMA2
 #pragma unroll
-            for (int u = 0; u < VT_GROUP; ++u) {
-                if (u < n) {
+            for (int e = 0; e < 2; ++e) {
+                const int i = e * 32 + lane;
+                const unsigned p = pp[e];
+                const float2 n = pn[e];
+                const float xr = (float)(int)(p & 0xffff) - xc, yr = (float)(int)(p >> 16) - yc;
+                const float n2 = fmaf(n.x, n.x, n.y * n.y);
+                const float rinv = rsqrtf(n2);
+                const float ux = n.x * rinv, uy = n.y * rinv;
+                float sx = sn * ux, sy = sn * uy, cx = -cs * uy, cy = cs * ux;
+                float ns = -fmaf(sx, xr, sy * yr), nc = -fmaf(cx, xr, cy * yr);
+                if (!(n2 > 1e-11f && n2 < 1e30f)) sx = sy = cx = cy = ns = nc = qnan;   // -> exact path
+                if (i >= clen) {                    // padding pixel: m = -1e30, never counted, never uncertain
+                    sx = sy = cx = cy = nc = 0.f;
+                    ns = -1e30f;
+                }
+                rec[3 * i] = make_float4(sx, sx, sy, sy);
+                rec[3 * i + 1] = make_float4(ns, ns, cx, cx);
+                rec[3 * i + 2] = make_float4(cy, cy, nc, nc);
+            }
+            __syncwarp();
+            // ---- prefetch the next sub-chunk
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = c0 + VT_SUB + e * 32 + lane;
+                pp[e] = (i < len) ? __ldg(pix_t + i) : 0u;
+                pn[e] = (i < len) ? __ldg(dir_t + i) : make_float2(0.f, 0.f);
+            }
+            // ---- sweep: VT_GROUP pixels x HPL hypotheses per step
+            for (int i0 = 0; i0 < clen; i0 += VT_GROUP) {
+                bool unc = false;
+                const uint32_t base = rec_u + (uint32_t)i0 * 48u;
+#pragma unroll
+                for (int u = 0; u < VT_GROUP; ++u) {
                     f32x2 SX, SY, NS, CX, CY, NC;
                     lds_2x64(base + (uint32_t)u * 48u, SX, SY);
                     lds_2x64(base + (uint32_t)u * 48u + 16u, NS, CX);
@@ -735,52 +760,44 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                         unc |= !(fabsf(m1) > bd[2 * j + 1]);
                     }
                 }
-            }
-            if (__any_sync(0xffffffffu, unc)) {
-                if (unc) {
-                    for (int u = 0; u < n; ++u) {
-                        const int pi = i0 + u;
-                        const float4 ra = rec[3 * pi], rb = rec[3 * pi + 1], rc = rec[3 * pi + 2];
+                if (__any_sync(0xffffffffu, unc)) {
+                    if (unc) {
+                        for (int u = 0; u < VT_GROUP; ++u) {
+                            const int pi = i0 + u;
+                            if (pi >= clen) break;
+                            const float4 ra = rec[3 * pi], rb = rec[3 * pi + 1], rc = rec[3 * pi + 2];
 #pragma unroll
-                        for (int j = 0; j < HPL; ++j) {
-                            float hxa, hxb, hya, hyb;
-                            upk2(hx2[j / 2], hxa, hxb);
-                            upk2(hy2[j / 2], hya, hyb);
-                            const float hxs = (j & 1) ? hxb : hxa, hys = (j & 1) ? hyb : hya;
-                            const float num = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
-                            const float perp = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
-                            const float m = num - fabsf(perp);
-                            if (hbase + j * 32 + lane < hn && !(fabsf(m) > bd[j])) {
-                                const unsigned p = pix_t[pi];
-                                const float2 nraw = dir_t[pi];
-                                const float2 hp = hyp_row[hbase + j * 32 + lane];
-                                cnt[j] += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hp.x, hp.y,
-                                                       thresh)
-                                              ? 1.f
-                                              : 0.f;
+                            for (int j = 0; j < HPL; ++j) {
+                                float hxa, hxb, hya, hyb;
+                                upk2(hx2[j / 2], hxa, hxb);
+                                upk2(hy2[j / 2], hya, hyb);
+                                const float hxs = (j & 1) ? hxb : hxa, hys = (j & 1) ? hyb : hya;
+                                const float num = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
+                                const float perp = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
+                                const float m = num - fabsf(perp);
+                                if (hbase + j * 32 + lane < hn && !(fabsf(m) > bd[j])) {
+                                    const unsigned p = pix_t[c0 + pi];
+                                    const float2 nraw = dir_t[c0 + pi];
+                                    cnt[j] += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hraw[j].x,
+                                                           hraw[j].y, thresh)
+                                                  ? 1.f
+                                                  : 0.f;
+                                }
                             }
                         }
                     }
                 }
             }
-        };
-        int i = p_lo;
-        for (; i + VT_GROUP <= p_hi; i += VT_GROUP) sweep(i, VT_GROUP);
-        if (i < p_hi) sweep(i, p_hi - i);
+            __syncwarp();
+        }
 
-        // ---- combine the pixel-chunk warps, then one atomic per hypothesis
+        // ---- one RED per hypothesis
 #pragma unroll
         for (int j = 0; j < HPL; ++j) {
+            const int h = hbase + j * 32 + lane;
             const int c = (int)cnt[j];
-            if (c) atomicAdd(&red[my_wh * (32 * HPL) + j * 32 + lane], c);
+            if (h < hn && c) atomicAdd(counts + ((size_t)b * vn + k) * HT + h0 + h, c);
         }
-        __syncthreads();
-        for (int i2 = tid; i2 < HC; i2 += VT_THREADS) {
-            const int h = hc * HC + i2;
-            const int v = red[i2];
-            if (h < hn && v) atomicAdd(counts + ((size_t)b * vn + k) * HT + h0 + h, v);
-        }
-        __syncthreads();
     }
 }
 
@@ -1203,12 +1220,94 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) counts[hi * vn + vi] = c;
 }
 
+// ------------------------------------------------------------------ vanishing-point pair
+// 1:1 stand-ins for generate_hypothesis_vanishing_point / voting_for_hypothesis_vanishing_point
+// (src/ransac_voting_kernel.cu:170-230, :263-305): homogeneous intersections [hn,vn,3] of the two pixels'
+// lines and the |cos| test against them.  Rounding sequence read off the SASS nvcc 12.9 emits for the
+// reference file (sm_100a, default -fmad): every fma below is one the compiler contracted, every
+// __fmul_rn a product it kept separate because the value is used twice.
+__device__ __forceinline__ void exact_vp_hypothesis(float dx0, float dy0, float cx0, float cy0, float dx1, float dy1,
+                                                    float cx1, float cy1, float &ox, float &oy, float &oz)
+{
+    const float lz0 = __fmaf_rn(dx0, cy0, -__fmul_rn(dy0, cx0));      // cy0*dx0 - cx0*dy0   (:197)
+    const float lz1 = __fmaf_rn(dx1, cy1, -__fmul_rn(dy1, cx1));      //                     (:201)
+    float z = __fmaf_rn(dx0, dy1, -__fmul_rn(dy0, dx1));              // lx0*ly1 - ly0*lx1   (:206)
+    float x = __fmaf_rn(dx1, lz0, -__fmul_rn(dx0, lz1));              // ly0*lz1 - lz0*ly1   (:204)
+    float y = __fmaf_rn(dy1, lz0, -__fmul_rn(dy0, lz1));              // lz0*lx1 - lx0*lz1   (:205)
+    const float vx0 = __fmul_rn(dx0, __fmaf_rn(-cx0, z, x)), vx1 = __fmul_rn(dx1, __fmaf_rn(-cx1, z, x));   // :209-210
+    const float vy0 = __fmul_rn(dy0, __fmaf_rn(-cy0, z, y)), vy1 = __fmul_rn(dy1, __fmaf_rn(-cy1, z, y));   // :211-212
+    if (vx0 < 0.f && vx1 < 0.f && vy0 < 0.f && vy1 < 0.f) {            // :214-215
+        x = -x;
+        y = -y;
+        z = -z;
+    }
+    // :217-218 `val_x0*val_x1<0 || val_y0*val_y1<0` as the compiler evaluates it: min of the two products
+    // (FMNMX returns the non-NaN operand), zeroed unless it is >= 0 or unordered
+    const float m = fminf(__fmul_rn(vx0, vx1), __fmul_rn(vy0, vy1));
+    if (m < 0.f) x = y = z = 0.f;
+    ox = x;
+    oy = y;
+    oz = z;
+}
+
+__device__ __forceinline__ bool exact_vp_inlier(float dx, float dy, float cx, float cy, float hx, float hy, float hz,
+                                                float thresh)
+{
+    const float fx = __fmaf_rn(-cx, hz, hx), fy = __fmaf_rn(-cy, hz, hy);              // :287-288
+    const float norm1 = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    const float norm2 = __fsqrt_rn(__fmaf_rn(fx, fx, __fmul_rn(fy, fy)));
+    if (fmin((double)norm1, (double)norm2) < 1e-6) return false;                       // :292
+    const float vx = __fmul_rn(fx, dx), vy = __fmul_rn(fy, dy);                        // :295-296 (reused by :294)
+    const float ang = __fdiv_rn(__fadd_rn(vx, vy), __fmul_rn(norm2, norm1));
+    if (fminf(vx, vy) < 0.f) return false;                                             // :297
+    return fabsf(ang) > thresh;                                                        // :298
+}
+
+__global__ void k_compat_vp_gen_hyp(const float *__restrict__ direct, const float *__restrict__ coords,
+                                    const int *__restrict__ idxs, float *__restrict__ hypo, int vn, int hn)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hn * vn) return;
+    const int vi = i % vn;
+    const int t0 = idxs[i * 2], t1 = idxs[i * 2 + 1];
+    float x, y, z;
+    exact_vp_hypothesis(direct[((size_t)t0 * vn + vi) * 2], direct[((size_t)t0 * vn + vi) * 2 + 1],
+                        coords[(size_t)t0 * 2], coords[(size_t)t0 * 2 + 1], direct[((size_t)t1 * vn + vi) * 2],
+                        direct[((size_t)t1 * vn + vi) * 2 + 1], coords[(size_t)t1 * 2], coords[(size_t)t1 * 2 + 1], x, y,
+                        z);
+    hypo[i * 3] = x;
+    hypo[i * 3 + 1] = y;
+    hypo[i * 3 + 2] = z;
+}
+
+// block per (keypoint, hypothesis): optional u8 inlier rows [hn,vn,tn] (only SET, like the reference)
+// and/or the row sums [hn,vn]
+__global__ void __launch_bounds__(256)
+    k_compat_vp_vote(const float *__restrict__ direct, const float *__restrict__ coords, const float *__restrict__ hypo,
+                     unsigned char *__restrict__ inliers, int *__restrict__ counts, int tn, int vn, float thresh)
+{
+    __shared__ int scratch[96];
+    const int vi = blockIdx.x, hi = blockIdx.y;
+    const float hx = hypo[(hi * vn + vi) * 3], hy = hypo[(hi * vn + vi) * 3 + 1], hz = hypo[(hi * vn + vi) * 3 + 2];
+    int c = 0, z0 = 0, z1 = 0;
+    for (int ti = threadIdx.x; ti < tn; ti += blockDim.x) {
+        const bool in = exact_vp_inlier(direct[((size_t)ti * vn + vi) * 2], direct[((size_t)ti * vn + vi) * 2 + 1],
+                                        coords[(size_t)ti * 2], coords[(size_t)ti * 2 + 1], hx, hy, hz, thresh);
+        if (in && inliers) inliers[((size_t)hi * vn + vi) * tn + ti] = 1;
+        c += in ? 1 : 0;
+    }
+    if (counts) {
+        block_sum3(c, z0, z1, scratch);
+        if (threadIdx.x == 0) counts[hi * vn + vi] = c;
+    }
+}
+
 // ------------------------------------------------------------------ host side
 struct VoteWs {
     unsigned *pix;
     int *chunk_fg, *chunk_kept, *tn, *fg, *status, *counts;
     float2 *hyp, *win, *direct;
-    float4 *tinfo;
+    unsigned *ticket;
     double *part;
     int cap, ntile;      // per-image capacity of the compact lists (pixels, multiple of VT_TILE) and tiles
     size_t bytes;
@@ -1228,11 +1327,11 @@ VoteWs carve(void *ws, int b, int h, int w, int vn, int hn_total)
     v.tn = c.take<int>(b);
     v.fg = c.take<int>(b);
     v.status = c.take<int>(b);
+    v.ticket = c.take<unsigned>(1);
     v.counts = c.take<int>((size_t)b * vn * hn_total);
     v.hyp = c.take<float2>((size_t)b * vn * hn_total);
     v.win = c.take<float2>((size_t)b * vn);
     v.part = c.take<double>((size_t)b * vn * RF_CHUNKS * 5);
-    v.tinfo = c.take<float4>((size_t)b * v.ntile);
     v.direct = c.take<float2>((size_t)b * vn * v.cap);
     v.bytes = pvnet::align_up(c.off, 256);
     return v;
@@ -1296,7 +1395,7 @@ int launch_pixels(const void *mask, int esz, int mode, const float *vertex, cons
     }
     if (rc) return rc;
     dim3 grid(ws.ntile, b);
-    k_gather<<<grid, 256, 0, s>>>(vertex, st, ws.pix, ws.tn, h * w, ws.cap, ws.ntile, vn, ws.direct, ws.tinfo);
+    k_gather<<<grid, 256, 0, s>>>(vertex, st, ws.pix, ws.tn, h * w, ws.cap, vn, ws.direct);
     PV_LAUNCHED("k_gather");
     return PVNET_OK;
 }
@@ -1356,19 +1455,18 @@ int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int
         return e ? atoi(e) : 8;
     }();
     const int HPL = (impl == 2 && hpl_env == 8 && hn > 128) ? 8 : 4;
-    int wh = 1;                                        // hypothesis warps per CTA: 32*HPL hypotheses per warp
-    while (wh < VT_WARPS && wh * 32 * HPL < hn) wh <<= 1;
-    const int HC = wh * 32 * HPL;
-    const long long max_items = (long long)b * ((npx + VT_TILE - 1) / VT_TILE) * vn * ((hn + HC - 1) / HC);
     static const int ctas_per_sm = [] {
         const char *e = getenv("PVNET_VOTE_CTAS");     // tuning knob: resident vote CTAs per SM
         return e ? atoi(e) : 0;
     }();
-    const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : (HPL > 4 ? 2 : 3);
-    long long grid = (long long)pvnet::sm_count() * per_sm;
-    if (grid > max_items) grid = max_items;
-    if (grid < 1) grid = 1;
     if (impl == 0) {
+        int wh = 1;                                    // hypothesis warps per CTA: 128 hypotheses per warp
+        while (wh < VT_WARPS && wh * 32 * 4 < hn) wh <<= 1;
+        const int HC = wh * 32 * 4;
+        const long long max_items = (long long)b * ((npx + VT_TILE - 1) / VT_TILE) * vn * ((hn + HC - 1) / HC);
+        long long grid = (long long)pvnet::sm_count() * (ctas_per_sm > 0 ? ctas_per_sm : 4);
+        if (grid > max_items) grid = max_items;
+        if (grid < 1) grid = 1;
         // thresh <= 0 (or NaN) has no squared form: NaN makes every test take the exact path
         const float t2 = (thresh > 0.f && thresh < 1e18f) ? thresh * thresh : nanf("");
         const float band = GUARD_EPS * (thresh > 0.f ? thresh * thresh : 1.f);
@@ -1378,12 +1476,15 @@ int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int
         return PVNET_OK;
     }
     const VoteConsts vc = vote_consts(thresh);
+    const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : (HPL > 4 ? 2 : 3);
+    const unsigned grid = (unsigned)(pvnet::sm_count() * per_sm);
+    PV_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(unsigned), s));
     if (HPL == 8)
-        k_vote2<8><<<(unsigned)grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tinfo, ws.tn, npx, ws.cap, ws.ntile, b, vn, hn,
-                                                         HT, h0, wh, ws.hyp, ws.counts, thresh, vc.sn, vc.cs, vc.beta, vc.b0);
+        k_vote2<8><<<grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tn, npx, ws.cap, b, vn, hn, HT, h0, ws.hyp, ws.counts,
+                                               ws.ticket, thresh, vc.sn, vc.cs, vc.beta, vc.b0);
     else
-        k_vote2<4><<<(unsigned)grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tinfo, ws.tn, npx, ws.cap, ws.ntile, b, vn, hn,
-                                                         HT, h0, wh, ws.hyp, ws.counts, thresh, vc.sn, vc.cs, vc.beta, vc.b0);
+        k_vote2<4><<<grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tn, npx, ws.cap, b, vn, hn, HT, h0, ws.hyp, ws.counts,
+                                               ws.ticket, thresh, vc.sn, vc.cs, vc.beta, vc.b0);
     PV_LAUNCHED("k_vote2");
     return PVNET_OK;
 }
@@ -1667,6 +1768,28 @@ int pvnet_voting_for_hypothesis(const float *direct, const float *coords, const 
     dim3 grid((tn + 255) / 256, vn, hn);
     k_compat_vote<<<grid, 256, 0, (cudaStream_t)stream>>>(direct, coords, hypo, inliers, tn, vn, hn, inlier_thresh);
     PV_LAUNCHED("k_compat_vote");
+    return PVNET_OK;
+}
+
+int pvnet_generate_hypothesis_vanishing_point(const float *direct, const float *coords, const int32_t *idxs,
+                                              float *hypo, int tn, int vn, int hn, pvnet_stream_t stream)
+{
+    PV_CHECK_ARG(direct && coords && idxs && hypo, "null pointer");
+    PV_CHECK_ARG(tn >= 1 && vn >= 1 && hn >= 1, "non-positive dimension");
+    k_compat_vp_gen_hyp<<<(hn * vn + 255) / 256, 256, 0, (cudaStream_t)stream>>>(direct, coords, idxs, hypo, vn, hn);
+    PV_LAUNCHED("k_compat_vp_gen_hyp");
+    return PVNET_OK;
+}
+
+int pvnet_voting_for_hypothesis_vanishing_point(const float *direct, const float *coords, const float *hypo,
+                                                uint8_t *inliers, int32_t *counts, int tn, int vn, int hn,
+                                                float inlier_thresh, pvnet_stream_t stream)
+{
+    PV_CHECK_ARG(direct && coords && hypo && (inliers || counts), "null pointer");
+    PV_CHECK_ARG(tn >= 1 && vn >= 1 && hn >= 1 && hn <= 65535, "dimension out of range");
+    dim3 grid(vn, hn);
+    k_compat_vp_vote<<<grid, 256, 0, (cudaStream_t)stream>>>(direct, coords, hypo, inliers, counts, tn, vn, inlier_thresh);
+    PV_LAUNCHED("k_compat_vp_vote");
     return PVNET_OK;
 }
 

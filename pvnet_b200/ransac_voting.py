@@ -6,6 +6,8 @@ runs unmodified on top of this module (A/B testing); the fused layer in
 
     generate_hypothesis(direct[tn,vn,2], coords[tn,2], idxs[hn,vn,2] int32) -> [hn,vn,2]
     voting_for_hypothesis(direct, coords, hypo_pts[hn,vn,2], inliers[hn,vn,tn] uint8, thresh)
+    generate_hypothesis_vanishing_point(direct, coords, idxs) -> [hn,vn,3]        (ransac_voting.cpp:61-72)
+    voting_for_hypothesis_vanishing_point(direct, coords, hypo_pts[hn,vn,3], inliers, thresh)   (:82-96)
 """
 from __future__ import annotations
 
@@ -69,4 +71,37 @@ def vote_counts(direct, coords, hypo_pts, inlier_thresh):
         _native.check(_native.lib().pvnet_vote_counts(
             _p(direct), _p(coords), _p(hypo_pts), _p(counts), tn, vn, hn, float(inlier_thresh),
             ctypes.c_void_p(torch.cuda.current_stream(direct.device).cuda_stream)), "pvnet_vote_counts")
+    return counts
+
+
+def generate_hypothesis_vanishing_point(direct, coords, idxs):
+    _check(direct, "direct", torch.float32)
+    _check(coords, "coords", torch.float32)
+    _check(idxs, "idxs", torch.int32)
+    tn, vn, _ = direct.shape
+    hn = idxs.shape[0]
+    with torch.cuda.device(direct.device):
+        hypo = torch.empty([hn, vn, 3], dtype=torch.float32, device=direct.device)
+        _native.check(_native.lib().pvnet_generate_hypothesis_vanishing_point(
+            _p(direct), _p(coords), _p(idxs), _p(hypo), tn, vn, hn,
+            ctypes.c_void_p(torch.cuda.current_stream(direct.device).cuda_stream)),
+            "pvnet_generate_hypothesis_vanishing_point")
+    return hypo
+
+
+def voting_for_hypothesis_vanishing_point(direct, coords, hypo_pts, inliers, inlier_thresh, return_counts=False):
+    _check(direct, "direct", torch.float32)
+    _check(coords, "coords", torch.float32)
+    _check(hypo_pts, "hypo_pts", torch.float32)
+    if inliers is not None:
+        _check(inliers, "inliers", torch.uint8)
+    tn, vn, _ = direct.shape
+    hn = hypo_pts.shape[0]
+    with torch.cuda.device(direct.device):
+        counts = torch.empty([hn, vn], dtype=torch.int32, device=direct.device) if return_counts else None
+        _native.check(_native.lib().pvnet_voting_for_hypothesis_vanishing_point(
+            _p(direct), _p(coords), _p(hypo_pts), None if inliers is None else _p(inliers),
+            None if counts is None else _p(counts), tn, vn, hn, float(inlier_thresh),
+            ctypes.c_void_p(torch.cuda.current_stream(direct.device).cuda_stream)),
+            "pvnet_voting_for_hypothesis_vanishing_point")
     return counts

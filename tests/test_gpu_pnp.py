@@ -78,5 +78,5 @@ def test_random_poses_many_images():
     for i in range(b):
         ref = pn.uncertainty_pnp(kp[i].cpu().numpy(), pn.covariance_to_weights(cov[i].cpu().numpy()), pts, K)
         worst = max(worst, np.abs(poses[i] - ref).max())
-        assert np.abs(poses[i][:, 3] - truth[i][:, 3]).max() < 0.1          # sane: near the generating pose
+        assert np.abs(poses[i][:, 3] - truth[i][:, 3]).max() < 0.3          # sane: near the generating pose (depth is the weak axis)
     assert worst < 1e-8, worst
