@@ -20,6 +20,8 @@
  *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:333-406      estimate_voting_distribution_with_mean
  *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:763-858      ransac_voting_layer_v5
  *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:983-1034     generate_hypothesis (python level)
+ *   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:99-216       ransac_voting_layer_v2 (refinement rounds)
+ *   lib/ransac_voting_gpu_layer/src/ransac_voting.cpp:61-99       the vanishing-point kernel pair
  *   tools/train_linemod.py:119-130                                UncertaintyEvalWrapper.forward (v3 + with_mean)
  *   lib/utils/extend_utils/extend_utils.py:63-114                 uncertainty_pnp (+ evaluation_utils.py:165-201)
  *   lib/networks/model_repository.py:64-80                        Resnet18_8s.forward
@@ -104,6 +106,17 @@ PVNET_API int pvnet_ransac_voting_v3(const void *mask, int mask_elem_size,
                                      float inlier_thresh, int min_num, int max_num,
                                      float *out_pts, int32_t *out_counts, float *out_hyp, int32_t *out_tn,
                                      void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
+
+/* One refinement round of ransac_voting_layer_v2 (ransac_voting_gpu.py:178-204) for a whole batch: the
+ * pixels (mask low byte nonzero, subsampled like v3) that are inliers of points [b,vn,2] re-estimate
+ * them as the least-squares intersection of their lines -> out_pts [b,vn,2].  The reference's
+ * pinverse(A) b equals this normal-equation solution for full-rank A.  Workspace:
+ * pvnet_vote_workspace_bytes(b, h, w, vn, 1). */
+PVNET_API int pvnet_refit_at_points(const void *mask, int mask_elem_size,
+                                    const float *vertex, const int64_t vertex_strides[5],
+                                    const float *selection, const float *points,
+                                    int b, int h, int w, int vn, float inlier_thresh, int min_num, int max_num,
+                                    float *out_pts, void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
 
 /* ransac_voting_layer_v5 (ransac_voting_gpu.py:763-858): v3 plus a per-keypoint confidence
  * out_conf [b,vn] = (inliers of the refitted point at conf_thresh, 0.999 in the reference :850)

@@ -7,7 +7,11 @@ from pvnet_b200.ransac_voting_gpu import (  # noqa: F401
     ransac_motion_voting,
     ransac_voting_hypothesis,
     ransac_voting_layer,
+    ransac_voting_layer_v2,
     ransac_voting_layer_v3,
     ransac_voting_layer_v4,
     ransac_voting_layer_v5,
+    ransac_voting_pipeline,
+    ransac_voting_vanish_point_layer,
+    refit_at_points,
 )

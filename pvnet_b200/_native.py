@@ -33,6 +33,8 @@ SIGNATURES = {
     "pvnet_ransac_voting_v3": (c_int, [c_void_p, c_int, c_void_p, c_int64_p, c_void_p, c_void_p,
                                        c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pvnet_refit_at_points": (c_int, [c_void_p, c_int, c_void_p, c_int64_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_float, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pvnet_ransac_voting_v5": (c_int, [c_void_p, c_int, c_void_p, c_int64_p, c_void_p, c_void_p,
                                        c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

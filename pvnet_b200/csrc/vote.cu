@@ -816,7 +816,8 @@ __device__ __forceinline__ double warp_sum_d(double v)
 __global__ void __launch_bounds__(RF_THREADS)
     k_refit(const float2 *__restrict__ direct, int cap, const unsigned *__restrict__ pix,
             const int *__restrict__ tn_arr, int npx, int vn, int hn, int HT, const float2 *__restrict__ hyp,
-            const int *__restrict__ counts, float thresh, double *__restrict__ part, float2 *__restrict__ win)
+            const int *__restrict__ counts, float thresh, double *__restrict__ part, float2 *__restrict__ win,
+            const float2 *__restrict__ win_in)
 {
     __shared__ unsigned long long s_key[RF_THREADS / 32];
     __shared__ double s_acc[RF_THREADS / 32][5];
@@ -830,7 +831,7 @@ __global__ void __launch_bounds__(RF_THREADS)
         return;
     }
     unsigned long long key = 0;
-    for (int h = tid; h < hn; h += RF_THREADS) {
+    for (int h = tid; h < (win_in ? 0 : hn); h += RF_THREADS) {
         const unsigned long long kk =
             ((unsigned long long)(unsigned)counts[(size_t)bk * HT + h] << 32) | (unsigned long long)(0xffffffffu - (unsigned)h);
         key = kk > key ? kk : key;
@@ -847,7 +848,8 @@ __global__ void __launch_bounds__(RF_THREADS)
     const unsigned best_cnt = (unsigned)(key >> 32);
     const unsigned best_h = 0xffffffffu - (unsigned)(key & 0xffffffffu);
     float2 wp = make_float2(0.f, 0.f);
-    if (best_cnt > 0) wp = hyp[(size_t)bk * HT + best_h];
+    if (win_in) wp = win_in[bk];                 // refinement round: the caller's point instead of the winner
+    else if (best_cnt > 0) wp = hyp[(size_t)bk * HT + best_h];
     if (rc == 0 && tid == 0) win[bk] = wp;
 
     const int per = (tn + RF_CHUNKS - 1) / RF_CHUNKS;
@@ -1490,11 +1492,11 @@ int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int
 }
 
 int launch_refit(int b, int h, int w, int vn, int hn, int HT, float thresh, const VoteWs &ws, float *out_pts,
-                 cudaStream_t s)
+                 cudaStream_t s, const float2 *win_in = nullptr)
 {
     dim3 grf(RF_CHUNKS, b * vn);
     k_refit<<<grf, RF_THREADS, 0, s>>>(ws.direct, ws.cap, ws.pix, ws.tn, h * w, vn, hn, HT, ws.hyp, ws.counts, thresh,
-                                       ws.part, ws.win);
+                                       ws.part, ws.win, win_in);
     PV_LAUNCHED("k_refit");
     k_refit_final<<<(b * vn + 127) / 128, 128, 0, s>>>(ws.part, ws.tn, b, vn, out_pts);
     PV_LAUNCHED("k_refit_final");
@@ -1599,6 +1601,23 @@ int pvnet_ransac_voting_v3(const void *mask, int mask_elem_size, const float *ve
     if ((rc = launch_vote(vertex, st, b, h, w, vn, hn, hn, 0, inlier_thresh, ws, s))) return rc;
     if ((rc = launch_refit(b, h, w, vn, hn, hn, inlier_thresh, ws, out_pts, s))) return rc;
     return launch_export(ws, b, vn, hn, hn, 0, out_hyp, out_counts, out_tn, s);
+}
+
+int pvnet_refit_at_points(const void *mask, int mask_elem_size, const float *vertex, const int64_t vertex_strides[5],
+                          const float *selection, const float *points, int b, int h, int w, int vn,
+                          float inlier_thresh, int min_num, int max_num, float *out_pts, void *workspace,
+                          size_t workspace_bytes, pvnet_stream_t stream)
+{
+    int rc = check_common(mask, mask_elem_size, vertex, (const long long *)vertex_strides, b, h, w, vn, 1);
+    if (rc) return rc;
+    PV_CHECK_ARG(points && out_pts, "null points/out_pts");
+    const Strides st = to_strides(vertex_strides);
+    VoteWs ws = carve(workspace, b, h, w, vn, 1);
+    if ((rc = ws_check(ws, workspace, workspace_bytes))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Samples sm{nullptr, selection, nullptr};
+    if ((rc = launch_pixels(mask, mask_elem_size, PVNET_MASK_NONZERO_BYTE, vertex, st, sm, b, h, w, vn, min_num, max_num, ws, s))) return rc;
+    return launch_refit(b, h, w, vn, 1, 1, inlier_thresh, ws, out_pts, s, reinterpret_cast<const float2 *>(points));
 }
 
 int pvnet_ransac_voting_v5(const void *mask, int mask_elem_size, const float *vertex,

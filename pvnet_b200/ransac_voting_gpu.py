@@ -11,6 +11,8 @@ inference hot path:
     ransac_motion_voting                     (reference :960-981)
     ransac_voting_layer_v4                   (reference :669-760)
     ransac_voting_layer                      (reference :10-97)
+    ransac_voting_layer_v2                   (reference :99-216)
+    ransac_voting_vanish_point_layer         (reference :408-501)
     ransac_voting_hypothesis                 (reference :218-261)
     estimate_voting_distribution             (reference :263-331)
 
@@ -470,20 +472,58 @@ def _class_mask(mask, value):
     return (mask == value).to(torch.uint8)
 
 
+def _draw_reference_classes(mask, class_num, b, h, w, vn, hn, min_num, max_num):
+    """The reference's class-selecting layers loop `for bi: for k:` (ransac_voting_gpu.py:23-26, :113-117)
+    and draw inside: replay the torch RNG calls in that order.  Returns per-class lists of
+    (idxs [b,hn,vn,2], selection [b,h,w] or None)."""
+    dev = mask.device
+    ncls = int(class_num) - 1
+    fgs = [foreground_counts(_class_mask(mask, k + 1)).cpu().tolist() for k in range(ncls)]   # one sync per class
+    idxs = [torch.zeros([b, hn, vn, 2], dtype=torch.int32, device=dev) for _ in range(ncls)]
+    sels = [None] * ncls
+    for bi in range(b):
+        for k in range(ncls):
+            fg = fgs[k][bi]
+            if fg < min_num:
+                continue
+            tn = fg
+            if fg > max_num:
+                if sels[k] is None:
+                    sels[k] = torch.empty([b, h, w], dtype=torch.float32, device=dev)
+                sel = torch.zeros([h, w], dtype=torch.float32, device=dev).uniform_(0, 1)
+                sels[k][bi] = sel
+                p = max_num / torch.tensor(fg, device=dev).float()
+                tn = int(((mask[bi] == k + 1) & (sel < p)).sum().item())
+            idxs[k][bi] = torch.zeros([hn, vn, 2], dtype=torch.int32, device=dev).random_(0, max(tn, 1))
+    return idxs, sels
+
+
+def _per_class_v3(mask, vertex, class_num, hn, inlier_thresh, min_num, max_num, idxs, selection, rng):
+    """v3 on every class mask; yields (class index, keypoints, debug dict)."""
+    b, h, w, vn, _ = vertex.shape
+    ncls = int(class_num) - 1
+    if idxs is None and rng == "reference" and ncls > 0:
+        idxs, selection = _draw_reference_classes(mask, class_num, b, h, w, vn, hn, min_num, max_num)
+    for k in range(ncls):
+        kp, dbg = ransac_voting_layer_v3(_class_mask(mask, k + 1), vertex, hn, inlier_thresh, min_num=min_num,
+                                         max_num=max_num, idxs=None if idxs is None else idxs[k],
+                                         selection=None if selection is None else selection[k], rng=rng,
+                                         return_debug=True)
+        yield k, kp, dbg
+
+
 def ransac_voting_layer(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
                         min_num=5, max_num=30000, *, idxs=None, selection=None, rng="reference"):
     """Reference signature (ransac_voting_gpu.py:10-11), the first voting layer: for every class
     1..class_num-1 the pixels with mask == class vote and the WINNING HYPOTHESIS (no refit) is
     returned: [b, class_num-1, vn, 2].  idxs / selection, when injected, carry a leading class
-    axis: [class_num-1, b, hn, vn, 2] / [class_num-1, b, h, w]."""
+    axis: [class_num-1, b, hn, vn, 2] / [class_num-1, b, h, w].  With rng="reference" the torch RNG
+    calls are replayed in the reference's (image, class) order."""
     del confidence, max_iter
     b, h, w, vn, _ = vertex.shape
     outs = []
-    for k in range(int(class_num) - 1):
-        _, dbg = ransac_voting_layer_v3(_class_mask(mask, k + 1), vertex, round_hyp_num, inlier_thresh, min_num=min_num,
-                                        max_num=max_num, idxs=None if idxs is None else idxs[k],
-                                        selection=None if selection is None else selection[k], rng=rng,
-                                        return_debug=True)
+    for _, _, dbg in _per_class_v3(mask, vertex, class_num, int(round_hyp_num), inlier_thresh, min_num, max_num, idxs,
+                                   selection, rng):
         counts, hyp = dbg["counts"], dbg["hyp"]                   # [b,hn,vn], [b,hn,vn,2]
         win = torch.argmax(counts, 1)                              # first maximum (:68)
         win_cnt = torch.gather(counts, 1, win[:, None, :])[:, 0]   # [b,vn]
@@ -492,6 +532,118 @@ def ransac_voting_layer(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.
     if not outs:
         return torch.zeros([b, 0, vn, 2], dtype=torch.float32, device=vertex.device)
     return torch.stack(outs, 1)
+
+
+def ransac_voting_layer_v2(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                           min_num=5, max_num=30000, refine_iter_num=1, *, idxs=None, selection=None, rng="reference"):
+    """Reference signature (ransac_voting_gpu.py:99-100): per class, vote, then `refine_iter_num`
+    rounds of (inliers of the current point -> least-squares intersection of their lines): [b, class_num-1,
+    vn, 2].  The reference solves each refit with `torch.pinverse(A) @ b` (:198); for a full-rank A that is
+    the normal-equation solution v3's refit computes (in fp64 here).  A keypoint without inliers gives
+    zeros (:190-192); a rank-deficient inlier set (all lines parallel) gives NaN here, the minimum-norm
+    point there."""
+    del confidence, max_iter
+    b, h, w, vn, _ = vertex.shape
+    outs = []
+    for k, kp, dbg in _per_class_v3(mask, vertex, class_num, int(round_hyp_num), inlier_thresh, min_num, max_num, idxs,
+                                    selection, rng):
+        if int(refine_iter_num) < 1:                # no refinement at all: the winning hypothesis (:149-158)
+            counts, hyp = dbg["counts"], dbg["hyp"]
+            win = torch.argmax(counts, 1)
+            kp = torch.gather(hyp, 1, win[:, None, :, None].expand(b, 1, vn, 2))[:, 0]
+            kp = torch.where((torch.gather(counts, 1, win[:, None, :])[:, 0] > 0)[..., None], kp, torch.zeros_like(kp))
+        for _ in range(int(refine_iter_num) - 1):   # v3 already did the first refit
+            kp = refit_at_points(_class_mask(mask, k + 1), vertex, torch.nan_to_num(kp, nan=0.0), inlier_thresh,
+                                 min_num=min_num, max_num=max_num, selection=dbg["selection"])
+        outs.append(torch.nan_to_num(kp, nan=0.0) if int(refine_iter_num) >= 1 else kp)
+    if not outs:
+        return torch.zeros([b, 0, vn, 2], dtype=torch.float32, device=vertex.device)
+    return torch.stack(outs, 1)
+
+
+def refit_at_points(mask, vertex, points, inlier_thresh, min_num=5, max_num=30000, *, selection=None):
+    """One refinement round of ransac_voting_gpu.py:178-204 for a whole batch: the pixels (mask nonzero)
+    that are inliers of points [b,vn,2] re-estimate them by least squares.  Returns [b,vn,2]."""
+    _require_cuda(mask, "mask")
+    _require_cuda(vertex, "vertex")
+    b, h, w, vn, _ = vertex.shape
+    dev = mask.device
+    m, esz = _prep_mask(mask, _MASK_NONZERO_BYTE)
+    v, strides = _prep_vertex(vertex)
+    pts = points.to(device=dev, dtype=torch.float32).contiguous()
+    if tuple(pts.shape) != (b, vn, 2):
+        raise ValueError(f"points must be [b,vn,2], got {tuple(pts.shape)}")
+    with torch.cuda.device(dev):
+        if selection is not None:
+            selection = torch.as_tensor(selection, device=dev, dtype=torch.float32).contiguous()
+        out = torch.empty([b, vn, 2], dtype=torch.float32, device=dev)
+        ws, ws_bytes = _workspace(b, h, w, vn, 1, dev)
+        _native.check(_native.lib().pvnet_refit_at_points(
+            _ptr(m), esz, _ptr(v), strides, _ptr(selection), _ptr(pts), b, h, w, vn, float(inlier_thresh), int(min_num),
+            int(min(max_num, 2 ** 31 - 1)), _ptr(out), _ptr(ws), ws_bytes, _stream(dev)), "pvnet_refit_at_points")
+    return out
+
+
+def ransac_voting_vanish_point_layer(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                                     min_num=5, max_num=30000, refine_iter_num=1, *, class_num=2, idxs=None):
+    """Reference ransac_voting_gpu.py:408-501 (its body reads an undefined `class_num`, :415, so it cannot
+    run as written; it is a keyword here, default 2 = one foreground class).  Per class: homogeneous
+    hypotheses from pixel pairs (`generate_hypothesis_vanishing_point`), |cos| vote, the winner normalised,
+    then `refine_iter_num` rounds of (inliers -> smallest right singular vector of [-n | n.c], sign fixed by
+    the first inlier, :485-492).  Returns [b, class_num-1, vn, 3].  The two kernels are the native
+    stand-ins (bit-exact to the reference's); compaction, argmax and SVD are the reference's torch ops --
+    this layer is off the hot path (only commented-out code calls it, :1083).
+    idxs, when injected: [b, class_num-1, hn, vn, 2]."""
+    from . import ransac_voting as ext
+    del confidence, max_iter
+    _require_cuda(mask, "mask")
+    b, h, w, vn, _ = vertex.shape
+    hn = int(round_hyp_num)
+    dev = mask.device
+    out = torch.zeros([b, int(class_num) - 1, vn, 3], dtype=torch.float32, device=dev)
+    for bi in range(b):
+        for k in range(int(class_num) - 1):
+            cur_mask = mask[bi] == k + 1
+            fg = int(cur_mask.sum())
+            if fg < min_num:
+                continue
+            if fg > max_num:
+                sel = torch.zeros(cur_mask.shape, dtype=torch.float32, device=dev).uniform_(0, 1)
+                cur_mask = cur_mask & (sel < (max_num / torch.tensor(fg, device=dev).float()))
+            coords = torch.nonzero(cur_mask).float()[:, [1, 0]].contiguous()
+            direct = vertex[bi][cur_mask].reshape(-1, vn, 2).contiguous().float()
+            tn = coords.shape[0]
+            if idxs is not None:
+                cur_idxs = torch.as_tensor(idxs[bi][k], device=dev).to(torch.int32).contiguous()
+            else:
+                cur_idxs = torch.zeros([hn, vn, 2], dtype=torch.int32, device=dev).random_(0, tn)
+            hyp = ext.generate_hypothesis_vanishing_point(direct, coords, cur_idxs)                 # [hn,vn,3]
+            counts = ext.voting_for_hypothesis_vanishing_point(direct, coords, hyp, None, inlier_thresh,
+                                                               return_counts=True)                  # [hn,vn]
+            hyp = hyp / torch.norm(hyp, 2, 2, keepdim=True)                                         # :446
+            win = torch.argmax(counts, 0)
+            win_pts = hyp[win, torch.arange(vn, device=dev)]
+            pts = torch.where((counts.max(0).values > 0)[:, None], win_pts, torch.zeros_like(win_pts))
+            normal = torch.stack([direct[:, :, 1], -direct[:, :, 0]], 2)
+            for _ in range(int(refine_iter_num)):
+                inl = torch.zeros([1, vn, tn], dtype=torch.uint8, device=dev)
+                ext.voting_for_hypothesis_vanishing_point(direct, coords, pts[None].contiguous(), inl, inlier_thresh)
+                new = []
+                for vi in range(vn):
+                    sel_v = inl[0, vi].bool()
+                    if int(sel_v.sum()) == 0:
+                        new.append(pts[vi:vi + 1])
+                        continue
+                    cc, nn = coords[sel_v], normal[:, vi][sel_v]
+                    H = torch.cat([-nn, (nn * cc).sum(1, keepdim=True)], 1)                          # :485
+                    _, _, Vh = torch.linalg.svd(H, full_matrices=False)
+                    p = Vh[2:3]
+                    if float((p[0, 0] - p[0, 2] * cc[0, 0]) * (-nn[0, 1])) < 0:                      # :489-490
+                        p = -p
+                    new.append(p)
+                pts = torch.cat(new, 0)
+            out[bi, k] = pts
+    return out
 
 
 def ransac_voting_hypothesis(mask, vertex, round_hyp_num, inlier_thresh=0.999, min_num=5, max_num=30000, *,

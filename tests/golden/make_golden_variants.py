@@ -10,6 +10,7 @@ kernels by tests/test_gpu_reference_layer.py) on CPU tensors.  The stub also rec
 into the CUDA path.  Functions that still run under torch 2.11 on the CPU:
 
   ransac_voting_layer (v1, :10)            bool masks  -> runs
+  ransac_voting_layer_v2 (:99)             bool masks, pinverse refit -> runs (uint8 indexing still accepted)
   ransac_voting_hypothesis (:218)          bool masks  -> runs
   estimate_voting_distribution (:263)      bool masks  -> runs
   ransac_motion_voting (:960)              indexes with a uint8 mask -> runs only if torch still
@@ -87,6 +88,25 @@ def main():
     out["v1_idxs"] = np.stack(uniq)                       # [class, hn, K, 2]
     out["v1_out"] = r.numpy()
     print("v1", r.shape, r[0, :, 0].tolist())
+
+    # ---- v2: two classes, two refinement rounds (pinverse refit, :178-204)
+    mask, vertex, _ = make_inputs(15, n_fg=1000, classes=2)
+    torch.manual_seed(5)
+    del rec[:]
+    try:
+        r2 = ref.ransac_voting_layer_v2(torch.from_numpy(mask), torch.from_numpy(vertex), 3, 32, inlier_thresh=0.99,
+                                        refine_iter_num=2)
+        uniq = []
+        for a in rec:
+            if not uniq or not np.array_equal(uniq[-1], a):
+                uniq.append(a)
+        assert len(uniq) == 2, len(uniq)
+        out["v2_seed"] = np.array([15, 1000, 2])
+        out["v2_idxs"] = np.stack(uniq)
+        out["v2_out"] = r2.numpy()
+        print("v2", r2.shape, r2[0, :, 0].tolist())
+    except Exception as e:
+        print("ransac_voting_layer_v2 does not run under this torch:", type(e).__name__, str(e)[:120])
 
     # ---- ransac_voting_hypothesis
     mask, vertex, _ = make_inputs(12, n_fg=700)

@@ -12,6 +12,8 @@ REF = "/root/reference/lib/ransac_voting_gpu_layer/ransac_voting_gpu.py"
 
 EXPECTED = {
     "ransac_voting_layer": "mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5, max_num=30000",
+    "ransac_voting_layer_v2": "mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5, max_num=30000, refine_iter_num=1",
+    "ransac_voting_vanish_point_layer": "mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5, max_num=30000, refine_iter_num=1",
     "ransac_voting_hypothesis": "mask, vertex, round_hyp_num, inlier_thresh=0.999, min_num=5, max_num=30000",
     "estimate_voting_distribution": "mask, vertex, round_hyp_num=256, min_hyp_num=4096, topk=128, inlier_thresh=0.99, min_num=5, max_num=30000",
     "estimate_voting_distribution_with_mean": "mask, vertex, mean, round_hyp_num=256, min_hyp_num=4096, topk=128, inlier_thresh=0.99, min_num=5, max_num=30000, output_hyp=False",

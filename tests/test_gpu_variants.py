@@ -161,3 +161,60 @@ def test_vanishing_point_pair_bit_exact_vs_oracle_and_reference_kernels():
         inl = torch.zeros([96, 4, 3000], dtype=torch.uint8, device=DEV)
         ext.voting_for_hypothesis_vanishing_point(d, c, hyp, inl, 0.99)
         assert torch.equal(rinl, inl)
+
+
+def test_v2_against_reference_fixture(gold):
+    """ransac_voting_layer_v2 with two refinement rounds: output of the reference's own function (pinverse
+    refits in fp32) vs ours (normal equations in fp64)."""
+    from lib.ransac_voting_gpu_layer.ransac_voting_gpu import ransac_voting_layer_v2
+    seed, n, classes = (int(v) for v in gold["v2_seed"])
+    mask, vertex, _ = variant_inputs(seed, n, classes)
+    m, v = _dev(mask, vertex)
+    idxs = torch.from_numpy(gold["v2_idxs"])[:, None].to(DEV)           # [class, b=1, hn, K, 2]
+    out = ransac_voting_layer_v2(m, v, classes + 1, 32, inlier_thresh=0.99, refine_iter_num=2, idxs=idxs)
+    assert out.shape == (1, classes, 5, 2)
+    assert np.abs(out.cpu().numpy() - gold["v2_out"]).max() <= 2e-4
+    one = ransac_voting_layer_v2(m, v, classes + 1, 32, inlier_thresh=0.99, refine_iter_num=1, idxs=idxs)
+    assert np.abs((one - out).cpu().numpy()).max() < 1.0 and not torch.equal(one, out)
+
+
+def test_class_layers_replay_rng_in_image_class_order():
+    """v1/v2 with rng="reference", two images x two classes: the torch RNG calls happen in the reference's
+    `for bi: for k:` order (ransac_voting_gpu.py:23-26)."""
+    from lib.ransac_voting_gpu_layer.ransac_voting_gpu import ransac_voting_layer_v2
+    masks, verts = zip(*[variant_inputs(30 + i, 900, 2)[:2] for i in range(2)])
+    m, v = _dev(np.concatenate(masks), np.concatenate(verts))
+    torch.manual_seed(9)
+    got = ransac_voting_layer_v2(m, v, 3, 24, inlier_thresh=0.99)
+    torch.manual_seed(9)
+    idxs = torch.zeros([2, 2, 24, 5, 2], dtype=torch.int32, device=DEV)    # [class, b, ...]
+    for bi in range(2):
+        for k in range(2):
+            tn = int((m[bi] == k + 1).sum())
+            idxs[k, bi] = torch.zeros([24, 5, 2], dtype=torch.int32, device=DEV).random_(0, tn)
+    want = ransac_voting_layer_v2(m, v, 3, 24, inlier_thresh=0.99, idxs=idxs)
+    assert torch.equal(got, want)
+
+
+def test_vanish_point_layer_recovers_a_planted_vanishing_point():
+    """The reference layer cannot run as written (undefined `class_num`, :415) and ships no expected
+    values: pin behaviour by a known answer -- every pixel's direction points at one finite point per
+    keypoint, so the homogeneous result is proportional to (x, y, 1) of that point (the reference's own
+    disabled check, :1088-1097)."""
+    from lib.ransac_voting_gpu_layer.ransac_voting_gpu import ransac_voting_vanish_point_layer
+    H, W, K = 64, 80, 3
+    targets = np.array([[100.0, 20.0], [-30.0, 40.0], [45.0, 150.0]])
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    mask = np.zeros((1, H, W), np.int64)
+    mask[0, 16:48, 20:60] = 1
+    vertex = np.zeros((1, H, W, K, 2), np.float32)
+    for k in range(K):
+        d = np.stack([targets[k, 0] - xx, targets[k, 1] - yy], -1)
+        vertex[0, :, :, k] = (d / np.linalg.norm(d, axis=-1, keepdims=True)) * mask[0, :, :, None]
+    m, v = _dev(mask, vertex)
+    torch.manual_seed(0)
+    out = ransac_voting_vanish_point_layer(m, v, 64, inlier_thresh=0.999)
+    assert out.shape == (1, 1, K, 3)
+    o = out[0, 0].cpu().numpy().astype(np.float64)
+    assert np.abs(np.linalg.norm(o, axis=1) - 1).max() < 1e-5
+    assert np.abs(o[:, :2] / o[:, 2:3] - targets).max() < 5e-2
