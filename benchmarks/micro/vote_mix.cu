@@ -1,0 +1,172 @@
+// vote_mix.cu -- microbenchmark of k_vote2's inner loop in isolation: which instruction mix per inlier
+// test does the SM sustain?  One CTA per SM-slot, no global traffic inside the timed loop: every lane keeps
+// HPL hypotheses in registers and sweeps a 64-pixel record tile from shared memory over and over.
+// Variants (template V):
+//   0  4 FFMA + FADD + FSETP(count) + IADD + FSETP(band)            (round 2, first form: ALU-heavy)
+//   1  4 FFMA + FADD + FFMA.SAT + FADD + FSETP(band)                 (scalar FMA, count on the FMA pipe)
+//   2  2 FFMA2 + FADD + FFMA.SAT + FADD + FSETP(band)                (shipped form)
+//   3  2 FFMA2 + FADD + FFMA.SAT + FADD                              (no band check: what the check costs)
+//   4  2 FFMA2 + FADD + FSETP(count) + IADD + FSETP(band)            (packed FMAs, ALU count)
+//   5  2 FFMA2 only                                                  (raw packed-FMA rate)
+//   6  4 FFMA only                                                   (raw scalar-FMA rate)
+// Output: cycles per test-warp (32 tests) per SM sub-partition, for 2/3/4/6/8 warps per sub-partition.
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o gpurun_out/vote_mix benchmarks/micro/vote_mix.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float fma_sat(float a, float b, float c) { float r; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ void count_if_gt(int &cnt, float a, float b)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "f"(a), "f"(b));
+}
+
+constexpr int HPL = 8, PIX = 64;
+
+template <int V>
+__global__ void __launch_bounds__(256) k_mix(int reps, float seed, float *out, long long *cycles)
+{
+    __shared__ float4 rec[3 * PIX];
+    for (int i = threadIdx.x; i < 3 * PIX; i += blockDim.x)
+        rec[i] = make_float4(0.01f * i + seed, 0.02f * i - seed, 0.5f - 0.003f * i, 0.25f + 0.001f * i);
+    __syncthreads();
+    float hx[HPL], hy[HPL], bd[HPL], nb2[HPL], cntf[HPL];
+    int cnt[HPL];
+    f32x2 hx2[HPL / 2], hy2[HPL / 2];
+    for (int j = 0; j < HPL; ++j) {
+        hx[j] = seed + 0.1f * j + 0.01f * threadIdx.x;
+        hy[j] = seed - 0.2f * j + 0.02f * threadIdx.x;
+        bd[j] = 1e-5f * (1 + j);
+        nb2[j] = -bd[j] * 18446744073709551616.f;
+        cntf[j] = 0.f;
+        cnt[j] = 0;
+    }
+    for (int j = 0; j < HPL / 2; ++j) {
+        hx2[j] = pk2(hx[2 * j], hx[2 * j + 1]);
+        hy2[j] = pk2(hy[2 * j], hy[2 * j + 1]);
+    }
+    bool unc = false;
+    f32x2 acc2[HPL / 2];
+    float accs[HPL];
+    for (int j = 0; j < HPL / 2; ++j) acc2[j] = pk2(0.f, 0.f);
+    for (int j = 0; j < HPL; ++j) accs[j] = 0.f;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll 4
+        for (int p = 0; p < PIX; ++p) {
+            const float4 a = rec[3 * p], b = rec[3 * p + 1], c = rec[3 * p + 2];
+            if (V == 0 || V == 1 || V == 6) {
+#pragma unroll
+                for (int j = 0; j < HPL; ++j) {
+                    const float num = fmaf(hx[j], a.x, fmaf(hy[j], a.z, b.x));
+                    const float per = fmaf(hx[j], b.z, fmaf(hy[j], c.x, c.z));
+                    if (V == 6) {
+                        accs[j] += 0.f;
+                        hx[j] = num;
+                        hy[j] = per;
+                        continue;
+                    }
+                    const float m = num - fabsf(per);
+                    if (V == 0) count_if_gt(cnt[j], m, bd[j]);
+                    else cntf[j] += fma_sat(m, 18446744073709551616.f, nb2[j]);
+                    unc |= !(fabsf(m) > bd[j]);
+                }
+            } else {
+                const f32x2 SX = pk2(a.x, a.y), SY = pk2(a.z, a.w), NS = pk2(b.x, b.y), CX = pk2(b.z, b.w), CY = pk2(c.x, c.y),
+                            NC = pk2(c.z, c.w);
+#pragma unroll
+                for (int j = 0; j < HPL / 2; ++j) {
+                    const f32x2 num2 = fma2(hx2[j], SX, fma2(hy2[j], SY, NS));
+                    const f32x2 per2 = fma2(hx2[j], CX, fma2(hy2[j], CY, NC));
+                    if (V == 5) {
+                        hx2[j] = num2;
+                        hy2[j] = per2;
+                        continue;
+                    }
+                    float n0, n1, q0, q1;
+                    upk2(num2, n0, n1);
+                    upk2(per2, q0, q1);
+                    const float m0 = n0 - fabsf(q0), m1 = n1 - fabsf(q1);
+                    if (V == 4) {
+                        count_if_gt(cnt[2 * j], m0, bd[2 * j]);
+                        count_if_gt(cnt[2 * j + 1], m1, bd[2 * j + 1]);
+                    } else {
+                        cntf[2 * j] += fma_sat(m0, 18446744073709551616.f, nb2[2 * j]);
+                        cntf[2 * j + 1] += fma_sat(m1, 18446744073709551616.f, nb2[2 * j + 1]);
+                    }
+                    if (V != 3) {
+                        unc |= !(fabsf(m0) > bd[2 * j]);
+                        unc |= !(fabsf(m1) > bd[2 * j + 1]);
+                    }
+                }
+            }
+        }
+    }
+    const long long t1 = clock64();
+    float s = unc ? 1.f : 0.f;
+    for (int j = 0; j < HPL; ++j) s += cntf[j] + (float)cnt[j] + hx[j] + hy[j] + accs[j];
+    for (int j = 0; j < HPL / 2; ++j) {
+        float x, y;
+        upk2(hx2[j], x, y);
+        s += x + y;
+        upk2(hy2[j], x, y);
+        s += x + y;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int V>
+void run(const char *name, int sms)
+{
+    float *out;
+    long long *cyc;
+    cudaMalloc(&out, sizeof(float) * sms * 4 * 256 * 2);
+    cudaMalloc(&cyc, sizeof(long long) * sms * 8);
+    const int reps = 400;
+    printf("%-58s", name);
+    for (int ctas = 1; ctas <= 4; ++ctas) {                      // 256-thread CTAs per SM: 2, 4, 6, 8 warps per sub-partition
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mix<V>, 256, 0);
+        if (ctas > occ) { printf("  %6s", "-"); continue; }
+        k_mix<V><<<sms * ctas, 256>>>(reps, 0.37f, out, cyc);
+        cudaDeviceSynchronize();
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        k_mix<V><<<sms * ctas, 256>>>(reps, 0.37f, out, cyc);
+        cudaEventRecord(e1);
+        cudaDeviceSynchronize();
+        long long h[8 * 200];
+        cudaMemcpy(h, cyc, sizeof(long long) * sms * ctas, cudaMemcpyDeviceToHost);
+        double mean = 0;
+        for (int i = 0; i < sms * ctas; ++i) mean += (double)h[i];
+        mean /= sms * ctas;
+        // test-warps per sub-partition in that time: ctas * 8 warps / 4 sub-partitions * reps * PIX * HPL
+        const double tw = (double)ctas * 2 * reps * PIX * HPL;
+        printf("  %6.2f", mean / tw);
+    }
+    printf("\n");
+    cudaFree(out);
+    cudaFree(cyc);
+}
+
+int main()
+{
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    printf("cycles per test-warp (32 inlier tests) per SM sub-partition; columns: 2, 4, 6, 8 resident warps per sub-partition\n");
+    run<0>("0: 4 FFMA + FADD + FSETP + IADD + FSETP(band)", sms);
+    run<1>("1: 4 FFMA + FADD + FFMA.SAT + FADD + FSETP(band)", sms);
+    run<2>("2: 2 FFMA2 + FADD + FFMA.SAT + FADD + FSETP(band)  [shipped]", sms);
+    run<3>("3: 2 FFMA2 + FADD + FFMA.SAT + FADD  (no band check)", sms);
+    run<4>("4: 2 FFMA2 + FADD + FSETP + IADD + FSETP(band)", sms);
+    run<5>("5: 2 FFMA2 only", sms);
+    run<6>("6: 4 FFMA only", sms);
+    return 0;
+}

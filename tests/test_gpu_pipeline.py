@@ -192,7 +192,7 @@ def test_device_rng_reproducible_fresh_and_uniform():
     assert int(d2["tn"][1]) != int(tn[1])
     # results agree with the planted keypoints (the sampler feeds a working RANSAC)
     kps = syn.planted_keypoints(9)
-    assert np.abs(kp1.cpu().numpy() - kps[None]).max() < 5.0
+    assert np.abs(kp1.cpu().numpy() - kps[None])[:, 0::2].max() < 3.0      # the keypoints near the object (R = 90 px)
     assert torch.isfinite(cov1).all()
 
 
