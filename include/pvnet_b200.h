@@ -326,6 +326,12 @@ PVNET_API int pvnet_backbone_create(int ver_dim, int seg_dim, int fcdim, int s8d
 PVNET_API void pvnet_backbone_destroy(pvnet_backbone_t *m);
 PVNET_API int pvnet_backbone_num_convs(void);
 PVNET_API int pvnet_backbone_set_conv(pvnet_backbone_t *m, int slot, const float *w_packed, const float *bias);
+/* Output layout of the following forward calls on this handle: 0 (default) = out [b,C,h,w], the
+ * reference's NCHW tensor whose channel slices are seg_pred / ver_pred (model_repository.py:77-78);
+ * 1 = pixel-major out [b,h,w,C]: the same values as one contiguous record per pixel, which is the
+ * vertex layout [b,h,w,K,2] the voting layer's gather reads without sector waste (the contiguous
+ * form of the permuted view of tools/demo.py:48-50). */
+PVNET_API int pvnet_backbone_set_output_layout(pvnet_backbone_t *m, int pixel_major);
 PVNET_API int pvnet_backbone_workspace_bytes(const pvnet_backbone_t *m, int b, int h, int w, size_t *bytes);
 PVNET_API int pvnet_backbone_forward(pvnet_backbone_t *m, const float *image_nchw, int b, int h, int w,
                                      float *out_nchw, void *mask_out, int mask_elem_size,

@@ -40,6 +40,7 @@ struct pvnet_backbone {
     bool head_fused = false;             // convraw.3 + argmax run inside convraw.0's epilogue
     bool stem_tc = false;                // stem runs as a 4x4 conv on the space-to-depth image
     bool raw_split = false;              // convraw.0 reads the upsampled features and the image slice from two dense buffers
+    int out_nhwc = 0;                    // output layout: 0 = [b,C,H,W] (reference), 1 = pixel-major [b,H,W,C]
 };
 
 // where the image comes from: float32 NCHW (already normalised) or raw uint8 HWC + mean/std
@@ -236,6 +237,13 @@ void pvnet_backbone_destroy(pvnet_backbone_t *m) { delete m; }
 
 int pvnet_backbone_num_convs(void) { return CV_COUNT; }
 
+int pvnet_backbone_set_output_layout(pvnet_backbone_t *m, int pixel_major)
+{
+    PV_CHECK_ARG(m, "null handle");
+    m->out_nhwc = pixel_major ? 1 : 0;
+    return PVNET_OK;
+}
+
 int pvnet_backbone_set_conv(pvnet_backbone_t *m, int slot, const float *w_packed, const float *bias)
 {
     PV_CHECK_ARG(m, "null handle");
@@ -338,7 +346,7 @@ int run_stage(pvnet_backbone *m, const Stage &st, const Buffers &B, const ImageS
     case ST_CONV: {
         unsigned char *pl = m->plans.data() + plan_stride() * st.slot;
         if (!m->use_col[st.slot]) return conv_launch_at(pl, s);
-        if (st.slot == CV_CONVRAW0 && m->head_fused) conv_col_set_head_ptrs(pl, out_nchw, mask_out, mask_elem_size);
+        if (st.slot == CV_CONVRAW0 && m->head_fused) conv_col_set_head_ptrs(pl, out_nchw, mask_out, mask_elem_size, m->out_nhwc);
         return conv_col_launch_at(pl, s);
     }
     case ST_UP8: return launch_upsample2x(B.U8, B.C4, b, h8, w8, m->s8, c4s, 0, s);
@@ -347,7 +355,7 @@ int run_stage(pvnet_backbone *m, const Stage &st, const Buffers &B, const ImageS
     case ST_HEAD:
         if (m->head_fused) return PVNET_OK;    // already written by convraw.0's epilogue
         return launch_head(B.R0, m->w[CV_HEAD], m->bias[CV_HEAD], out_nchw, mask_out, mask_elem_size, m->seg_dim,
-                           m->seg_dim + m->ver_dim, b, h, w, s);
+                           m->seg_dim + m->ver_dim, b, h, w, m->out_nhwc, s);
     }
     return PVNET_E_INVALID;
 }

@@ -366,7 +366,7 @@ constexpr int HEAD_MAX_COUT = 64;
 __global__ void __launch_bounds__(256)
     k_head(const float *__restrict__ in, const float *__restrict__ w /*[Cout][32]*/, const float *__restrict__ bias,
            float *__restrict__ out, void *__restrict__ mask, int mask_esz, int seg_dim, int Cout, int npix,
-           long long total)
+           long long total, int nhwc)
 {
     __shared__ float sw[HEAD_MAX_COUT * 32];
     __shared__ float sb[HEAD_MAX_COUT];
@@ -389,13 +389,14 @@ __global__ void __launch_bounds__(256)
     }
     float best = -INFINITY;
     int best_c = 0;
-    float *o = out + n * Cout * (long long)npix + p;
+    float *o = nhwc ? out + i * Cout : out + n * Cout * (long long)npix + p;
+    const long long ostride = nhwc ? 1 : npix;
     for (int co = 0; co < Cout; ++co) {
         float acc = sb[co];
         const float *wr = sw + co * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc = fmaf(v[j], wr[j], acc);
-        o[(long long)co * npix] = acc;
+        o[(long long)co * ostride] = acc;
         if (co < seg_dim && acc > best) {
             best = acc;
             best_c = co;
@@ -410,13 +411,13 @@ __global__ void __launch_bounds__(256)
 }
 
 int launch_head(const float *in, const float *w, const float *bias, float *out, void *mask, int mask_esz, int seg_dim,
-                int Cout, int b, int H, int W, cudaStream_t s)
+                int Cout, int b, int H, int W, int nhwc, cudaStream_t s)
 {
     PV_CHECK_ARG(Cout >= 1 && Cout <= HEAD_MAX_COUT, "head: %d output channels unsupported (max %d)", Cout,
                  HEAD_MAX_COUT);
     const long long total = (long long)b * H * W;
     k_head<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, w, bias, out, mask, mask_esz, seg_dim, Cout, H * W,
-                                                          total);
+                                                          total, nhwc);
     PV_LAUNCHED("k_head");
     return PVNET_OK;
 }

@@ -48,6 +48,7 @@ struct ColGeom {
     int act, round_out;
     // fused head
     int head_cout, head_seg, mask_esz;
+    int head_nhwc;          // fused head writes pixel-major [b,H,W,cout] instead of the reference's NCHW
 };
 
 
@@ -338,17 +339,40 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                     ptx::tmem_ld_wait();
                     if (valid) {
                         const size_t npix = (size_t)g.Ho * g.Wo;
-                        float *o = head_out + (size_t)img * g.head_cout * npix + (size_t)y * g.Wo + x;
                         float best = -INFINITY;
                         int best_c = 0;
+                        if (g.head_nhwc) {
+                            // pixel-major record [cout] per pixel (what the voting layer's gather reads as one
+                            // contiguous piece): 16-byte stores, scalar tail when cout is not a multiple of 4
+                            float *o = head_out + pix * (size_t)g.head_cout;
+                            float val[32];
 #pragma unroll
-                        for (int co = 0; co < 32; ++co) {
-                            if (co < g.head_cout) {
-                                const float val = __uint_as_float(d2[co]) + s_head[co];
-                                o[(size_t)co * npix] = val;
-                                if (co < g.head_seg && val > best) {
-                                    best = val;
+                            for (int co = 0; co < 32; ++co) {
+                                val[co] = __uint_as_float(d2[co]) + (co < g.head_cout ? s_head[co] : 0.f);
+                                if (co < g.head_seg && val[co] > best) {
+                                    best = val[co];
                                     best_c = co;
+                                }
+                            }
+#pragma unroll
+                            for (int c4 = 0; c4 < 32; c4 += 4) {
+                                if (c4 + 4 <= g.head_cout)
+                                    *reinterpret_cast<float4 *>(o + c4) = make_float4(val[c4], val[c4 + 1], val[c4 + 2], val[c4 + 3]);
+                                else
+                                    for (int co = c4; co < c4 + 4; ++co)
+                                        if (co < g.head_cout) o[co] = val[co];
+                            }
+                        } else {
+                            float *o = head_out + (size_t)img * g.head_cout * npix + (size_t)y * g.Wo + x;
+#pragma unroll
+                            for (int co = 0; co < 32; ++co) {
+                                if (co < g.head_cout) {
+                                    const float val = __uint_as_float(d2[co]) + s_head[co];
+                                    o[(size_t)co * npix] = val;
+                                    if (co < g.head_seg && val > best) {
+                                        best = val;
+                                        best_c = co;
+                                    }
                                 }
                             }
                         }
@@ -466,6 +490,7 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     g.head_cout = head ? head->cout : 0;
     g.head_seg = head ? head->seg_dim : 0;
     g.mask_esz = head ? head->mask_esz : 0;
+    g.head_nhwc = 0;
     // Resident weights whenever at least 2 A stages (one channel chunk with all its taps each) still
     // fit next to them; otherwise the KH*KW weight tiles of a chunk travel with its A box.  Two CTAs
     // per SM when the footprint allows.
@@ -556,9 +581,10 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     return PVNET_OK;
 }
 
-void conv_col_set_head_ptrs(void *storage, float *out_nchw, void *mask, int mask_esz)
+void conv_col_set_head_ptrs(void *storage, float *out_nchw, void *mask, int mask_esz, int nhwc)
 {
     ColPlan *p = static_cast<ColPlan *>(storage);
+    p->g.head_nhwc = nhwc;
     p->hd.out_nchw = out_nchw;
     p->hd.mask = mask;
     p->hd.mask_esz = mask_esz;

@@ -48,7 +48,7 @@ bool conv_col_eligible(const ConvDesc &d);
 size_t conv_col_plan_size();
 int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *plan_storage);
 int conv_col_launch_at(const void *plan_storage, cudaStream_t s);
-void conv_col_set_head_ptrs(void *plan_storage, float *out_nchw, void *mask, int mask_esz);
+void conv_col_set_head_ptrs(void *plan_storage, float *out, void *mask, int mask_esz, int nhwc);
 
 // A plan = encoded tensor maps + launch geometry; opaque bytes so callers can cache it.
 size_t conv_plan_size();
@@ -64,7 +64,7 @@ int launch_maxpool(const float *in, float *out, int b, int H, int W, int C, int 
 int launch_upsample2x(const float *in, float *out, int b, int h, int w, int C, int out_cs, int out_co,
                       cudaStream_t s);
 int launch_head(const float *in, const float *w, const float *bias, float *out, void *mask, int mask_esz,
-                int seg_dim, int Cout, int b, int H, int W, cudaStream_t s);
+                int seg_dim, int Cout, int b, int H, int W, int nhwc, cudaStream_t s);
 
 #ifdef __CUDACC__
 // Coalesced residual fetch shared by the conv epilogues (128-pixel tiles TW pixels wide, one pixel

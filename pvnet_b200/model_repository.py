@@ -216,9 +216,11 @@ class Resnet18_8s(nn.Module):
                           "pvnet_backbone_set_conv(stem s2d)")
         return _NativeEntry(handle, keep, key)
 
-    def forward_native(self, x, with_mask=False, mask_dtype=torch.int64, mean=None, std=None):
+    def forward_native(self, x, with_mask=False, mask_dtype=torch.int64, mean=None, std=None, pixel_major=False):
         """x [b,3,H,W] float32 CUDA (normalised) -- or uint8 [b,H,W,3] raw images with `mean`/`std`
-        (normalised on the device) -> out [b,seg+ver,H,W] (and the fused argmax mask)."""
+        (normalised on the device) -> out [b,seg+ver,H,W] (and the fused argmax mask).
+        pixel_major=True returns the same values as out [b,H,W,seg+ver] (one contiguous record per pixel:
+        `out[..., seg:].view(b,H,W,K,2)` is the contiguous vertex tensor the voting layer likes best)."""
         if not x.is_cuda:
             raise RuntimeError("pvnet_b200: the native backbone needs a CUDA tensor (there is no CPU path)")
         raw_u8 = x.dtype == torch.uint8
@@ -242,7 +244,10 @@ class Resnet18_8s(nn.Module):
             _native.check(L.pvnet_backbone_workspace_bytes(handle, b, h, w, ctypes.byref(n)),
                           "pvnet_backbone_workspace_bytes")
             ws = self._workspace(n.value, dev)
-            out = torch.empty([b, self.seg_dim + self.ver_dim, h, w], dtype=torch.float32, device=dev)
+            ctot = self.seg_dim + self.ver_dim
+            out = torch.empty([b, h, w, ctot] if pixel_major else [b, ctot, h, w], dtype=torch.float32, device=dev)
+            _native.check(L.pvnet_backbone_set_output_layout(handle, 1 if pixel_major else 0),
+                          "pvnet_backbone_set_output_layout")
             mask = torch.empty([b, h, w], dtype=mask_dtype, device=dev) if with_mask else None
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             mptr, msz = (None, 0) if mask is None else (mask.data_ptr(), mask.element_size())

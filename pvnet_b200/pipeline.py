@@ -10,6 +10,10 @@ Per batch the device work is: `pvnet_backbone_forward` (fused argmax -> uint8 ma
 `pvnet_ransac_voting_pipeline` call (v3, plus estimate_voting_distribution_with_mean when
 `with_covariance`), sampling on the device (rng="device": no torch RNG launches).
 
+With `points_3d` + `camera_matrix` the uncertainty-driven PnP of `Evaluator.evaluate_uncertainty`
+(lib/utils/evaluation_utils.py:165-201) runs on the device as well (`pvnet_uncertainty_pnp`), so POSES
+[b,3,4] are what leaves the GPU (and what an 8-GPU job gathers).
+
 Inputs may be float32 [b,3,H,W] (already normalised, what `ToTensor` + `Normalize` produce,
 tools/demo.py:89-95) or uint8 [b,H,W,3] raw images: the latter are normalised on the device inside
 the packing kernel (4x fewer host->device bytes).
@@ -18,6 +22,7 @@ from __future__ import annotations
 
 import torch
 
+from . import extend_utils as eu
 from . import ransac_voting_gpu as rv
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)      # tools/demo.py:91-94, lib/datasets/linemod_dataset.py:191-195
@@ -26,7 +31,8 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 
 class PoseKeypointPipeline:
     def __init__(self, net, round_hyp_num=256, inlier_thresh=0.99, rng="device", with_covariance=False,
-                 cov_round_hyp_num=256, cov_min_hyp_num=4096, max_num=30000, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+                 cov_round_hyp_num=256, cov_min_hyp_num=4096, max_num=30000, mean=IMAGENET_MEAN, std=IMAGENET_STD,
+                 points_3d=None, camera_matrix=None):
         self.net = net
         self.hn = round_hyp_num
         self.thresh = inlier_thresh
@@ -36,6 +42,10 @@ class PoseKeypointPipeline:
         self.cov_min = cov_min_hyp_num
         self.max_num = max_num
         self.mean, self.std = tuple(mean), tuple(std)
+        self.with_pose = points_3d is not None and camera_matrix is not None
+        if self.with_pose and not with_covariance:
+            raise ValueError("poses need the covariances: with_covariance=True")
+        self.points_3d, self.camera_matrix = points_3d, camera_matrix
         self._bufs = None
         self._copy_stream = None
 
@@ -52,27 +62,35 @@ class PoseKeypointPipeline:
 
     def step(self, x):
         """x on the device: float32 [b,3,H,W] or uint8 [b,H,W,3] -> keypoints [b,K,2]
-        (and covariances [b,K,2,2])."""
+        (and covariances [b,K,2,2]) (and poses [b,3,4] float64)."""
+        # pixel-major head output: the vertex field is the contiguous [b,h,w,K,2] form of the permuted view of
+        # tools/demo.py:48-50 (same values; the voting layer's gather then reads whole records, not sectors)
         if x.dtype == torch.uint8:
-            out, mask = self.net.forward_native(x, with_mask=True, mask_dtype=torch.uint8, mean=self.mean, std=self.std)
+            out, mask = self.net.forward_native(x, with_mask=True, mask_dtype=torch.uint8, mean=self.mean, std=self.std,
+                                                pixel_major=True)
         else:
-            out, mask = self.net.forward_native(x, with_mask=True, mask_dtype=torch.uint8)
-        b, c, h, w = out.shape
+            out, mask = self.net.forward_native(x, with_mask=True, mask_dtype=torch.uint8, pixel_major=True)
+        b, h, w, c = out.shape
         k = (c - self.net.seg_dim) // 2
-        vertex = out[:, self.net.seg_dim:].permute(0, 2, 3, 1).view(b, h, w, k, 2)      # tools/demo.py:48-50
+        vertex = out[..., self.net.seg_dim:].unflatten(3, (k, 2))
         # a 2-class argmax mask is binary: v3's `nonzero` and with_mean's `== 1` readings coincide
         if self.net.seg_dim == 2 or not self.with_cov:
-            return rv.ransac_voting_pipeline(mask, vertex, self.hn, self.thresh, self.with_cov, self.cov_hn, self.cov_min,
-                                             self.thresh, max_num=self.max_num, rng=self.rng)
-        kp = rv.ransac_voting_layer_v3(mask, vertex, self.hn, inlier_thresh=self.thresh, max_num=self.max_num,
-                                       rng="batched")
-        _, cov = rv.estimate_voting_distribution_with_mean(mask, vertex, kp, round_hyp_num=self.cov_hn,
-                                                           min_hyp_num=self.cov_min, inlier_thresh=self.thresh,
-                                                           max_num=self.max_num, rng="batched")
-        return kp, cov
+            res = rv.ransac_voting_pipeline(mask, vertex, self.hn, self.thresh, self.with_cov, self.cov_hn, self.cov_min,
+                                            self.thresh, max_num=self.max_num, rng=self.rng)
+        else:
+            kp = rv.ransac_voting_layer_v3(mask, vertex, self.hn, inlier_thresh=self.thresh, max_num=self.max_num,
+                                           rng="batched")
+            _, cov = rv.estimate_voting_distribution_with_mean(mask, vertex, kp, round_hyp_num=self.cov_hn,
+                                                               min_hyp_num=self.cov_min, inlier_thresh=self.thresh,
+                                                               max_num=self.max_num, rng="batched")
+            res = (kp, cov)
+        if self.with_pose:
+            pose = eu.uncertainty_pnp_batched(res[0], self.points_3d, self.camera_matrix, cov=res[1])
+            return res[0], res[1], pose
+        return res
 
     @torch.no_grad()
-    def run(self, host_batches, out_host=None, cov_host=None, on_result=None):
+    def run(self, host_batches, out_host=None, cov_host=None, on_result=None, pose_host=None):
         """host_batches: sequence of pinned [b,3,H,W] float32 (or [b,H,W,3] uint8) tensors.  Results are
         copied device->host into out_host[i] (and cov_host[i]) -- pinned tensors -- when given; the call
         returns after the last of those copies has completed.  Returns the last device result."""
@@ -104,9 +122,11 @@ class PoseKeypointPipeline:
                 out_host[i].copy_(kp, non_blocking=True)
             if cov_host is not None and isinstance(result, tuple):
                 cov_host[i].copy_(result[1], non_blocking=True)
+            if pose_host is not None and isinstance(result, tuple) and len(result) > 2:
+                pose_host[i].copy_(result[2], non_blocking=True)
             if on_result is not None:
                 on_result(i, result)
-        if out_host is not None or cov_host is not None:
+        if out_host is not None or cov_host is not None or pose_host is not None:
             self._done.record(main)
             self._done.synchronize()
         return result

@@ -161,3 +161,31 @@ def test_pose_pipeline_run_from_host_buffers():
     pipe.run(hf, out_host=kp2)
     for i in range(3):
         assert torch.equal(kp2[i], got_kp[i])
+
+
+def test_pipeline_with_pose_and_pixel_major_equals_separate_calls():
+    """PoseKeypointPipeline(points_3d, camera_matrix): keypoints / covariances / poses equal the ones obtained by
+    calling the reference-shaped API step by step (NCHW output + permuted view, then v3 + with_mean with the same
+    samples, then uncertainty_pnp) -- the pixel-major head output and the fused voting call change layouts, not values."""
+    from pvnet_b200 import extend_utils as eu
+    net = _net()
+    rng = np.random.default_rng(4)
+    pts3d = rng.uniform(-0.1, 0.1, (9, 3)).astype(np.float32)
+    K = np.array([[572.4114, 0., 325.2611], [0., 573.57043, 242.04899], [0., 0., 1.]])
+    pipe = PoseKeypointPipeline(net, round_hyp_num=64, with_covariance=True, cov_round_hyp_num=64, cov_min_hyp_num=128,
+                                points_3d=pts3d, camera_matrix=K)
+    x = torch.from_numpy(syn.backbone_input(2, 21, 96, 128)).to(DEV)
+    with torch.no_grad():
+        torch.manual_seed(3)
+        rv.reset_device_rng(DEV)
+        kp, cov, pose = pipe.step(x)
+        out, mask = net.forward_native(x, with_mask=True)                       # NCHW, int64 mask (reference shapes)
+        vertex = out[:, 2:].permute(0, 2, 3, 1).view(2, 96, 128, 9, 2)
+        rv.reset_device_rng(DEV)
+        kp2, cov2 = rv.ransac_voting_pipeline(mask, vertex, 64, 0.99, True, 64, 128, 0.99, rng="device")
+        pose2 = eu.uncertainty_pnp_batched(kp2, pts3d, K, cov=cov2)
+        pm = net.forward_native(x, pixel_major=True)
+    assert torch.equal(pm.permute(0, 3, 1, 2), out)
+    assert torch.equal(kp, kp2) and torch.equal(cov, cov2)
+    assert pose.shape == (2, 3, 4) and pose.dtype == torch.float64
+    assert torch.equal(torch.nan_to_num(pose), torch.nan_to_num(pose2))
