@@ -8,9 +8,9 @@
 //                                                      Ceres LM over (angle-axis, t) of sum_i |W_i (proj(R X_i + t) - x_i)|^2
 //
 // Here: one WARP per image, everything in fp64.  Lane i owns keypoint i (K <= 32): its weight
-// matrix, residual and Jacobian rows; the 6x6 normal equations are butterfly-reduced over the warp
-// and solved redundantly by every lane (Cholesky), so the loop has no divergence and no shared
-// memory.  Rotation is kept as a matrix and updated on the manifold (R <- exp(dw) R), which has the
+// matrix, residual and Jacobian rows; the 6x6 normal equations are summed over the warp through a
+// 7 KB slice of shared memory and solved redundantly by every lane (Cholesky, fully unrolled in
+// registers), so the loop has no divergence.  Rotation is kept as a matrix and updated on the manifold (R <- exp(dw) R), which has the
 // same minimiser as the reference's angle-axis parametrisation; damping follows Ceres'
 // Levenberg-Marquardt strategy (diagonal scaling, radius /= max(1/3, 1 - (2 rho - 1)^3) on success,
 // shrink by 2, 4, 8.. on failure) but iterates to |step| < 1e-12 instead of Ceres'
@@ -142,9 +142,12 @@ __device__ void so3_exp(double wx, double wy, double wz, double (&E)[9])
 __device__ bool chol6(const double (&A)[36], const double (&rhs)[6], double (&x)[6])
 {
     double L[36];
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
+#pragma unroll
         for (int j = 0; j <= i; ++j) {
             double s = A[i * 6 + j];
+#pragma unroll
             for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
             if (i == j) {
                 if (!(s > 0.0)) return false;
@@ -155,13 +158,17 @@ __device__ bool chol6(const double (&A)[36], const double (&rhs)[6], double (&x)
         }
     }
     double y[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
         double s = rhs[i];
+#pragma unroll
         for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k];
         y[i] = s / L[i * 6 + i];
     }
+#pragma unroll
     for (int i = 5; i >= 0; --i) {
         double s = y[i];
+#pragma unroll
         for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * x[k];
         x[i] = s / L[i * 6 + i];
     }
@@ -220,15 +227,37 @@ __device__ __forceinline__ void cov_to_weight(double c00, double c01, double c10
     wyy = r00 / rdet;
 }
 
+// Sum 28 per-lane doubles (21 upper-triangle entries of J^T J, 6 of J^T r, the cost) over the warp through
+// this warp's slice of shared memory: lanes write rows, the first 28 lanes add one column each, everyone
+// reads the totals back.  (28 butterfly reductions of doubles cost ~10x more issue slots.)
+constexpr int PNP_NRED = 28;
+__device__ __forceinline__ void warp_reduce28(double (&v)[PNP_NRED], double *sm /* [33][PNP_NRED] */, int lane)
+{
+#pragma unroll
+    for (int i = 0; i < PNP_NRED; ++i) sm[lane * PNP_NRED + i] = v[i];
+    __syncwarp();
+    if (lane < PNP_NRED) {
+        double s = 0.0;
+        for (int r = 0; r < 32; ++r) s += sm[r * PNP_NRED + lane];
+        sm[32 * PNP_NRED + lane] = s;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < PNP_NRED; ++i) v[i] = sm[32 * PNP_NRED + i];
+    __syncwarp();
+}
+
 // one warp per image
 __global__ void __launch_bounds__(128)
     k_uncertainty_pnp(const float *__restrict__ kp, const float *__restrict__ cov, const float *__restrict__ wgt,
                       const float *__restrict__ pts3d, double fx, double fy, double cx, double cy, int nb, int K,
                       double *__restrict__ out_pose, int *__restrict__ out_info)
 {
+    __shared__ double s_red[4][33 * PNP_NRED];
     const int img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (img >= nb) return;
+    double *sm = s_red[threadIdx.x >> 5];
     const bool active = lane < K;
     const int li = active ? lane : 0;
     const double u = kp[((size_t)img * K + li) * 2], v = kp[((size_t)img * K + li) * 2 + 1];
@@ -338,21 +367,33 @@ __global__ void __launch_bounds__(128)
         double cost = 0.5 * warp_sum_all(r0 * r0 + r1 * r1);
         for (; iters < PNP_MAX_ITERS; ++iters) {
             double A[36], g[6];
+            {
+                double red[PNP_NRED];
+                int q = 0;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                g[i] = warp_sum_all(J[0][i] * r0 + J[1][i] * r1);
+                for (int i = 0; i < 6; ++i)
 #pragma unroll
-                for (int j = i; j < 6; ++j) {
-                    const double s = warp_sum_all(J[0][i] * J[0][j] + J[1][i] * J[1][j]);
-                    A[i * 6 + j] = s;
-                    A[j * 6 + i] = s;
-                }
+                    for (int j = i; j < 6; ++j) red[q++] = J[0][i] * J[0][j] + J[1][i] * J[1][j];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) red[21 + i] = J[0][i] * r0 + J[1][i] * r1;
+                red[27] = 0.0;
+                warp_reduce28(red, sm, lane);
+                q = 0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int j = i; j < 6; ++j) {
+                        A[i * 6 + j] = red[q];
+                        A[j * 6 + i] = red[q++];
+                    }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) g[i] = red[21 + i];
             }
             double gmax = 0.0;
             for (int i = 0; i < 6; ++i) gmax = fmax(gmax, fabs(g[i]));
             if (gmax < 1e-14) break;
             bool stepped = false, converged = false;
-            for (int tries = 0; tries < 30 && !stepped; ++tries) {
+            for (int tries = 0; tries < 12 && !stepped; ++tries) {
                 double Ad[36], rhs[6], d[6];
                 for (int i = 0; i < 36; ++i) Ad[i] = A[i];
                 for (int i = 0; i < 6; ++i) {
@@ -365,6 +406,8 @@ __global__ void __launch_bounds__(128)
                     decrease *= 2.0;
                     continue;
                 }
+                double dn = 0.0;
+                for (int i = 0; i < 6; ++i) dn = fmax(dn, fabs(d[i]));
                 PnpState cand;
                 double E[9];
                 so3_exp(d[0], d[1], d[2], E);
@@ -372,6 +415,11 @@ __global__ void __launch_bounds__(128)
                     for (int c = 0; c < 3; ++c)
                         cand.R[r * 3 + c] = E[r * 3] * st.R[c] + E[r * 3 + 1] * st.R[3 + c] + E[r * 3 + 2] * st.R[6 + c];
                 for (int i = 0; i < 3; ++i) cand.t[i] = st.t[i] + d[3 + i];
+                if (dn < 1e-11) {                   // at the stationary point to working precision: take the step, stop
+                    st = cand;                      // (cost differences are below rounding here: rho would be noise)
+                    converged = true;
+                    break;
+                }
                 double c0, c1, Jc[2][6];
                 lane_residual(cand, active, X, u, v, wxx, wxy, wyy, fx, fy, cx, cy, c0, c1, Jc);
                 const double new_cost = 0.5 * warp_sum_all(c0 * c0 + c1 * c1);
@@ -383,8 +431,6 @@ __global__ void __launch_bounds__(128)
                     md -= d[i] * (g[i] + 0.5 * Adi);
                 }
                 const double rho = (cost - new_cost) / md;
-                double dn = 0.0;
-                for (int i = 0; i < 6; ++i) dn = fmax(dn, fabs(d[i]));
                 if (new_cost <= cost && md > 0.0 && rho > 1e-3) {
                     st = cand;
                     r0 = c0;
@@ -398,12 +444,7 @@ __global__ void __launch_bounds__(128)
                     decrease = 2.0;
                     cost = new_cost;
                     stepped = true;
-                    if (dn < 1e-12) converged = true;
                 } else {
-                    if (dn < 1e-13) {               // cannot improve at machine precision
-                        converged = true;
-                        break;
-                    }
                     radius /= decrease;
                     decrease *= 2.0;
                 }

@@ -594,7 +594,7 @@ constexpr float VT_SCALE = 18446744073709551616.f;     // 2^64
 constexpr int VT_SUB = 64;        // pixels per staged sub-chunk (2 per lane)
 
 template <int HPL>
-__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
+__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 4)
     k_vote2(const unsigned *__restrict__ pix, const float2 *__restrict__ direct, const int *__restrict__ tn_arr, int npx,
             int cap, int nb, int vn, int hn, int HT, int h0, const float2 *__restrict__ hyp, int *__restrict__ counts,
             unsigned *__restrict__ ticket, float thresh, float sn, float cs, float beta, float b0)
@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
         // ---- this lane's hypotheses (issued first: their latency overlaps the bounding-box pass)
         const int hbase = hc * HC;
         const float2 *hyp_row = hyp + ((size_t)b * vn + k) * HT + h0;
-        float2 hraw[HPL];
+        float2 hraw[HPL];                           // consumed by the centring below; the rare exact path reloads
 #pragma unroll
         for (int j = 0; j < HPL; ++j) {
             const int h = hbase + j * 32 + lane;
@@ -778,8 +778,9 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                                 if (hbase + j * 32 + lane < hn && !(fabsf(m) > bd[j])) {
                                     const unsigned p = pix_t[c0 + pi];
                                     const float2 nraw = dir_t[c0 + pi];
-                                    cnt[j] += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hraw[j].x,
-                                                           hraw[j].y, thresh)
+                                    const float2 hp = hyp_row[hbase + j * 32 + lane];
+                                    cnt[j] += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hp.x, hp.y,
+                                                           thresh)
                                                   ? 1.f
                                                   : 0.f;
                                 }
@@ -1478,7 +1479,7 @@ int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int
         return PVNET_OK;
     }
     const VoteConsts vc = vote_consts(thresh);
-    const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : (HPL > 4 ? 2 : 3);
+    const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : (HPL > 4 ? 2 : 4);
     const unsigned grid = (unsigned)(pvnet::sm_count() * per_sm);
     PV_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(unsigned), s));
     if (HPL == 8)

@@ -90,6 +90,8 @@ def _product_vs_reference_layer(mask_np, field_np, hn, thresh, max_num=30000, la
     print(f"\n[reference-layer gap] {label}: |ours - ref(fp32 refit)| = {gap32:.3e}; "
           f"|ours - ref(fp64 refit)| = {gap64:.3e}; reference's own fp32 noise |ref32 - ref64| = {noise:.3e}")
     assert gap64 <= 1e-4, "product differs from the reference layer beyond its fp32 refit rounding"
+    # and the distance to the STOCK fp32 reference is explained by that rounding noise, not hidden behind it
+    assert gap32 <= 1.5 * noise + 1e-5, (gap32, noise)
     return gap32, gap64, noise
 
 
