@@ -55,7 +55,9 @@ __device__ __forceinline__ void tri_frame(Vec3 p0, Vec3 p1, Vec3 p2, double (&F)
     F[6] = e1.z; F[7] = e2.z; F[8] = e3.z;
 }
 
-// all roots of c4 z^4 + .. + c0 by Durand-Kerner; returns the real ones, Newton-polished
+// all roots of c4 z^4 + .. + c0 by Durand-Kerner (stopped at 1e-9 of the root bound: P3P's quartics have
+// clustered roots whose last digits never settle), the real ones Newton-polished on the real polynomial.
+// Loops over the four roots are unrolled so that they live in registers.
 __device__ int quartic_real_roots(const double (&c)[5], double (&out)[4])
 {
     if (!(fabs(c[4]) > 1e-300)) return 0;
@@ -63,47 +65,53 @@ __device__ int quartic_real_roots(const double (&c)[5], double (&out)[4])
     double zr[4], zi[4];
     // start on a circle of the Cauchy bound's size, off the real axis
     const double rad = 1.0 + fmax(fmax(fabs(a3), fabs(a2)), fmax(fabs(a1), fabs(a0)));
-    double pr = 1.0, pi = 0.0;
-    for (int k = 0; k < 4; ++k) {
-        zr[k] = pr * rad * 0.5;
-        zi[k] = pi * rad * 0.5;
-        const double nr = pr * 0.4 - pi * 0.9, ni = pr * 0.9 + pi * 0.4;
-        pr = nr;
-        pi = ni;
+    {
+        double pr = 1.0, pi = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            zr[k] = pr * rad * 0.5;
+            zi[k] = pi * rad * 0.5;
+            const double nr = pr * 0.4 - pi * 0.9, ni = pr * 0.9 + pi * 0.4;
+            pr = nr;
+            pi = ni;
+        }
     }
-    for (int it = 0; it < 200; ++it) {
+    for (int it = 0; it < 60; ++it) {
         double move = 0.0;
+#pragma unroll
         for (int k = 0; k < 4; ++k) {
             // p(z) by Horner (monic)
-            double vr = 1.0, vi = 0.0;
-            const double co[4] = {a3, a2, a1, a0};
-            for (int j = 0; j < 4; ++j) {
-                const double tr = vr * zr[k] - vi * zi[k] + co[j], ti = vr * zi[k] + vi * zr[k];
-                vr = tr;
-                vi = ti;
-            }
+            double vr = zr[k] + a3, vi = zi[k];
+            double tr = vr * zr[k] - vi * zi[k] + a2, ti = vr * zi[k] + vi * zr[k];
+            vr = tr * zr[k] - ti * zi[k] + a1;
+            vi = tr * zi[k] + ti * zr[k];
+            tr = vr * zr[k] - vi * zi[k] + a0;
+            ti = vr * zi[k] + vi * zr[k];
             double dr = 1.0, di = 0.0;
+#pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (j == k) continue;
                 const double er = zr[k] - zr[j], ei = zi[k] - zi[j];
-                const double tr = dr * er - di * ei, ti = dr * ei + di * er;
-                dr = tr;
-                di = ti;
+                const double xr = dr * er - di * ei, xi = dr * ei + di * er;
+                dr = xr;
+                di = xi;
             }
             const double den = dr * dr + di * di;
-            if (!(den > 0.0)) continue;
-            const double qr = (vr * dr + vi * di) / den, qi = (vi * dr - vr * di) / den;
-            zr[k] -= qr;
-            zi[k] -= qi;
-            move = fmax(move, fabs(qr) + fabs(qi));
+            if (den > 0.0) {
+                const double qr = (tr * dr + ti * di) / den, qi = (ti * dr - tr * di) / den;
+                zr[k] -= qr;
+                zi[k] -= qi;
+                move = fmax(move, fabs(qr) + fabs(qi));
+            }
         }
-        if (move < 1e-15 * rad) break;
+        if (move < 1e-9 * rad) break;
     }
     int n = 0;
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (!(fabs(zi[k]) <= 1e-6 * fmax(1.0, fabs(zr[k])))) continue;
+        if (!(fabs(zi[k]) <= 1e-5 * fmax(1.0, fabs(zr[k])))) continue;
         double v = zr[k];
-        for (int it = 0; it < 6; ++it) {
+        for (int it = 0; it < 8; ++it) {
             const double p = (((v + a3) * v + a2) * v + a1) * v + a0;
             const double d = ((4.0 * v + 3.0 * a3) * v + 2.0 * a2) * v + a1;
             if (d == 0.0) break;

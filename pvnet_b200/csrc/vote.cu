@@ -736,54 +736,53 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 4)
                 pp[e] = (i < len) ? __ldg(pix_t + i) : 0u;
                 pn[e] = (i < len) ? __ldg(dir_t + i) : make_float2(0.f, 0.f);
             }
-            // ---- sweep: VT_GROUP pixels x HPL hypotheses per step
-            for (int i0 = 0; i0 < clen; i0 += VT_GROUP) {
-                bool unc = false;
-                const uint32_t base = rec_u + (uint32_t)i0 * 48u;
+            // ---- sweep: the whole sub-chunk branch-free (the compiler pipelines the LDS of the next pixels under
+            // the arithmetic of the current ones -- a vote + branch per 4-pixel group cost 40 % here, see
+            // benchmarks/micro/vote_mix.cu); the guard-band flag is checked ONCE per sub-chunk
+            bool unc = false;
+#pragma unroll 4
+            for (int u = 0; u < VT_SUB; ++u) {
+                f32x2 SX, SY, NS, CX, CY, NC;
+                lds_2x64(rec_u + (uint32_t)u * 48u, SX, SY);
+                lds_2x64(rec_u + (uint32_t)u * 48u + 16u, NS, CX);
+                lds_2x64(rec_u + (uint32_t)u * 48u + 32u, CY, NC);
 #pragma unroll
-                for (int u = 0; u < VT_GROUP; ++u) {
-                    f32x2 SX, SY, NS, CX, CY, NC;
-                    lds_2x64(base + (uint32_t)u * 48u, SX, SY);
-                    lds_2x64(base + (uint32_t)u * 48u + 16u, NS, CX);
-                    lds_2x64(base + (uint32_t)u * 48u + 32u, CY, NC);
-#pragma unroll
-                    for (int j = 0; j < HPL / 2; ++j) {
-                        const f32x2 num2 = fma2(hx2[j], SX, fma2(hy2[j], SY, NS));
-                        const f32x2 per2 = fma2(hx2[j], CX, fma2(hy2[j], CY, NC));
-                        float n0, n1, q0, q1;
-                        upk2(num2, n0, n1);
-                        upk2(per2, q0, q1);
-                        const float m0 = n0 - fabsf(q0), m1 = n1 - fabsf(q1);
-                        cnt[2 * j] += fma_sat(m0, VT_SCALE, nb2[2 * j]);
-                        cnt[2 * j + 1] += fma_sat(m1, VT_SCALE, nb2[2 * j + 1]);
-                        unc |= !(fabsf(m0) > bd[2 * j]);
-                        unc |= !(fabsf(m1) > bd[2 * j + 1]);
-                    }
+                for (int j = 0; j < HPL / 2; ++j) {
+                    const f32x2 num2 = fma2(hx2[j], SX, fma2(hy2[j], SY, NS));
+                    const f32x2 per2 = fma2(hx2[j], CX, fma2(hy2[j], CY, NC));
+                    float n0, n1, q0, q1;
+                    upk2(num2, n0, n1);
+                    upk2(per2, q0, q1);
+                    const float m0 = n0 - fabsf(q0), m1 = n1 - fabsf(q1);
+                    cnt[2 * j] += fma_sat(m0, VT_SCALE, nb2[2 * j]);
+                    cnt[2 * j + 1] += fma_sat(m1, VT_SCALE, nb2[2 * j + 1]);
+                    unc |= !(fabsf(m0) > bd[2 * j]);
+                    unc |= !(fabsf(m1) > bd[2 * j + 1]);
                 }
-                if (__any_sync(0xffffffffu, unc)) {
-                    if (unc) {
-                        for (int u = 0; u < VT_GROUP; ++u) {
-                            const int pi = i0 + u;
-                            if (pi >= clen) break;
-                            const float4 ra = rec[3 * pi], rb = rec[3 * pi + 1], rc = rec[3 * pi + 2];
+            }
+            // ---- rare: some lane saw a test inside its guard band (not counted above: |m| <= B excludes m > B).
+            // Those lanes re-walk the sub-chunk and decide exactly the in-band tests with the reference's sequence.
+            if (__any_sync(0xffffffffu, unc)) {
+                if (unc) {
+                    for (int pi = 0; pi < clen; ++pi) {
+                        const float4 ra = rec[3 * pi], rb = rec[3 * pi + 1], rc = rec[3 * pi + 2];
 #pragma unroll
-                            for (int j = 0; j < HPL; ++j) {
-                                float hxa, hxb, hya, hyb;
-                                upk2(hx2[j / 2], hxa, hxb);
-                                upk2(hy2[j / 2], hya, hyb);
-                                const float hxs = (j & 1) ? hxb : hxa, hys = (j & 1) ? hyb : hya;
-                                const float num = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
-                                const float perp = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
-                                const float m = num - fabsf(perp);
-                                if (hbase + j * 32 + lane < hn && !(fabsf(m) > bd[j])) {
-                                    const unsigned p = pix_t[c0 + pi];
-                                    const float2 nraw = dir_t[c0 + pi];
-                                    const float2 hp = hyp_row[hbase + j * 32 + lane];
-                                    cnt[j] += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hp.x, hp.y,
-                                                           thresh)
-                                                  ? 1.f
-                                                  : 0.f;
-                                }
+                        for (int j = 0; j < HPL; ++j) {
+                            float hxa, hxb, hya, hyb;
+                            upk2(hx2[j / 2], hxa, hxb);
+                            upk2(hy2[j / 2], hya, hyb);
+                            const float hxs = (j & 1) ? hxb : hxa, hys = (j & 1) ? hyb : hya;
+                            const float num = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
+                            const float perp = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
+                            const float m = num - fabsf(perp);
+                            if (hbase + j * 32 + lane < hn && !(fabsf(m) > bd[j])) {
+                                const unsigned p = pix_t[c0 + pi];
+                                const float2 nraw = dir_t[c0 + pi];
+                                const float2 hp = hyp_row[hbase + j * 32 + lane];
+                                cnt[j] += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hp.x, hp.y,
+                                                       thresh)
+                                              ? 1.f
+                                              : 0.f;
                             }
                         }
                     }

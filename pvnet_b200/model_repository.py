@@ -262,6 +262,26 @@ class Resnet18_8s(nn.Module):
                                                        ws.data_ptr(), ws.numel(), stream), "pvnet_backbone_forward")
         return (out, mask) if with_mask else out
 
+    def run_stages(self, x, out, mask, lo, hi, pixel_major=False):
+        """Stages [lo, hi) of the forward pass (pvnet_backbone_run_stage; stage names:
+        pvnet_backbone_stage_name) on caller-provided output tensors -- lets a caller interleave other work
+        (e.g. the previous batch's voting layer on a second stream) at a stage boundary.  x float32 [b,3,H,W]."""
+        b, _, h, w = x.shape
+        dev = x.device
+        with torch.cuda.device(dev):
+            handle = self._prepare_native(dev)
+            L = _native.lib()
+            n = ctypes.c_size_t()
+            _native.check(L.pvnet_backbone_workspace_bytes(handle, b, h, w, ctypes.byref(n)), "pvnet_backbone_workspace_bytes")
+            ws = self._workspace(n.value, dev)
+            _native.check(L.pvnet_backbone_set_output_layout(handle, 1 if pixel_major else 0), "set_output_layout")
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for i in range(lo, hi):
+                _native.check(L.pvnet_backbone_run_stage(handle, i, x.data_ptr(), b, h, w, out.data_ptr(),
+                                                         None if mask is None else mask.data_ptr(),
+                                                         0 if mask is None else mask.element_size(), ws.data_ptr(), ws.numel(),
+                                                         stream), "pvnet_backbone_run_stage")
+
     def _workspace(self, nbytes, dev):
         # one persistent workspace per (device, stream) (activations of the largest batch seen); reusing
         # the same address also lets the C handle keep its encoded tensor maps
