@@ -13,7 +13,7 @@
 // registers), so the loop has no divergence.  Rotation is kept as a matrix and updated on the manifold (R <- exp(dw) R), which has the
 // same minimiser as the reference's angle-axis parametrisation; damping follows Ceres'
 // Levenberg-Marquardt strategy (diagonal scaling, radius /= max(1/3, 1 - (2 rho - 1)^3) on success,
-// shrink by 2, 4, 8.. on failure) but iterates to |step| < 1e-12 instead of Ceres'
+// shrink by 2, 4, 8.. on failure) but iterates to |step| < 1e-9 (the next one is ~1e-11) instead of Ceres'
 // function_tolerance 1e-6, i.e. to the minimiser the reference approximates.
 // Initialisation: Grunert's P3P quartic (roots by Durand-Kerner + Newton polish) on the first three
 // of the four selected points, the fourth picks the solution -- OpenCV's SOLVEPNP_P3P contract.
@@ -55,69 +55,78 @@ __device__ __forceinline__ void tri_frame(Vec3 p0, Vec3 p1, Vec3 p2, double (&F)
     F[6] = e1.z; F[7] = e2.z; F[8] = e3.z;
 }
 
-// all roots of c4 z^4 + .. + c0 by Durand-Kerner (stopped at 1e-9 of the root bound: P3P's quartics have
-// clustered roots whose last digits never settle), the real ones Newton-polished on the real polynomial.
-// Loops over the four roots are unrolled so that they live in registers.
+// all roots of c4 z^4 + .. + c0: Durand-Kerner in fp32 (it only has to separate the roots: P3P's quartics have
+// clustered roots whose last digits never settle, and one warp's serial fp64 divisions were a third of the
+// kernel's time), then the real ones are Newton-polished in fp64 on the real polynomial.
 __device__ int quartic_real_roots(const double (&c)[5], double (&out)[4])
 {
     if (!(fabs(c[4]) > 1e-300)) return 0;
     const double a3 = c[3] / c[4], a2 = c[2] / c[4], a1 = c[1] / c[4], a0 = c[0] / c[4];
-    double zr[4], zi[4];
+    const float f3 = (float)a3, f2 = (float)a2, f1 = (float)a1, f0 = (float)a0;
+    float zr[4], zi[4];
     // start on a circle of the Cauchy bound's size, off the real axis
-    const double rad = 1.0 + fmax(fmax(fabs(a3), fabs(a2)), fmax(fabs(a1), fabs(a0)));
+    const float rad = 1.0f + fmaxf(fmaxf(fabsf(f3), fabsf(f2)), fmaxf(fabsf(f1), fabsf(f0)));
+    if (!(rad < 1e18f)) return 0;
     {
-        double pr = 1.0, pi = 0.0;
+        float pr = 1.0f, pi = 0.0f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            zr[k] = pr * rad * 0.5;
-            zi[k] = pi * rad * 0.5;
-            const double nr = pr * 0.4 - pi * 0.9, ni = pr * 0.9 + pi * 0.4;
+            zr[k] = pr * rad * 0.5f;
+            zi[k] = pi * rad * 0.5f;
+            const float nr = pr * 0.4f - pi * 0.9f, ni = pr * 0.9f + pi * 0.4f;
             pr = nr;
             pi = ni;
         }
     }
-    for (int it = 0; it < 60; ++it) {
-        double move = 0.0;
+    for (int it = 0; it < 48; ++it) {
+        float move = 0.0f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             // p(z) by Horner (monic)
-            double vr = zr[k] + a3, vi = zi[k];
-            double tr = vr * zr[k] - vi * zi[k] + a2, ti = vr * zi[k] + vi * zr[k];
-            vr = tr * zr[k] - ti * zi[k] + a1;
+            float vr = zr[k] + f3, vi = zi[k];
+            float tr = vr * zr[k] - vi * zi[k] + f2, ti = vr * zi[k] + vi * zr[k];
+            vr = tr * zr[k] - ti * zi[k] + f1;
             vi = tr * zi[k] + ti * zr[k];
-            tr = vr * zr[k] - vi * zi[k] + a0;
+            tr = vr * zr[k] - vi * zi[k] + f0;
             ti = vr * zi[k] + vi * zr[k];
-            double dr = 1.0, di = 0.0;
+            float dr = 1.0f, di = 0.0f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (j == k) continue;
-                const double er = zr[k] - zr[j], ei = zi[k] - zi[j];
-                const double xr = dr * er - di * ei, xi = dr * ei + di * er;
+                const float er = zr[k] - zr[j], ei = zi[k] - zi[j];
+                const float xr = dr * er - di * ei, xi = dr * ei + di * er;
                 dr = xr;
                 di = xi;
             }
-            const double den = dr * dr + di * di;
-            if (den > 0.0) {
-                const double qr = (tr * dr + ti * di) / den, qi = (ti * dr - tr * di) / den;
+            const float den = dr * dr + di * di;
+            if (den > 0.0f) {
+                const float inv = 1.0f / den;
+                const float qr = (tr * dr + ti * di) * inv, qi = (ti * dr - tr * di) * inv;
                 zr[k] -= qr;
                 zi[k] -= qi;
-                move = fmax(move, fabs(qr) + fabs(qi));
+                move = fmaxf(move, fabsf(qr) + fabsf(qi));
             }
         }
-        if (move < 1e-9 * rad) break;
+        if (move < 2e-6f * rad) break;
     }
     int n = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (!(fabs(zi[k]) <= 1e-5 * fmax(1.0, fabs(zr[k])))) continue;
-        double v = zr[k];
-        for (int it = 0; it < 8; ++it) {
+        // generous real-root filter (fp32 separation of near-double roots), then fp64 Newton; a complex pair that
+        // slipped through polishes to a point where the quartic is not ~0 and is dropped
+        if (!(fabsf(zi[k]) <= 2e-2f * fmaxf(1.0f, fabsf(zr[k])))) continue;
+        double v = (double)zr[k];
+        for (int it = 0; it < 12; ++it) {
             const double p = (((v + a3) * v + a2) * v + a1) * v + a0;
             const double d = ((4.0 * v + 3.0 * a3) * v + 2.0 * a2) * v + a1;
             if (d == 0.0) break;
-            v -= p / d;
+            const double st = p / d;
+            v -= st;
+            if (fabs(st) < 1e-15 * fmax(1.0, fabs(v))) break;
         }
-        out[n++] = v;
+        const double resid = (((v + a3) * v + a2) * v + a1) * v + a0;
+        const double scale = ((fabs(v) + fabs(a3)) * fabs(v) + fabs(a2)) * fabs(v) * fabs(v) + fabs(a1 * v) + fabs(a0);
+        if (fabs(resid) <= 1e-9 * fmax(scale, 1e-300)) out[n++] = v;
     }
     return n;
 }
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(128)
                     for (int c = 0; c < 3; ++c)
                         cand.R[r * 3 + c] = E[r * 3] * st.R[c] + E[r * 3 + 1] * st.R[3 + c] + E[r * 3 + 2] * st.R[6 + c];
                 for (int i = 0; i < 3; ++i) cand.t[i] = st.t[i] + d[3 + i];
-                if (dn < 1e-11) {                   // at the stationary point to working precision: take the step, stop
+                if (dn < 1e-9) {                    // the next Gauss-Newton step would be ~50x smaller: take this one, stop
                     st = cand;                      // (cost differences are below rounding here: rho would be noise)
                     converged = true;
                     break;
@@ -511,7 +520,9 @@ int pvnet_uncertainty_pnp(const float *points_2d, const float *cov, const float 
     PV_CHECK_ARG(pn >= 4 && pn <= 32, "point count %d outside [4,32] (one warp per image)", pn);
     const double fx = camera_matrix[0], fy = camera_matrix[4], cx = camera_matrix[2], cy = camera_matrix[5];
     PV_CHECK_ARG(fx != 0.0 && fy != 0.0, "zero focal length");
-    const int warps_per_cta = 4;
+    // one warp per CTA: the solve is a serial fp64 chain, so images should sit on different SMs, not share
+    // one SM's fp64 pipe (4 warps per CTA doubled the time at batch 16)
+    const int warps_per_cta = b <= 592 ? 1 : 4;
     k_uncertainty_pnp<<<(b + warps_per_cta - 1) / warps_per_cta, 32 * warps_per_cta, 0, (cudaStream_t)stream>>>(
         points_2d, cov, weights_2d, points_3d, fx, fy, cx, cy, b, pn, out_pose, out_info);
     PV_LAUNCHED("k_uncertainty_pnp");

@@ -594,7 +594,7 @@ constexpr float VT_SCALE = 18446744073709551616.f;     // 2^64
 constexpr int VT_SUB = 64;        // pixels per staged sub-chunk (2 per lane)
 
 template <int HPL>
-__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 4)
+__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
     k_vote2(const unsigned *__restrict__ pix, const float2 *__restrict__ direct, const int *__restrict__ tn_arr, int npx,
             int cap, int nb, int vn, int hn, int HT, int h0, const float2 *__restrict__ hyp, int *__restrict__ counts,
             unsigned *__restrict__ ticket, float thresh, float sn, float cs, float beta, float b0)
@@ -738,33 +738,47 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 4)
             }
             // ---- sweep: the whole sub-chunk branch-free (the compiler pipelines the LDS of the next pixels under
             // the arithmetic of the current ones -- a vote + branch per 4-pixel group cost 40 % here, see
-            // benchmarks/micro/vote_mix.cu); the guard-band flag is checked ONCE per sub-chunk
-            bool unc = false;
-#pragma unroll 4
-            for (int u = 0; u < VT_SUB; ++u) {
-                f32x2 SX, SY, NS, CX, CY, NC;
-                lds_2x64(rec_u + (uint32_t)u * 48u, SX, SY);
-                lds_2x64(rec_u + (uint32_t)u * 48u + 16u, NS, CX);
-                lds_2x64(rec_u + (uint32_t)u * 48u + 32u, CY, NC);
+            // benchmarks/micro/vote_mix.cu).  Each lane keeps one bit per pixel: "some test of mine at this
+            // pixel fell inside its guard band"; the warp looks at the bits once per sub-chunk.
+            unsigned ubits[2] = {0u, 0u};
 #pragma unroll
-                for (int j = 0; j < HPL / 2; ++j) {
-                    const f32x2 num2 = fma2(hx2[j], SX, fma2(hy2[j], SY, NS));
-                    const f32x2 per2 = fma2(hx2[j], CX, fma2(hy2[j], CY, NC));
-                    float n0, n1, q0, q1;
-                    upk2(num2, n0, n1);
-                    upk2(per2, q0, q1);
-                    const float m0 = n0 - fabsf(q0), m1 = n1 - fabsf(q1);
-                    cnt[2 * j] += fma_sat(m0, VT_SCALE, nb2[2 * j]);
-                    cnt[2 * j + 1] += fma_sat(m1, VT_SCALE, nb2[2 * j + 1]);
-                    unc |= !(fabsf(m0) > bd[2 * j]);
-                    unc |= !(fabsf(m1) > bd[2 * j + 1]);
+            for (int hf = 0; hf < 2; ++hf) {
+                unsigned mk = 0u;
+#pragma unroll 4
+                for (int u = 0; u < 32; ++u) {
+                    const uint32_t ra = rec_u + (uint32_t)(hf * 32 + u) * 48u;
+                    f32x2 SX, SY, NS, CX, CY, NC;
+                    lds_2x64(ra, SX, SY);
+                    lds_2x64(ra + 16u, NS, CX);
+                    lds_2x64(ra + 32u, CY, NC);
+                    bool unc = false;
+#pragma unroll
+                    for (int j = 0; j < HPL / 2; ++j) {
+                        const f32x2 num2 = fma2(hx2[j], SX, fma2(hy2[j], SY, NS));
+                        const f32x2 per2 = fma2(hx2[j], CX, fma2(hy2[j], CY, NC));
+                        float n0, n1, q0, q1;
+                        upk2(num2, n0, n1);
+                        upk2(per2, q0, q1);
+                        const float m0 = n0 - fabsf(q0), m1 = n1 - fabsf(q1);
+                        cnt[2 * j] += fma_sat(m0, VT_SCALE, nb2[2 * j]);
+                        cnt[2 * j + 1] += fma_sat(m1, VT_SCALE, nb2[2 * j + 1]);
+                        unc |= !(fabsf(m0) > bd[2 * j]);
+                        unc |= !(fabsf(m1) > bd[2 * j + 1]);
+                    }
+                    mk |= unc ? (1u << u) : 0u;
                 }
+                ubits[hf] = mk;
             }
-            // ---- rare: some lane saw a test inside its guard band (not counted above: |m| <= B excludes m > B).
-            // Those lanes re-walk the sub-chunk and decide exactly the in-band tests with the reference's sequence.
-            if (__any_sync(0xffffffffu, unc)) {
-                if (unc) {
-                    for (int pi = 0; pi < clen; ++pi) {
+            // ---- rare: in-band tests were not counted above (|m| <= B excludes m > B): the lanes that saw any
+            // re-evaluate just those pixels and decide the in-band tests with the reference's own sequence
+            if (__any_sync(0xffffffffu, (ubits[0] | ubits[1]) != 0u)) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    unsigned mk = ubits[hf];
+                    while (mk) {
+                        const int pi = hf * 32 + (__ffs(mk) - 1);
+                        mk &= mk - 1u;
+                        if (pi >= clen) continue;
                         const float4 ra = rec[3 * pi], rb = rec[3 * pi + 1], rc = rec[3 * pi + 2];
 #pragma unroll
                         for (int j = 0; j < HPL; ++j) {
@@ -1478,7 +1492,7 @@ int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int
         return PVNET_OK;
     }
     const VoteConsts vc = vote_consts(thresh);
-    const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : (HPL > 4 ? 2 : 4);
+    const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : (HPL > 4 ? 2 : 3);
     const unsigned grid = (unsigned)(pvnet::sm_count() * per_sm);
     PV_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(unsigned), s));
     if (HPL == 8)
