@@ -73,5 +73,46 @@ def main():
         print(json.dumps(row), flush=True)
 
 
+def pnp_timing():
+    """The device PnP alone on well-posed inputs (the network above has random weights: its keypoints are
+    noise, so the LM there runs into its iteration cap): object keypoints under random poses + anisotropic
+    noise, batch 1 / 16 / 128; CUDA events over 50 calls; mean LM iterations from the info output."""
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-0.1, 0.1, (9, 3)).astype(np.float32)
+
+    def rod(r):
+        th = np.linalg.norm(r)
+        k = r / th
+        kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        return np.eye(3) + np.sin(th) * kx + (1 - np.cos(th)) * kx @ kx
+    for b in (1, 16, 128):
+        kps, covs = [], []
+        for _ in range(b):
+            R, t = rod(rng.normal(0, 1, 3)), np.array([rng.uniform(-.1, .1), rng.uniform(-.1, .1), rng.uniform(.6, 1.2)])
+            X = pts @ R.T + t
+            uv = np.stack([K_MAT[0, 0] * X[:, 0] / X[:, 2] + K_MAT[0, 2], K_MAT[1, 1] * X[:, 1] / X[:, 2] + K_MAT[1, 2]], 1)
+            A = rng.normal(0, 1, (9, 2, 2))
+            cov = A @ A.transpose(0, 2, 1) + 0.3 * np.eye(2)
+            kps.append(uv + np.stack([rng.multivariate_normal(np.zeros(2), c) for c in cov]))
+            covs.append(cov)
+        kp = torch.from_numpy(np.stack(kps).astype(np.float32)).to(DEV)
+        cov = torch.from_numpy(np.stack(covs).astype(np.float32)).to(DEV)
+        p3 = torch.from_numpy(pts).to(DEV)
+        for _ in range(5):
+            _, info = eu.uncertainty_pnp_batched(kp, p3, K_MAT, cov=cov, return_info=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            eu.uncertainty_pnp_batched(kp, p3, K_MAT, cov=cov)
+        e1.record()
+        torch.cuda.synchronize()
+        print(json.dumps({"variant": "uncertainty_pnp alone, well-posed inputs", "batch": b,
+                          "ms_per_call": round(e0.elapsed_time(e1) / 50, 4),
+                          "lm_iterations_mean": round(float(info[:, 1].float().mean()), 2),
+                          "status_nonzero": int((info[:, 0] != 0).sum())}), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if os.environ.get("LAT_ONLY_PNP") != "1":
+        main()
+    pnp_timing()

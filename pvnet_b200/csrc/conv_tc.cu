@@ -596,6 +596,16 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
     g.cin_pad = g.cin_chunks * kc;
     g.Cout = d.Cout;
     g.BN = d.Cout > 256 ? 256 : d.Cout;
+    // Small batches (the reference's own calling shape is batch 1: 38 M tiles at 60x80 for 148 SMs): narrower N
+    // tiles until every SM has an item.  The MMA issue floor per output column is the same for N = 256 and
+    // N = 128 (128 / 64 cycles, benchmarks/micro/mma_rate.cu) and 1.5x at N = 64, so this trades nothing at
+    // 128 and little at 64 for 2-4x more parallelism; batch >= 4 keeps the wide tiles.
+    static const int env_small = [] {
+        const char *e = getenv("PVNET_CONV_SMALL_BATCH_SPLIT");     // tuning knob: 0 disables
+        return e ? atoi(e) : 1;
+    }();
+    if (env_small)
+        while (g.BN > 64 && (long long)g.total_m_tiles * (d.Cout / g.BN) < sm_count()) g.BN /= 2;
     PV_CHECK_ARG(d.Cout % g.BN == 0, "conv: Cout %d not a multiple of the N tile %d", d.Cout, g.BN);
     g.out_cs = d.out_cs;
     g.out_co = d.out_co;

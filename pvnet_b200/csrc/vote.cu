@@ -593,7 +593,7 @@ constexpr float VT_SCALE = 18446744073709551616.f;     // 2^64
 // per hypothesis.  No CTA barrier after the prologue.
 constexpr int VT_SUB = 64;        // pixels per staged sub-chunk (2 per lane)
 
-template <int HPL>
+template <int HPL, int G>
 __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
     k_vote2(const unsigned *__restrict__ pix, const float2 *__restrict__ direct, const int *__restrict__ tn_arr, int npx,
             int cap, int nb, int vn, int hn, int HT, int h0, const float2 *__restrict__ hyp, int *__restrict__ counts,
@@ -736,22 +736,19 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                 pp[e] = (i < len) ? __ldg(pix_t + i) : 0u;
                 pn[e] = (i < len) ? __ldg(dir_t + i) : make_float2(0.f, 0.f);
             }
-            // ---- sweep: the whole sub-chunk branch-free (the compiler pipelines the LDS of the next pixels under
-            // the arithmetic of the current ones -- a vote + branch per 4-pixel group cost 40 % here, see
-            // benchmarks/micro/vote_mix.cu).  Each lane keeps one bit per pixel: "some test of mine at this
-            // pixel fell inside its guard band"; the warp looks at the bits once per sub-chunk.
-            unsigned ubits[2] = {0u, 0u};
+            // ---- sweep: G pixels x HPL hypotheses per step; the guard-band flag is OR-ed into ONE predicate over the
+            // group (FSETP.LEU.OR chains) and checked with one vote.  (Two branch-free variants were measured
+            // and lost: one check per 64-pixel sub-chunk re-walks 26 % of the sub-chunks at B ~ 2.6e-3 px; per-pixel
+            // bits compile to FSETP + SEL chains on the half-rate ALU pipe: 2.74 vs 2.91e12 tests/s.)
+            for (int i0 = 0; i0 < clen; i0 += G) {
+                bool unc = false;
+                const uint32_t base = rec_u + (uint32_t)i0 * 48u;
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                unsigned mk = 0u;
-#pragma unroll 4
-                for (int u = 0; u < 32; ++u) {
-                    const uint32_t ra = rec_u + (uint32_t)(hf * 32 + u) * 48u;
+                for (int u = 0; u < G; ++u) {
                     f32x2 SX, SY, NS, CX, CY, NC;
-                    lds_2x64(ra, SX, SY);
-                    lds_2x64(ra + 16u, NS, CX);
-                    lds_2x64(ra + 32u, CY, NC);
-                    bool unc = false;
+                    lds_2x64(base + (uint32_t)u * 48u, SX, SY);
+                    lds_2x64(base + (uint32_t)u * 48u + 16u, NS, CX);
+                    lds_2x64(base + (uint32_t)u * 48u + 32u, CY, NC);
 #pragma unroll
                     for (int j = 0; j < HPL / 2; ++j) {
                         const f32x2 num2 = fma2(hx2[j], SX, fma2(hy2[j], SY, NS));
@@ -765,38 +762,31 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                         unc |= !(fabsf(m0) > bd[2 * j]);
                         unc |= !(fabsf(m1) > bd[2 * j + 1]);
                     }
-                    mk |= unc ? (1u << u) : 0u;
                 }
-                ubits[hf] = mk;
-            }
-            // ---- rare: in-band tests were not counted above (|m| <= B excludes m > B): the lanes that saw any
-            // re-evaluate just those pixels and decide the in-band tests with the reference's own sequence
-            if (__any_sync(0xffffffffu, (ubits[0] | ubits[1]) != 0u)) {
+                if (__any_sync(0xffffffffu, unc)) {
+                    if (unc) {
+                        for (int u = 0; u < G; ++u) {
+                            const int pi = i0 + u;
+                            if (pi >= clen) break;
+                            const float4 ra = rec[3 * pi], rb = rec[3 * pi + 1], rc = rec[3 * pi + 2];
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    unsigned mk = ubits[hf];
-                    while (mk) {
-                        const int pi = hf * 32 + (__ffs(mk) - 1);
-                        mk &= mk - 1u;
-                        if (pi >= clen) continue;
-                        const float4 ra = rec[3 * pi], rb = rec[3 * pi + 1], rc = rec[3 * pi + 2];
-#pragma unroll
-                        for (int j = 0; j < HPL; ++j) {
-                            float hxa, hxb, hya, hyb;
-                            upk2(hx2[j / 2], hxa, hxb);
-                            upk2(hy2[j / 2], hya, hyb);
-                            const float hxs = (j & 1) ? hxb : hxa, hys = (j & 1) ? hyb : hya;
-                            const float num = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
-                            const float perp = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
-                            const float m = num - fabsf(perp);
-                            if (hbase + j * 32 + lane < hn && !(fabsf(m) > bd[j])) {
-                                const unsigned p = pix_t[c0 + pi];
-                                const float2 nraw = dir_t[c0 + pi];
-                                const float2 hp = hyp_row[hbase + j * 32 + lane];
-                                cnt[j] += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hp.x, hp.y,
-                                                       thresh)
-                                              ? 1.f
-                                              : 0.f;
+                            for (int j = 0; j < HPL; ++j) {
+                                float hxa, hxb, hya, hyb;
+                                upk2(hx2[j / 2], hxa, hxb);
+                                upk2(hy2[j / 2], hya, hyb);
+                                const float hxs = (j & 1) ? hxb : hxa, hys = (j & 1) ? hyb : hya;
+                                const float num = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
+                                const float perp = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
+                                const float m = num - fabsf(perp);
+                                if (hbase + j * 32 + lane < hn && !(fabsf(m) > bd[j])) {
+                                    const unsigned p = pix_t[c0 + pi];
+                                    const float2 nraw = dir_t[c0 + pi];
+                                    const float2 hp = hyp_row[hbase + j * 32 + lane];
+                                    cnt[j] += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hp.x, hp.y,
+                                                           thresh)
+                                                  ? 1.f
+                                                  : 0.f;
+                                }
                             }
                         }
                     }
@@ -1495,12 +1485,18 @@ int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int
     const int per_sm = ctas_per_sm > 0 ? ctas_per_sm : (HPL > 4 ? 2 : 3);
     const unsigned grid = (unsigned)(pvnet::sm_count() * per_sm);
     PV_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(unsigned), s));
-    if (HPL == 8)
-        k_vote2<8><<<grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tn, npx, ws.cap, b, vn, hn, HT, h0, ws.hyp, ws.counts,
-                                               ws.ticket, thresh, vc.sn, vc.cs, vc.beta, vc.b0);
-    else
-        k_vote2<4><<<grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tn, npx, ws.cap, b, vn, hn, HT, h0, ws.hyp, ws.counts,
-                                               ws.ticket, thresh, vc.sn, vc.cs, vc.beta, vc.b0);
+    static const int grp = [] {
+        const char *e = getenv("PVNET_VOTE_GROUP");    // tuning knob: pixels per guard-band check (4 or 8)
+        return e ? atoi(e) : 4;
+    }();
+#define VOTE2(H_, G_)                                                                                                  \
+    k_vote2<H_, G_><<<grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tn, npx, ws.cap, b, vn, hn, HT, h0, ws.hyp, ws.counts, \
+                                                ws.ticket, thresh, vc.sn, vc.cs, vc.beta, vc.b0)
+    if (HPL == 8 && grp == 8) VOTE2(8, 8);
+    else if (HPL == 8) VOTE2(8, 4);
+    else if (grp == 8) VOTE2(4, 8);
+    else VOTE2(4, 4);
+#undef VOTE2
     PV_LAUNCHED("k_vote2");
     return PVNET_OK;
 }
