@@ -252,10 +252,10 @@ def vote_roofline(torch, pipe, x, peaks, clocks, cfg):
     HBM rate B_alg / t against the measured copy bandwidth."""
     from pvnet_b200 import ransac_voting_gpu as rv
     net = pipe.net
-    out, mask = net.forward_native(x, with_mask=True, mask_dtype=torch.uint8)
-    b, c, h, w = out.shape
+    out, mask = net.forward_native(x, with_mask=True, mask_dtype=torch.uint8, pixel_major=True)     # as pipe.step does
+    b, h, w, c = out.shape
     k = (c - 2) // 2
-    vertex = out[:, 2:].permute(0, 2, 3, 1).view(b, h, w, k, 2)
+    vertex = out[..., 2:].unflatten(3, (k, 2))
     cov = cfg["cov"]
     hn = cfg["hyp"]
     hnt = 0 if cov is None else cov[0] * -(-cov[1] // cov[0])
