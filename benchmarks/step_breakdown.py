@@ -15,6 +15,9 @@ from pvnet_b200 import ransac_voting_gpu as rv  # noqa: E402
 from pvnet_b200 import synthetic as syn  # noqa: E402
 
 
+WITH_COV = os.environ.get("BREAKDOWN_COV", "0") == "1"
+
+
 def main():
     dev = torch.device("cuda", 0)
     net = bench.build_model(torch, dev)
@@ -29,12 +32,11 @@ def main():
             t0 = time.perf_counter()
             if i >= warm:
                 ev[i - warm][0].record()
-            out, mask = net.forward_native(x, with_mask=True)
+            out, mask = net.forward_native(x, with_mask=True, mask_dtype=torch.uint8, pixel_major=True)
             if i >= warm:
                 ev[i - warm][1].record()
-            b, c, h, w = out.shape
-            vertex = out[:, 2:].permute(0, 2, 3, 1).view(b, h, w, bench.K_KP, 2)
-            rv.ransac_voting_layer_v3(mask, vertex, bench.HYP, inlier_thresh=bench.THRESH, rng="batched")
+            vertex = out[..., 2:].unflatten(3, (bench.K_KP, 2))
+            rv.ransac_voting_pipeline(mask, vertex, bench.HYP, bench.THRESH, WITH_COV, 256, 4096, bench.THRESH, rng="device")
             if i >= warm:
                 ev[i - warm][2].record()
             cpu.append(time.perf_counter() - t0)
@@ -42,7 +44,7 @@ def main():
     bb = [e[0].elapsed_time(e[1]) for e in ev]
     vt = [e[1].elapsed_time(e[2]) for e in ev]
     total = ev[0][0].elapsed_time(ev[-1][2]) / steps
-    print(json.dumps(dict(backbone_ms=round(float(np.median(bb)), 4), vote_ms=round(float(np.median(vt)), 4),
+    print(json.dumps(dict(with_cov=WITH_COV, backbone_ms=round(float(np.median(bb)), 4), vote_ms=round(float(np.median(vt)), 4),
                           step_ms=round(total, 4), cpu_enqueue_ms=round(float(np.median(cpu[warm:])) * 1e3, 4))))
 
 

@@ -597,12 +597,12 @@ int conv_plan(const ConvDesc &d, ConvPlan *p)
     g.Cout = d.Cout;
     g.BN = d.Cout > 256 ? 256 : d.Cout;
     // Small batches (the reference's own calling shape is batch 1: 38 M tiles at 60x80 for 148 SMs): narrower N
-    // tiles until every SM has an item.  The MMA issue floor per output column is the same for N = 256 and
-    // N = 128 (128 / 64 cycles, benchmarks/micro/mma_rate.cu) and 1.5x at N = 64, so this trades nothing at
-    // 128 and little at 64 for 2-4x more parallelism; batch >= 4 keeps the wide tiles.
+    // tiles until every SM has an item -- MEASURED SLOWER and therefore off by default (batch 1, backbone + v3 as
+    // one CUDA graph: 0.80 ms with the wide tiles, 0.86 ms with N = 64/128 tiles): a 128x64 tile needs 24 KB of
+    // operands per 192 MMA cycles = 125 B/clk/SM, the L2->SM fill limit, on 152 SMs at once.
     static const int env_small = [] {
-        const char *e = getenv("PVNET_CONV_SMALL_BATCH_SPLIT");     // tuning knob: 0 disables
-        return e ? atoi(e) : 1;
+        const char *e = getenv("PVNET_CONV_SMALL_BATCH_SPLIT");     // tuning knob: 1 enables
+        return e ? atoi(e) : 0;
     }();
     if (env_small)
         while (g.BN > 64 && (long long)g.total_m_tiles * (d.Cout / g.BN) < sm_count()) g.BN /= 2;

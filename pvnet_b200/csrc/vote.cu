@@ -582,19 +582,6 @@ __device__ __forceinline__ void lds_2x64(uint32_t addr, f32x2 &a, f32x2 &b)
 {
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
-// min(|a|, |b|, |c|), NaN if any is NaN: one FMNMX3.NAN on sm_100
-__device__ __forceinline__ float min3_abs_nan(float a, float b, float c)
-{
-    float r;
-    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c)));
-    return r;
-}
-__device__ __forceinline__ float min2_abs_nan(float a, float b)
-{
-    float r;
-    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(fabsf(a)), "f"(fabsf(b)));
-    return r;
-}
 constexpr float VT_SCALE = 18446744073709551616.f;     // 2^64
 
 // Work decomposition (second ncu pass: with CTA-wide tiles, 48 % of the stall samples sat OUTSIDE the
@@ -606,8 +593,8 @@ constexpr float VT_SCALE = 18446744073709551616.f;     // 2^64
 // per hypothesis.  No CTA barrier after the prologue.
 constexpr int VT_SUB = 64;        // pixels per staged sub-chunk (2 per lane)
 
-template <int HPL, int G, int MINB>
-__global__ void __launch_bounds__(VT_THREADS, MINB)
+template <int HPL, int G>
+__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
     k_vote2(const unsigned *__restrict__ pix, const float2 *__restrict__ direct, const int *__restrict__ tn_arr, int npx,
             int cap, int nb, int vn, int hn, int HT, int h0, const float2 *__restrict__ hyp, int *__restrict__ counts,
             unsigned *__restrict__ ticket, float thresh, float sn, float cs, float beta, float b0)
@@ -695,33 +682,28 @@ __global__ void __launch_bounds__(VT_THREADS, MINB)
         const float xc = (float)((xmin + xmax) >> 1), yc = (float)((ymin + ymax) >> 1);
         const float r1 = (float)(max((int)xc - xmin, xmax - (int)xc) + max((int)yc - ymin, ymax - (int)yc));
 
-        // One band per LANE, the largest of its hypotheses' (a test with B_j < m <= B_lane is then left to the
-        // exact path instead of being counted here: still exact, ~2x more in-band tests, 14 registers fewer
-        // and the band check becomes min |m| over the lane's hypotheses: FMNMX3 chains + ONE FSETP per pixel).
         f32x2 hx2[HPL / 2], hy2[HPL / 2];
-        float cnt[HPL];                             // counts (exact small integers in fp32)
-        float bdl = 0.f;
+        float bd[HPL], nb2[HPL], cnt[HPL];          // band, -band * 2^64, count (exact small integers in fp32)
 #pragma unroll
         for (int j = 0; j < HPL; j += 2) {
             float hxv[2], hyv[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int h = hbase + (j + e) * 32 + lane;
-                hxv[e] = hyv[e] = 1e30f;            // padding: |m| ~ 1e29, never in the band, count discarded
+                hxv[e] = hyv[e] = 0.f;
+                bd[j + e] = -1.f;                   // padding: never uncertain, count discarded
                 if (h < hn) {
                     hxv[e] = hraw[j + e].x - xc;
                     hyv[e] = hraw[j + e].y - yc;
-                    float bj = fmaf(beta, fabsf(hxv[e]) + fabsf(hyv[e]) + r1, b0);
-                    if (!(bj < 1e18f)) bj = qnan;   // absurdly far / non-finite: exact path
-                    bdl = (bj > bdl || bj != bj) ? bj : bdl;       // max, NaN sticks
+                    bd[j + e] = fmaf(beta, fabsf(hxv[e]) + fabsf(hyv[e]) + r1, b0);
+                    if (!(bd[j + e] < 1e18f)) bd[j + e] = qnan;     // absurdly far / non-finite: exact path
                 }
+                nb2[j + e] = -bd[j + e] * VT_SCALE;
                 cnt[j + e] = 0.f;
             }
             hx2[j / 2] = pk2(hxv[0], hxv[1]);
             hy2[j / 2] = pk2(hyv[0], hyv[1]);
         }
-        if (bdl != bdl) bdl = qnan;
-        const float nbl = -bdl * VT_SCALE;
 
         for (int c0 = 0; c0 < len; c0 += VT_SUB) {
             const int clen = min(VT_SUB, len - c0);
@@ -757,7 +739,9 @@ __global__ void __launch_bounds__(VT_THREADS, MINB)
             // ---- sweep: G pixels x HPL hypotheses per step; the guard-band flag is OR-ed into ONE predicate over the
             // group (FSETP.LEU.OR chains) and checked with one vote.  (Two branch-free variants were measured
             // and lost: one check per 64-pixel sub-chunk re-walks 26 % of the sub-chunks at B ~ 2.6e-3 px; per-pixel
-            // bits compile to FSETP + SEL chains on the half-rate ALU pipe: 2.74 vs 2.91e12 tests/s.)
+            // bits compile to FSETP + SEL chains on the half-rate ALU pipe: 2.74 vs 2.94e12 tests/s.  So did one
+            // band per LANE (max over its 8 hypotheses, FMNMX3 band check): the heavy tail of |h'| inflates it,
+            // 2.16e12.)
             for (int i0 = 0; i0 < clen; i0 += G) {
                 bool unc = false;
                 const uint32_t base = rec_u + (uint32_t)i0 * 48u;
@@ -767,7 +751,6 @@ __global__ void __launch_bounds__(VT_THREADS, MINB)
                     lds_2x64(base + (uint32_t)u * 48u, SX, SY);
                     lds_2x64(base + (uint32_t)u * 48u + 16u, NS, CX);
                     lds_2x64(base + (uint32_t)u * 48u + 32u, CY, NC);
-                    float mm[HPL];
 #pragma unroll
                     for (int j = 0; j < HPL / 2; ++j) {
                         const f32x2 num2 = fma2(hx2[j], SX, fma2(hy2[j], SY, NS));
@@ -776,20 +759,11 @@ __global__ void __launch_bounds__(VT_THREADS, MINB)
                         upk2(num2, n0, n1);
                         upk2(per2, q0, q1);
                         const float m0 = n0 - fabsf(q0), m1 = n1 - fabsf(q1);
-                        cnt[2 * j] += fma_sat(m0, VT_SCALE, nbl);
-                        cnt[2 * j + 1] += fma_sat(m1, VT_SCALE, nbl);
-                        mm[2 * j] = m0;
-                        mm[2 * j + 1] = m1;
+                        cnt[2 * j] += fma_sat(m0, VT_SCALE, nb2[2 * j]);
+                        cnt[2 * j + 1] += fma_sat(m1, VT_SCALE, nb2[2 * j + 1]);
+                        unc |= !(fabsf(m0) > bd[2 * j]);
+                        unc |= !(fabsf(m1) > bd[2 * j + 1]);
                     }
-                    float lo = min3_abs_nan(mm[0], mm[1], mm[2]);
-                    if (HPL == 8) {
-                        lo = min3_abs_nan(lo, mm[3], mm[4]);
-                        lo = min3_abs_nan(lo, mm[5], mm[6]);
-                        lo = min2_abs_nan(lo, mm[7]);
-                    } else {
-                        lo = min2_abs_nan(lo, mm[3]);
-                    }
-                    unc |= !(lo > bdl);
                 }
                 if (__any_sync(0xffffffffu, unc)) {
                     if (unc) {
@@ -806,7 +780,7 @@ __global__ void __launch_bounds__(VT_THREADS, MINB)
                                 const float num = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
                                 const float perp = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
                                 const float m = num - fabsf(perp);
-                                if (hbase + j * 32 + lane < hn && !(fabsf(m) > bdl)) {
+                                if (hbase + j * 32 + lane < hn && !(fabsf(m) > bd[j])) {
                                     const unsigned p = pix_t[c0 + pi];
                                     const float2 nraw = dir_t[c0 + pi];
                                     const float2 hp = hyp_row[hbase + j * 32 + lane];
@@ -1517,15 +1491,13 @@ int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int
         const char *e = getenv("PVNET_VOTE_GROUP");    // tuning knob: pixels per guard-band check (4 or 8)
         return e ? atoi(e) : 8;
     }();
-#define VOTE2(H_, G_, B_)                                                                                              \
-    k_vote2<H_, G_, B_><<<grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tn, npx, ws.cap, b, vn, hn, HT, h0, ws.hyp,    \
-                                                    ws.counts, ws.ticket, thresh, vc.sn, vc.cs, vc.beta, vc.b0)
-    if (HPL == 8 && per_sm >= 3 && grp == 8) VOTE2(8, 8, 3);
-    else if (HPL == 8 && per_sm >= 3) VOTE2(8, 4, 3);
-    else if (HPL == 8 && grp == 8) VOTE2(8, 8, 2);
-    else if (HPL == 8) VOTE2(8, 4, 2);
-    else if (grp == 8) VOTE2(4, 8, 3);
-    else VOTE2(4, 4, 3);
+#define VOTE2(H_, G_)                                                                                                  \
+    k_vote2<H_, G_><<<grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tn, npx, ws.cap, b, vn, hn, HT, h0, ws.hyp, ws.counts, \
+                                                ws.ticket, thresh, vc.sn, vc.cs, vc.beta, vc.b0)
+    if (HPL == 8 && grp == 8) VOTE2(8, 8);
+    else if (HPL == 8) VOTE2(8, 4);
+    else if (grp == 8) VOTE2(4, 8);
+    else VOTE2(4, 4);
 #undef VOTE2
     PV_LAUNCHED("k_vote2");
     return PVNET_OK;
