@@ -59,7 +59,7 @@ def conv(rep, md, js, batch=16):
     col = {c: i for i, c in enumerate(h)}
     tens = [c for c in h if "tensor" in c and "pct" in c]
     gm = _gmac()
-    lines = ["# ncu --set full, all 25 tensor-core conv launches of one bench step (batch 16, 480x640)", "",
+    lines = ["# ncu --set full, all 25 tensor-core conv launches (stem .. convraw.0 + fused head) of one bench step (batch 16, 480x640)", "",
              "`ncu --profile-from-start off --set full --clock-control none --import-source on -k "
              "regex:\"k_conv_tap_p|k_conv_col|k_conv_tc\" -c 25 python benchmarks/profile_step.py 1`"
              " -> `python benchmarks/ncu_tables.py conv ...`", "",
@@ -106,23 +106,42 @@ VOTE_METRICS = ["launch__grid_size", "launch__block_size", "gpu__time_duration.s
                 "sm__cycles_elapsed.avg.per_second"]
 
 
-def vote(rep, md):
+VOTE_METRICS += ["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+                 "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+                 "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+                 "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+                 "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+                 "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
+
+
+def vote(rep, md, bench_json=None):
     h, units, rows = raw(rep)
     col = {c: i for i, c in enumerate(h)}
     r = rows[0]
-    lines = ["# ncu --set full, k_vote inside one bench step (16 images x ~19900 px, 256 hyp, K=9)", "",
-             "`ncu --profile-from-start off --set full --clock-control none -k regex:k_vote -c 1 python "
+    tests, fg, k, hn = 16 * 20000 * 9 * 256, 20000.0, 9, 256
+    if bench_json:
+        rv = json.load(open(bench_json))["roofline_vote"]
+        fg = rv["fg_px_per_image"]
+        tests = int(16 * fg * k * hn)                       # the kernel's own tests (the refit's +1 vote is k_refit's)
+    lines = [f"# ncu --set full, k_vote2 inside one bench step (16 images x ~{fg:.0f} px, {hn} hyp, K={k})", "",
+             "`ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_vote2 -c 1 python "
              "benchmarks/profile_step.py 1` -> `python benchmarks/ncu_tables.py vote ...`", "",
              f"Kernel: `{r[col['Kernel Name']][:100]}`", "", "| metric | value | unit |", "|---|---|---|"]
     for m in VOTE_METRICS:
         if m in col:
             lines.append(f"| {m} | {r[col[m]]} | {units[col[m]]} |")
     inst = float(r[col["smsp__inst_executed.sum"]].replace(",", ""))
-    tests = 16 * 19905 * 9 * 256
-    lines += ["", f"Tests in this launch: 16 x ~19905 px x 9 kp x 256 hyp = {tests / 1e6:.0f} M -> "
-                  f"{inst * 32 / tests:.1f} lane-instructions per test (all kernel phases included).  Algorithmic HBM bytes "
-                  "(DESIGN.md) ~ 16 x (480*640*8 + 19905*9*8 + 256*9*8) = 62.5 MB; DRAM traffic above is the measured "
-                  "figure.  The kernel is FP32-issue bound (issue-active and pipe % above), not HBM bound: see DESIGN.md §3."]
+    us = to_unit(r[col["gpu__time_duration.sum"]], units[col["gpu__time_duration.sum"]], "us")
+    rd = to_unit(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]], "MB")
+    wr = to_unit(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]], "MB")
+    alg = 16 * (fg * 4 + fg * k * 8 + hn * k * 8 + hn * k * 4) / 1e6        # pixel list + direct lists + hypotheses + counts
+    lines += ["", f"Tests in this launch: 16 x ~{fg:.0f} px x {k} kp x {hn} hyp = {tests / 1e6:.0f} M -> "
+                  f"{inst * 32 / tests:.2f} warp-instructions per 32 tests (all kernel phases included), "
+                  f"{tests / (us * 1e-6) / 1e12:.2f}e12 tests/s under the profiler.",
+              f"The kernel's algorithmic HBM bytes (compact pixel list 4 B/px + direct lists 8 B/px/keypoint + hypotheses + "
+              f"counts) = {alg:.1f} MB; measured DRAM read + write = {rd + wr:.1f} MB = {(rd + wr) / alg:.2f}x "
+              "(round 1, gathering sectors from the NCHW field per keypoint: 313 MB = 4.9x its 62.5 MB).",
+              "It is FP32-pipe bound (FMA-pipe cycles and issue-active above), not HBM bound: DESIGN.md section 3."]
     open(md, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines[6:]))
 
@@ -186,6 +205,6 @@ if __name__ == "__main__":
     elif cmd == "list":
         launch_list(sys.argv[2], sys.argv[3])
     elif cmd == "vote":
-        vote(sys.argv[2], sys.argv[3])
+        vote(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
     elif cmd == "top":
         top(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 16)

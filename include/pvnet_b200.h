@@ -345,6 +345,19 @@ PVNET_API int pvnet_backbone_forward_u8(pvnet_backbone_t *m, const uint8_t *imag
                                         const float std[3], int b, int h, int w,
                                         float *out_nchw, void *mask_out, int mask_elem_size,
                                         void *workspace, size_t workspace_bytes, pvnet_stream_t stream);
+/* JPEG bytes -> the uint8 [b,h,w,3] RGB batch pvnet_backbone_forward_u8 takes, decoded on the device by
+ * NVIDIA's nvJPEG (library code; dlopen'ed on first use -- pvnet_jpeg_available() says whether it was found).
+ * Replaces the host-side `Image.open` of lib/datasets/linemod_dataset.py:180-195 / tools/demo.py:89.
+ * jpeg_data / lengths: HOST arrays of b host pointers / sizes; every image must be h x w.  The decoder object
+ * owns nvJPEG's internal buffers (the one place this library lets a dependency allocate).  Different decoder
+ * than the reference's libjpeg: +-1 level from the IDCT, more at colour edges of chroma-subsampled files. */
+typedef struct pvnet_jpeg_decoder pvnet_jpeg_decoder_t;
+PVNET_API int pvnet_jpeg_available(void);
+PVNET_API int pvnet_jpeg_decoder_create(pvnet_jpeg_decoder_t **out);
+PVNET_API void pvnet_jpeg_decoder_destroy(pvnet_jpeg_decoder_t *d);
+PVNET_API int pvnet_jpeg_decode_batch(pvnet_jpeg_decoder_t *d, const uint8_t *const *jpeg_data, const size_t *lengths,
+                                      int b, int h, int w, uint8_t *out_hwc, pvnet_stream_t stream);
+
 /* The forward pass is an ordered list of single-kernel stages; these run/describe one of
  * them with the same arguments (per-layer timing in bench.py, layer-wise parity tests). */
 PVNET_API int pvnet_backbone_num_stages(void);

@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [nvcc, "-shared", "-o", LIB + ".tmp", *objs]
+    cmd = [nvcc, "-shared", "-o", LIB + ".tmp", *objs, "-ldl"]
     subprocess.check_call(cmd)
     os.replace(LIB + ".tmp", LIB)
     with open(os.path.join(LIBDIR, "build.log"), "w") as f:

@@ -77,6 +77,11 @@ SIGNATURES = {
                                        c_void_p, c_size_t, c_void_p]),
     "pvnet_backbone_forward_u8": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_int, c_int,
                                           c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "pvnet_jpeg_available": (c_int, []),
+    "pvnet_jpeg_decoder_create": (c_int, [ctypes.POINTER(c_void_p)]),
+    "pvnet_jpeg_decoder_destroy": (None, [c_void_p]),
+    "pvnet_jpeg_decode_batch": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_size_t), c_int, c_int,
+                                        c_int, c_void_p, c_void_p]),
     "pvnet_backbone_num_stages": (c_int, []),
     "pvnet_backbone_stage_name": (ctypes.c_char_p, [c_int]),
     "pvnet_backbone_run_stage": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,

@@ -536,6 +536,13 @@ int tma_encode(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dim
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), dims,
                     strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+        // a thread that has only selected its device through the runtime (nn.DataParallel's per-GPU workers) may
+        // have no driver context bound yet: cudaFree(0) binds the device's primary context to this thread
+        cudaFree(nullptr);
+        r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), dims, strides_bytes, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u, swizzle %d)",
                   (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1],
