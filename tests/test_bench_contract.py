@@ -28,6 +28,20 @@ def test_reference_arm_prints_one_json_line():
     assert "workload" in d["config"] and "model" not in d["config"]
 
 
+def test_round2_snapshot_has_the_new_blocks():
+    """profiles/r02_bench_n1.json: uint8 end-to-end input, vote roofline, config 4 measured in the same line,
+    conv DRAM traffic marked as not measured live."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")))
+    assert BASE_KEYS | {"gpu_launches", "clocks", "roofline", "roofline_vote", "config4", "cpu_baseline"} <= set(d)
+    assert d["e2e"]["h2d_bytes_per_step"] == 16 * 480 * 640 * 3                   # raw uint8 HWC images
+    assert d["roofline"]["traffic"]["measured"] is False
+    rv = d["roofline_vote"]
+    assert {"layer_ms", "tests", "tests_per_s", "alg_hbm_gbs", "alg_hbm_frac", "issue_frac"} <= set(rv)
+    c4 = d["config4"]
+    assert {"value", "e2e", "roofline_vote", "workload"} <= set(c4) and "with_mean" in c4["workload"]
+    assert c4["e2e"]["d2h_bytes_per_step"] == 16 * 9 * 2 * 4 * 3                   # keypoints + covariances
+
+
 def test_committed_gpu_snapshot_has_the_contract_keys():
     d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1_final.json")))
     assert BASE_KEYS | {"gpu_launches", "clocks", "roofline", "cpu_baseline"} <= set(d)
