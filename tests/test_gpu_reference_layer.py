@@ -151,3 +151,38 @@ def test_covariance_fixed_seed_parity():
     print(f"\n[reference-layer gap] covariance: max abs {gap.max().item():.3e}, "
           f"max rel {(gap / ref_cov.abs().clamp_min(1e-6)).max().item():.3e}, |cov| max {ref_cov.abs().max().item():.3e}")
     assert torch.allclose(cov, ref_cov, atol=1e-4, rtol=1e-4)
+
+
+def _cov_vs_reference_layer(masks, fields, hn, min_hyp, thresh, max_num, seed):
+    mask, vertex = _dev_inputs(masks, fields)
+    torch.manual_seed(seed)
+    mean = rv.ransac_voting_layer_v3(mask, vertex, hn, inlier_thresh=thresh, max_num=max_num)
+    rec = []
+    torch.manual_seed(seed + 1)
+    _, ref_cov = ref_cuda.layer_cov_with_mean(mask, vertex, mean, round_hyp_num=hn, min_hyp_num=min_hyp,
+                                              inlier_thresh=thresh, max_num=max_num, record=rec)
+    torch.manual_seed(seed + 1)
+    _, cov, dbg = rv.estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=hn, min_hyp_num=min_hyp,
+                                                            inlier_thresh=thresh, max_num=max_num, return_debug=True)
+    for bi, r in enumerate(rec):
+        assert torch.equal(dbg["idxs"][bi], r["idxs"]), "RNG stream differs from the reference's"
+        assert torch.equal(dbg["counts"][bi].long(), r["counts"]), "inlier counts differ from the reference layer"
+    assert torch.allclose(cov, ref_cov, atol=1e-4, rtol=1e-4), (cov - ref_cov).abs().max().item()
+
+
+def test_config4_shape_fixed_seed_vs_reference_layer():
+    """BASELINE config 4 per image (K=9, 20000 px, v3(256) + with_mean(256, 4096), thresh 0.99) against the reference's
+    own kernels + torch ops under the same torch seed: samples, counts, keypoints, covariances."""
+    masks = np.stack([syn.disc_mask(20000)])
+    fields = np.stack([syn.planted_field(masks[0], 9, 4400, sigma=0.05)[0]])
+    _product_vs_reference_layer(masks, fields, 256, 0.99, label="config 4 shape, tn=20000, K=9, 256 hyp")
+    _cov_vs_reference_layer(masks, fields, 256, 4096, 0.99, 30000, seed=44)
+
+
+def test_config5_shape_fixed_seed_vs_reference_layer():
+    """BASELINE config 5 per image (K=17, 92160 px subsampled to ~30000 by the reference's own uniform_ draw,
+    v3(1024) + with_mean(1024, 1024))."""
+    masks = np.stack([syn.disc_mask(92160)])
+    fields = np.stack([syn.planted_field(masks[0], 17, 5500, sigma=0.05)[0]])
+    _product_vs_reference_layer(masks, fields, 1024, 0.99, max_num=30000, label="config 5 shape, 92160 px -> ~30000, K=17, 1024 hyp")
+    _cov_vs_reference_layer(masks, fields, 1024, 1024, 0.99, 30000, seed=55)
