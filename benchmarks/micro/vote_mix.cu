@@ -20,6 +20,9 @@ __device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %
 __device__ __forceinline__ void upk2(f32x2 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ float fma_sat(float a, float b, float c) { float r; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float min_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float min3_nan_abs(float a, float b, float c) { float r; asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(fabsf(b)), "f"(fabsf(c))); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ void count_if_gt(int &cnt, float a, float b)
 {
     asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "f"(a), "f"(b));
@@ -49,13 +52,76 @@ __global__ void __launch_bounds__(256) k_mix(int reps, float seed, float *out, l
         hx2[j] = pk2(hx[2 * j], hx[2 * j + 1]);
         hy2[j] = pk2(hy[2 * j], hy[2 * j + 1]);
     }
-    bool unc = false;
+    bool unc = false, unc1 = false, unc2 = false, unc3 = false;
     f32x2 acc2[HPL / 2];
     float accs[HPL];
     for (int j = 0; j < HPL / 2; ++j) acc2[j] = pk2(0.f, 0.f);
     for (int j = 0; j < HPL; ++j) accs[j] = 0.f;
+    float mab[HPL], mabB[HPL];
+    for (int j = 0; j < HPL; ++j) mab[j] = mabB[j] = 1e30f;
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
+        if (V >= 7 && V != 13) {
+#pragma unroll 2
+            for (int p = 0; p < PIX; p += 2) {
+                const float4 a0 = rec[3 * p], b0 = rec[3 * p + 1], c0 = rec[3 * p + 2];
+                const float4 a1 = rec[3 * p + 3], b1 = rec[3 * p + 4], c1 = rec[3 * p + 5];
+                const f32x2 AP0 = pk2(a0.x, a0.y), BP0 = pk2(a0.z, a0.w), CP0 = pk2(b0.x, b0.y), AM0 = pk2(b0.z, b0.w),
+                            BM0 = pk2(c0.x, c0.y), CM0 = pk2(c0.z, c0.w);
+                const f32x2 AP1 = pk2(a1.x, a1.y), BP1 = pk2(a1.z, a1.w), CP1 = pk2(b1.x, b1.y), AM1 = pk2(b1.z, b1.w),
+                            BM1 = pk2(c1.x, c1.y), CM1 = pk2(c1.z, c1.w);
+#pragma unroll
+                for (int j = 0; j < HPL / 2; ++j) {
+                    const f32x2 p0 = fma2(hx2[j], AP0, fma2(hy2[j], BP0, CP0));
+                    const f32x2 q0 = fma2(hx2[j], AM0, fma2(hy2[j], BM0, CM0));
+                    const f32x2 p1 = fma2(hx2[j], AP1, fma2(hy2[j], BP1, CP1));
+                    const f32x2 q1 = fma2(hx2[j], AM1, fma2(hy2[j], BM1, CM1));
+                    float p0a, p0b, q0a, q0b, p1a, p1b, q1a, q1b;
+                    upk2(p0, p0a, p0b);
+                    upk2(q0, q0a, q0b);
+                    upk2(p1, p1a, p1b);
+                    upk2(q1, q1a, q1b);
+                    float m0a, m0b, m1a, m1b;
+                    if (V == 11 || V == 15) {
+                        m0a = p0a - fabsf(q0a), m0b = p0b - fabsf(q0b), m1a = p1a - fabsf(q1a), m1b = p1b - fabsf(q1b);
+                    } else {
+                        m0a = min_nan(p0a, q0a), m0b = min_nan(p0b, q0b), m1a = min_nan(p1a, q1a), m1b = min_nan(p1b, q1b);
+                    }
+                    const float s0a = fma_sat(m0a, 18446744073709551616.f, nb2[2 * j]);
+                    const float s0b = fma_sat(m0b, 18446744073709551616.f, nb2[2 * j + 1]);
+                    const float s1a = fma_sat(m1a, 18446744073709551616.f, nb2[2 * j]);
+                    const float s1b = fma_sat(m1b, 18446744073709551616.f, nb2[2 * j + 1]);
+                    if (V == 8) {
+                        cnt[2 * j] += __float_as_int(s0a) + __float_as_int(s1a);
+                        cnt[2 * j + 1] += __float_as_int(s0b) + __float_as_int(s1b);
+                    } else if (V == 10) {
+                        acc2[j] = add2(acc2[j], pk2(s0a, s0b));
+                        acc2[j] = add2(acc2[j], pk2(s1a, s1b));
+                    } else {
+                        cntf[2 * j] += s0a;
+                        cntf[2 * j + 1] += s0b;
+                        cntf[2 * j] += s1a;
+                        cntf[2 * j + 1] += s1b;
+                    }
+                    if (V == 11 || V == 12) {
+                        // two accumulators per hypothesis, or ptxas fuses the nested mins back into FMNMX3
+                        mab[2 * j] = min_nan(mab[2 * j], fabsf(m0a));
+                        mabB[2 * j] = min_nan(mabB[2 * j], fabsf(m1a));
+                        mab[2 * j + 1] = min_nan(mab[2 * j + 1], fabsf(m0b));
+                        mabB[2 * j + 1] = min_nan(mabB[2 * j + 1], fabsf(m1b));
+                    } else if (V == 14) {
+                        accs[2 * j] += fma_sat(m0a, 18446744073709551616.f, bd[2 * j]);
+                        accs[2 * j + 1] += fma_sat(m0b, 18446744073709551616.f, bd[2 * j + 1]);
+                        accs[2 * j] += fma_sat(m1a, 18446744073709551616.f, bd[2 * j]);
+                        accs[2 * j + 1] += fma_sat(m1b, 18446744073709551616.f, bd[2 * j + 1]);
+                    } else if (V != 9) {
+                        mab[2 * j] = min3_nan_abs(mab[2 * j], m0a, m1a);
+                        mab[2 * j + 1] = min3_nan_abs(mab[2 * j + 1], m0b, m1b);
+                    }
+                }
+            }
+            continue;
+        }
 #pragma unroll 4
         for (int p = 0; p < PIX; ++p) {
             const float4 a = rec[3 * p], b = rec[3 * p + 1], c = rec[3 * p + 2];
@@ -98,7 +164,15 @@ __global__ void __launch_bounds__(256) k_mix(int reps, float seed, float *out, l
                         cntf[2 * j] += fma_sat(m0, 18446744073709551616.f, nb2[2 * j]);
                         cntf[2 * j + 1] += fma_sat(m1, 18446744073709551616.f, nb2[2 * j + 1]);
                     }
-                    if (V != 3) {
+                    if (V == 13) {
+                        if (j & 1) {
+                            unc2 |= !(fabsf(m0) > bd[2 * j]);
+                            unc3 |= !(fabsf(m1) > bd[2 * j + 1]);
+                        } else {
+                            unc |= !(fabsf(m0) > bd[2 * j]);
+                            unc1 |= !(fabsf(m1) > bd[2 * j + 1]);
+                        }
+                    } else if (V != 3) {
                         unc |= !(fabsf(m0) > bd[2 * j]);
                         unc |= !(fabsf(m1) > bd[2 * j + 1]);
                     }
@@ -107,8 +181,13 @@ __global__ void __launch_bounds__(256) k_mix(int reps, float seed, float *out, l
         }
     }
     const long long t1 = clock64();
-    float s = unc ? 1.f : 0.f;
-    for (int j = 0; j < HPL; ++j) s += cntf[j] + (float)cnt[j] + hx[j] + hy[j] + accs[j];
+    float s = (unc ? 1.f : 0.f) + (unc1 ? 2.f : 0.f) + (unc2 ? 4.f : 0.f) + (unc3 ? 8.f : 0.f);
+    for (int j = 0; j < HPL; ++j) s += cntf[j] + (float)cnt[j] + hx[j] + hy[j] + accs[j] + mab[j] + mabB[j];
+    for (int j = 0; j < HPL / 2; ++j) {
+        float x, y;
+        upk2(acc2[j], x, y);
+        s += x + y;
+    }
     for (int j = 0; j < HPL / 2; ++j) {
         float x, y;
         upk2(hx2[j], x, y);
@@ -163,10 +242,19 @@ int main()
     printf("cycles per test-warp (32 inlier tests) per SM sub-partition; columns: 2, 4, 6, 8 resident warps per sub-partition\n");
     run<0>("0: 4 FFMA + FADD + FSETP + IADD + FSETP(band)", sms);
     run<1>("1: 4 FFMA + FADD + FFMA.SAT + FADD + FSETP(band)", sms);
-    run<2>("2: 2 FFMA2 + FADD + FFMA.SAT + FADD + FSETP(band)  [shipped]", sms);
+    run<2>("2: 2 FFMA2 + FADD + FFMA.SAT + FADD + FSETP(band)  [k_vote2]", sms);
     run<3>("3: 2 FFMA2 + FADD + FFMA.SAT + FADD  (no band check)", sms);
     run<4>("4: 2 FFMA2 + FADD + FSETP + IADD + FSETP(band)", sms);
     run<5>("5: 2 FFMA2 only", sms);
     run<6>("6: 4 FFMA only", sms);
+    run<7>("7: 2 FFMA2 + FMNMX + FFMA.SAT + FADD + 1/2 FMNMX3  [k_vote3]", sms);
+    run<8>("8: 2 FFMA2 + FMNMX + FFMA.SAT + 1/2 IADD3 + 1/2 FMNMX3", sms);
+    run<9>("9: 2 FFMA2 + FMNMX + FFMA.SAT + FADD  (no band tracking)", sms);
+    run<10>("10: 2 FFMA2 + FMNMX + FFMA.SAT + 1/2 FADD2 + 1/2 FMNMX3", sms);
+    run<11>("11: 2 FFMA2 + FADD + FFMA.SAT + FADD + FMNMX(band)", sms);
+    run<12>("12: 2 FFMA2 + FMNMX + FFMA.SAT + FADD + FMNMX(band)", sms);
+    run<13>("13: = 2 with four band predicates", sms);
+    run<14>("14: 2 FFMA2 + FMNMX + 2 FFMA.SAT + 2 FADD", sms);
+    run<15>("15: 2 FFMA2 + FADD + FFMA.SAT + FADD + 1/2 FMNMX3", sms);
     return 0;
 }

@@ -807,6 +807,293 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
     }
 }
 
+// ------------------------------------------------------------------ the vote, deferred guard band
+// k_vote3 = k_vote2's decomposition (autonomous warps, ticket counter, private 3 KB staging, compact lists) with
+// a branch-free test loop.  Two changes to the arithmetic:
+//   * the two EDGES of the inlier cone are staged instead of (num, perp):  m+ = num - perp,  m- = num + perp,
+//     each one affine functional of h' -- (s -+ c).h' - (s -+ c).p' -- so  m = num - |perp| = min(m+, m-)  costs an
+//     FMNMX on the ALU pipe instead of an FADD on the (binding) FMA pipe;
+//   * the guard band is not tested per test: every hypothesis keeps  mab = min over the sub-chunk of |m|
+//     (one FMNMX3.NAN with |.| operand modifiers per TWO tests, ALU pipe), compared with B once per 64 pixels.  A
+//     hypothesis with mab <= B (or NaN) is re-walked by the whole warp -- 2 pixels per lane, the same fma chains
+//     bit for bit -- and exactly its in-band tests are decided by exact_inlier() and added with one RED.  The
+//     fast path never counts an in-band test (m <= B adds 0), so nothing is counted twice.
+// Per test: 2 FFMA2 + FMNMX + FFMA.SAT + FADD + 1/2 FMNMX3 = 5.5 issue slots, 6 FMA-pipe cycles, 3 ALU-pipe
+// cycles (k_vote2: 6 slots + the group branch, 7 FMA-pipe cycles, and a serial FSETP.OR predicate chain).
+// Error budget: the staged coefficients are fma(sn,ux,cs uy) etc. (<= 2u relative each), the constant one fma
+// more: < 10u (|h'|_1 + r1) all told, inside the 18u the band reserves for our side (vote_consts).
+__device__ __forceinline__ float min_nan(float a, float b)
+{
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float min3_nan_abs(float a, float b, float c)     // min(a, |b|, |c|), NaN if any is
+{
+    float r;
+    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(fabsf(b)), "f"(fabsf(c)));
+    return r;
+}
+
+// m from the two staged functionals: FORM 0 = cone edges (min), FORM 1/2 = num - |perp|
+template <int FORM>
+__device__ __forceinline__ float combine(float f1, float f2)
+{
+    return FORM == 0 ? min_nan(f1, f2) : f1 - fabsf(f2);
+}
+
+template <int HPL, int G, int FORM>
+__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
+    k_vote3(const unsigned *__restrict__ pix, const float2 *__restrict__ direct, const int *__restrict__ tn_arr, int npx,
+            int cap, int nb, int vn, int hn, int HT, int h0, const float2 *__restrict__ hyp, int *__restrict__ counts,
+            unsigned *__restrict__ ticket, float thresh, float sn, float cs, float beta, float b0, int items_per_warp)
+{
+    static_assert(G % 2 == 0 && VT_SUB % G == 0, "pixels are swept in pairs");
+    // per warp, per pixel 48 bytes: {ap,ap,bp,bp} {cp,cp,am,am} {bm,bm,cm,cm}:  m+ = ap hx' + bp hy' + cp, m- likewise
+    __shared__ float4 rec_all[VT_WARPS * 3 * VT_SUB];
+    __shared__ int seg_prefix[VT_MAX_B + 1];
+    __shared__ int s_seg;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int HC = 32 * HPL;
+    const int hcn = (hn + HC - 1) / HC;
+    if (tid == 0) {
+        long long px = 0;
+        for (int i = 0; i < nb; ++i) px += tn_arr[i];
+        const long long want = (long long)gridDim.x * VT_WARPS * items_per_warp;
+        int seg = 4096;
+        while (seg > 4 * VT_SUB && (px / seg + nb) * vn * hcn < want) seg >>= 1;
+        int acc = 0;
+        for (int i = 0; i < nb; ++i) {
+            seg_prefix[i] = acc;
+            acc += (tn_arr[i] + seg - 1) / seg;
+        }
+        seg_prefix[nb] = acc;
+        s_seg = seg;
+    }
+    __syncthreads();
+    const int SEG = s_seg;
+    const long long n_items = (long long)seg_prefix[nb] * vn * hcn;
+    const float qnan = __int_as_float(0x7fc00000);
+    const float finf = __int_as_float(0x7f800000);
+    float4 *rec = rec_all + warp * (3 * VT_SUB);
+    const uint32_t rec_u = ptx_smem_u32(rec);
+
+    for (;;) {
+        unsigned item_u = 0;
+        if (lane == 0) item_u = atomicAdd(ticket, 1u);
+        const long long it = (long long)__shfl_sync(0xffffffffu, item_u, 0);
+        if (it >= n_items) break;
+        const int hc = (int)(it % hcn);
+        const long long r = it / hcn;
+        const int k = (int)(r % vn);
+        const int g = (int)(r / vn);
+        int lo = 0, hi = nb;                         // b with seg_prefix[b] <= g < seg_prefix[b+1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (seg_prefix[mid] <= g) lo = mid; else hi = mid;
+        }
+        const int b = lo;
+        const int tn = tn_arr[b];
+        const int t0 = (g - seg_prefix[b]) * SEG;
+        const int len = min(SEG, tn - t0);
+        const unsigned *pix_t = pix + (size_t)b * npx + t0;
+        const float2 *dir_t = direct + ((size_t)b * vn + k) * cap + t0;
+
+        const int hbase = hc * HC;
+        const float2 *hyp_row = hyp + ((size_t)b * vn + k) * HT + h0;
+        int *cnt_row = counts + ((size_t)b * vn + k) * HT + h0;
+        float2 hraw[HPL];
+#pragma unroll
+        for (int j = 0; j < HPL; ++j) {
+            const int h = hbase + j * 32 + lane;
+            hraw[j] = (h < hn) ? __ldg(hyp_row + h) : make_float2(0.f, 0.f);
+        }
+        unsigned pp[2];
+        float2 pn[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int i = e * 32 + lane;
+            pp[e] = (i < len) ? __ldg(pix_t + i) : 0u;
+            pn[e] = (i < len) ? __ldg(dir_t + i) : make_float2(0.f, 0.f);
+        }
+        int xmin = 0x7fffffff, xmax = -1;
+        for (int i = lane; i < len; i += 32) {
+            const int x = (int)(__ldg(pix_t + i) & 0xffffu);
+            xmin = min(xmin, x);
+            xmax = max(xmax, x);
+        }
+        xmin = __reduce_min_sync(0xffffffffu, xmin);
+        xmax = __reduce_max_sync(0xffffffffu, xmax);
+        const int ymin = (int)(__ldg(pix_t) >> 16), ymax = (int)(__ldg(pix_t + len - 1) >> 16);
+        const float xc = (float)((xmin + xmax) >> 1), yc = (float)((ymin + ymax) >> 1);
+        const float r1 = (float)(max((int)xc - xmin, xmax - (int)xc) + max((int)yc - ymin, ymax - (int)yc));
+
+        // centred hypothesis and its band; ONE definition, used by the set-up and by the re-walk
+        auto centre = [&](float2 hp, float &hxv, float &hyv, float &bd) {
+            hxv = hp.x - xc;
+            hyv = hp.y - yc;
+            bd = fmaf(beta, fabsf(hxv) + fabsf(hyv) + r1, b0);
+            if (!(bd < 1e18f)) bd = qnan;           // absurdly far / non-finite: every test exact
+        };
+        f32x2 hx2[HPL / 2], hy2[HPL / 2];
+        float nb2[HPL], cnt[HPL], mab[HPL];         // -band * 2^64, count (exact small integers in fp32), min |m|
+        float mabB[FORM == 1 ? HPL : 1];            // FORM 1: odd pixels' minimum (two 2-input FMNMX instead of one FMNMX3)
+#pragma unroll
+        for (int j = 0; j < HPL; j += 2) {
+            float hxv[2], hyv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int h = hbase + (j + e) * 32 + lane;
+                float bd = -1.f;                    // padding: never in band, count discarded
+                hxv[e] = hyv[e] = 0.f;
+                if (h < hn) centre(hraw[j + e], hxv[e], hyv[e], bd);
+                nb2[j + e] = -bd * VT_SCALE;
+                cnt[j + e] = 0.f;
+                mab[j + e] = finf;
+                if (FORM == 1) mabB[j + e] = finf;
+            }
+            hx2[j / 2] = pk2(hxv[0], hxv[1]);
+            hy2[j / 2] = pk2(hyv[0], hyv[1]);
+        }
+
+        for (int c0 = 0; c0 < len; c0 += VT_SUB) {
+            const int clen = min(VT_SUB, len - c0);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = e * 32 + lane;
+                const unsigned p = pp[e];
+                const float2 n = pn[e];
+                const float xr = (float)(int)(p & 0xffff) - xc, yr = (float)(int)(p >> 16) - yc;
+                const float n2 = fmaf(n.x, n.x, n.y * n.y);
+                const float rinv = rsqrtf(n2);
+                const float ux = n.x * rinv, uy = n.y * rinv;
+                float ap, bp, am, bm;
+                if (FORM == 0) {                    // cone edges  s - c,  s + c   (c = cs (-uy, ux))
+                    ap = fmaf(sn, ux, cs * uy), bp = fmaf(sn, uy, -(cs * ux));
+                    am = fmaf(sn, ux, -(cs * uy)), bm = fmaf(sn, uy, cs * ux);
+                } else {                            // s and c themselves:  m = f1 - |f2|
+                    ap = sn * ux, bp = sn * uy;
+                    am = -cs * uy, bm = cs * ux;
+                }
+                float cp = -fmaf(ap, xr, bp * yr), cm = -fmaf(am, xr, bm * yr);
+                if (!(n2 > 1e-11f && n2 < 1e30f)) ap = bp = am = bm = cp = cm = qnan;   // -> exact path
+                if (i >= clen) {                    // padding pixel: m = -1e30, never counted, never in band
+                    ap = bp = am = bm = 0.f;
+                    cp = cm = -1e30f;
+                }
+                rec[3 * i] = make_float4(ap, ap, bp, bp);
+                rec[3 * i + 1] = make_float4(cp, cp, am, am);
+                rec[3 * i + 2] = make_float4(bm, bm, cm, cm);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = c0 + VT_SUB + e * 32 + lane;
+                pp[e] = (i < len) ? __ldg(pix_t + i) : 0u;
+                pn[e] = (i < len) ? __ldg(dir_t + i) : make_float2(0.f, 0.f);
+            }
+            // ---- sweep, two pixels at a time (branch-free)
+            const int cend = (clen + G - 1) / G * G;
+            for (int i0 = 0; i0 < cend; i0 += G) {
+                const uint32_t base = rec_u + (uint32_t)i0 * 48u;
+#pragma unroll
+                for (int u = 0; u < G; u += 2) {
+                    f32x2 AP0, BP0, CP0, AM0, BM0, CM0, AP1, BP1, CP1, AM1, BM1, CM1;
+                    lds_2x64(base + (uint32_t)u * 48u, AP0, BP0);
+                    lds_2x64(base + (uint32_t)u * 48u + 16u, CP0, AM0);
+                    lds_2x64(base + (uint32_t)u * 48u + 32u, BM0, CM0);
+                    lds_2x64(base + (uint32_t)u * 48u + 48u, AP1, BP1);
+                    lds_2x64(base + (uint32_t)u * 48u + 64u, CP1, AM1);
+                    lds_2x64(base + (uint32_t)u * 48u + 80u, BM1, CM1);
+#pragma unroll
+                    for (int j = 0; j < HPL / 2; ++j) {
+                        const f32x2 p0 = fma2(hx2[j], AP0, fma2(hy2[j], BP0, CP0));
+                        const f32x2 q0 = fma2(hx2[j], AM0, fma2(hy2[j], BM0, CM0));
+                        const f32x2 p1 = fma2(hx2[j], AP1, fma2(hy2[j], BP1, CP1));
+                        const f32x2 q1 = fma2(hx2[j], AM1, fma2(hy2[j], BM1, CM1));
+                        float p0a, p0b, q0a, q0b, p1a, p1b, q1a, q1b;
+                        upk2(p0, p0a, p0b);
+                        upk2(q0, q0a, q0b);
+                        upk2(p1, p1a, p1b);
+                        upk2(q1, q1a, q1b);
+                        const float m0a = combine<FORM>(p0a, q0a), m0b = combine<FORM>(p0b, q0b);
+                        const float m1a = combine<FORM>(p1a, q1a), m1b = combine<FORM>(p1b, q1b);
+                        cnt[2 * j] += fma_sat(m0a, VT_SCALE, nb2[2 * j]);
+                        cnt[2 * j + 1] += fma_sat(m0b, VT_SCALE, nb2[2 * j + 1]);
+                        cnt[2 * j] += fma_sat(m1a, VT_SCALE, nb2[2 * j]);
+                        cnt[2 * j + 1] += fma_sat(m1b, VT_SCALE, nb2[2 * j + 1]);
+                        if (FORM == 1) {
+                            mab[2 * j] = min_nan(mab[2 * j], fabsf(m0a));
+                            mabB[2 * j] = min_nan(mabB[2 * j], fabsf(m1a));
+                            mab[2 * j + 1] = min_nan(mab[2 * j + 1], fabsf(m0b));
+                            mabB[2 * j + 1] = min_nan(mabB[2 * j + 1], fabsf(m1b));
+                        } else {
+                            mab[2 * j] = min3_nan_abs(mab[2 * j], m0a, m1a);
+                            mab[2 * j + 1] = min3_nan_abs(mab[2 * j + 1], m0b, m1b);
+                        }
+                    }
+                }
+            }
+            // ---- guard band, once per sub-chunk: which of my hypotheses came within B of a cone edge?
+            unsigned fl = 0;
+#pragma unroll
+            for (int j = 0; j < HPL; ++j) {
+                const float bd = nb2[j] * (-1.f / VT_SCALE);      // exact (power of two)
+                if (!(mab[j] > bd)) fl |= 1u << j;
+                mab[j] = finf;
+                if (FORM == 1) {
+                    if (!(mabB[j] > bd)) fl |= 1u << j;
+                    mabB[j] = finf;
+                }
+            }
+            unsigned lanes = __ballot_sync(0xffffffffu, fl != 0);
+            while (lanes) {                                        // rare: ~1 hypothesis in 1000 per sub-chunk
+                const int src = __ffs(lanes) - 1;
+                lanes &= lanes - 1;
+                unsigned fm = __shfl_sync(0xffffffffu, fl, src);
+                while (fm) {
+                    const int j = __ffs(fm) - 1;
+                    fm &= fm - 1;
+                    const int h = hbase + j * 32 + src;
+                    if (h >= hn) continue;
+                    const float2 hp = __ldg(hyp_row + h);
+                    float hxs, hys, bd;
+                    centre(hp, hxs, hys, bd);
+                    int add = 0;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int pi = e * 32 + lane;
+                        if (pi < clen) {
+                            const float4 ra = rec[3 * pi], rb = rec[3 * pi + 1], rc = rec[3 * pi + 2];
+                            const float mp = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
+                            const float mm = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
+                            const float m = combine<FORM>(mp, mm);
+                            if (!(fabsf(m) > bd)) {
+                                const unsigned p = __ldg(pix_t + c0 + pi);
+                                const float2 nraw = __ldg(dir_t + c0 + pi);
+                                add += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hp.x, hp.y, thresh)
+                                           ? 1
+                                           : 0;
+                            }
+                        }
+                    }
+                    add = __reduce_add_sync(0xffffffffu, add);
+                    if (lane == 0 && add) atomicAdd(cnt_row + h, add);
+                }
+            }
+            __syncwarp();
+        }
+
+#pragma unroll
+        for (int j = 0; j < HPL; ++j) {
+            const int h = hbase + j * 32 + lane;
+            const int c = (int)cnt[j];
+            if (h < hn && c) atomicAdd(cnt_row + h, c);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ argmax + refit
 __device__ __forceinline__ double warp_sum_d(double v)
 {
@@ -1425,7 +1712,8 @@ int launch_gen_hyp(const Samples &sm, int rng_stream, int b, int h, int w, int v
 //   the numerator with its inner product, one multiply, one division) plus u rad from rounding d;
 //   in m = |d| sin(theta_T - |theta|) that is a band of (eta T / sin(theta_T) + u) |d|;
 //   ours: unit vector, functionals, centring and the two fma chains: < 8 u (|h'|_1 + r1).
-// beta = 1.25 (1.1 eta T / s + u) + 16 u; b0 = 1e-5 covers |d| < 1e-6 (norm test of the reference).
+//   (k_vote3's edge functionals: < 10 u.)
+// beta = 1.25 (1.1 eta T / s + u) + 18 u; b0 = 1e-5 covers |d| < 1e-6 (norm test of the reference).
 // Outside T in [0.05, 1 - 1e-6] (and for NaN) beta is NaN: every test takes the exact path.
 struct VoteConsts {
     float sn, cs, beta, b0;
@@ -1439,7 +1727,7 @@ VoteConsts vote_consts(float thresh)
         const double eta = (7.0 + 1.0 / T) * u * 1.05;
         c.sn = (float)sn;
         c.cs = (float)T;
-        c.beta = (float)(1.25 * (1.1 * eta * T / sn + u) + 16.0 * u);
+        c.beta = (float)(1.25 * (1.1 * eta * T / sn + u) + 18.0 * u);
     } else {
         c.sn = 0.f;
         c.cs = 1.f;
@@ -1455,14 +1743,14 @@ int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int
 {
     const int npx = h * w;
     static const int impl = [] {
-        const char *e = getenv("PVNET_VOTE_IMPL");     // tuning knob: 0 = round-1 kernel (k_vote), 2 = k_vote2 (default)
-        return e ? atoi(e) : 2;
+        const char *e = getenv("PVNET_VOTE_IMPL");     // tuning knob: 0 = round-1 kernel (k_vote), 2 = k_vote2, 3 = k_vote3 (default)
+        return e ? atoi(e) : 3;
     }();
     static const int hpl_env = [] {
         const char *e = getenv("PVNET_VOTE_HPL");      // tuning knob: hypotheses per lane of k_vote2 (4 or 8)
         return e ? atoi(e) : 8;
     }();
-    const int HPL = (impl == 2 && hpl_env == 8 && hn > 128) ? 8 : 4;
+    const int HPL = (impl >= 2 && hpl_env == 8 && hn > 128) ? 8 : 4;
     static const int ctas_per_sm = [] {
         const char *e = getenv("PVNET_VOTE_CTAS");     // tuning knob: resident vote CTAs per SM
         return e ? atoi(e) : 0;
@@ -1488,12 +1776,39 @@ int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int
     const unsigned grid = (unsigned)(pvnet::sm_count() * per_sm);
     PV_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(unsigned), s));
     static const int grp = [] {
-        const char *e = getenv("PVNET_VOTE_GROUP");    // tuning knob: pixels per guard-band check (4 or 8)
-        return e ? atoi(e) : 8;
+        const char *e = getenv("PVNET_VOTE_GROUP");    // tuning knob: pixels per unrolled step (4 or 8); k_vote2: per band check
+        return e ? atoi(e) : (impl == 3 ? 4 : 8);
     }();
 #define VOTE2(H_, G_)                                                                                                  \
     k_vote2<H_, G_><<<grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tn, npx, ws.cap, b, vn, hn, HT, h0, ws.hyp, ws.counts, \
                                                 ws.ticket, thresh, vc.sn, vc.cs, vc.beta, vc.b0)
+    static const int items_pw = [] {
+        const char *e = getenv("PVNET_VOTE_ITEMS");    // tuning knob: work items per resident warp the segment length aims at
+        return e ? atoi(e) : 6;
+    }();
+    static const int form = [] {
+        const char *e = getenv("PVNET_VOTE_FORM");     // tuning knob: arithmetic form of k_vote3 (0, 1, 2: see the kernel)
+        return e ? atoi(e) : 2;
+    }();
+#define VOTE3F(H_, G_, F_)                                                                                             \
+    k_vote3<H_, G_, F_><<<grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tn, npx, ws.cap, b, vn, hn, HT, h0, ws.hyp,     \
+                                                    ws.counts, ws.ticket, thresh, vc.sn, vc.cs, vc.beta, vc.b0, items_pw)
+#define VOTE3(H_, G_)                                                                                                  \
+    do {                                                                                                               \
+        if (form == 1) VOTE3F(H_, G_, 1);                                                                              \
+        else if (form == 2) VOTE3F(H_, G_, 2);                                                                         \
+        else VOTE3F(H_, G_, 0);                                                                                        \
+    } while (0)
+    if (impl == 3) {
+        if (HPL == 8 && grp == 8) VOTE3(8, 8);
+        else if (HPL == 8) VOTE3(8, 4);
+        else if (grp == 8) VOTE3(4, 8);
+        else VOTE3(4, 4);
+        PV_LAUNCHED("k_vote3");
+        return PVNET_OK;
+    }
+#undef VOTE3
+#undef VOTE3F
     if (HPL == 8 && grp == 8) VOTE2(8, 8);
     else if (HPL == 8) VOTE2(8, 4);
     else if (grp == 8) VOTE2(4, 8);
