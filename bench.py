@@ -46,8 +46,9 @@ if ROOT not in sys.path:
 
 H, W, K_KP, HYP, BATCH = 480, 640, 9, 256, 16
 THRESH = 0.99
-VOTE_ISSUE_SLOTS_PER_TEST = 6.0   # k_vote2's inner loop in SASS: 2 FFMA2 (per 2 tests: 4) + FADD + FFMA.SAT + FADD + FSETP
-VOTE_FMA_CYCLES_PER_TEST = 6.9    # the same mix on the FMA pipe (FFMA2 = 2 cycles): measured, profiles/r02_micro_vote_mix.txt
+VOTE_ISSUE_SLOTS_PER_TEST = 5.5   # k_vote3's sweep in SASS: 2 FFMA2 + FADD + FFMA.SAT + FADD + 1/2 FMNMX3 per test (+0.4 LDS/loop)
+VOTE_MICRO_CYCLES_PER_TEST = 7.99  # that mix alone, in registers, at the kernel's 4 resident warps per sub-partition
+#                                    (profiles/r02_micro_vote_mix.txt row 15; 7.00 at 6 warps): what the SM sustains
 
 # BASELINE.json configs that bench.py can run as the headline (per-GPU batch: weak scaling)
 CONFIGS = {
@@ -280,23 +281,24 @@ def vote_roofline(torch, pipe, x, peaks, clocks, cfg):
     clk = ((clocks or {}).get("sm_mhz") or 1900.0) * 1e6
     sms = torch.cuda.get_device_properties(x.device).multi_processor_count
     issue_roof = sms * 128 * clk / VOTE_ISSUE_SLOTS_PER_TEST
-    fma_roof = sms * 128 * clk / VOTE_FMA_CYCLES_PER_TEST
+    micro_roof = sms * 128 * clk / VOTE_MICRO_CYCLES_PER_TEST
     b_alg = b * (h * w * 1 + k * 24 + (hn + hnt) * k * 8) + float(tn.sum()) * k * 8
     hbm = peaks.get("hbm_gbs") or 6575.0
     return {
-        "kernel": "k_vote2 inside pvnet_ransac_voting_pipeline (whole layer timed: compaction, gather, hypotheses, "
+        "kernel": "k_vote3 inside pvnet_ransac_voting_pipeline (whole layer timed: compaction, gather, hypotheses, "
                   "vote, refit" + (", covariance)" if cov else ")"),
         "layer_ms": round(ms, 4), "tests": int(tests), "tests_per_s": round(tests / (ms * 1e-3), 1),
-        "issue_slots_per_test": VOTE_ISSUE_SLOTS_PER_TEST, "fma_pipe_cycles_per_test": VOTE_FMA_CYCLES_PER_TEST,
+        "issue_slots_per_test": VOTE_ISSUE_SLOTS_PER_TEST, "micro_cycles_per_32_tests": VOTE_MICRO_CYCLES_PER_TEST,
         "sm_clock_mhz": round(clk / 1e6, 1),
         "issue_frac": round(tests / (ms * 1e-3) / issue_roof, 4),
-        "fma_pipe_frac": round(tests / (ms * 1e-3) / fma_roof, 4), "bound": "fp32 FMA pipe",
+        "micro_frac": round(tests / (ms * 1e-3) / micro_roof, 4), "bound": "fp32 issue",
         "alg_bytes": int(b_alg), "alg_hbm_gbs": round(b_alg / (ms * 1e-3) / 1e9, 2),
         "alg_hbm_frac": round(b_alg / (ms * 1e-3) / 1e9 / hbm, 5), "hbm_peak_gbs": hbm,
         "fg_px_per_image": round(float(tn.mean()), 1),
-        "note": "whole layer timed (10 launches); FP32-pipe bound by construction (SURVEY 8d): the [hn,K,tn] inlier tensor the "
-                "reference streams through HBM never exists here; fractions are of SMs x 128 lanes x clock / (slots or FMA-pipe "
-                "cycles per test); the kernel's own ncu DRAM bytes (1.00x its algorithmic bytes) are in profiles/r02_ncu_vote.md",
+        "note": "whole layer timed (10 launches); FP32-issue bound by construction (SURVEY 8d): the [hn,K,tn] inlier tensor the "
+                "reference streams through HBM never exists here; issue_frac = tests/s over SMs x 128 lanes x clock / 5.5 slots, "
+                "micro_frac = over what the instruction mix alone sustains in a register-only microbenchmark at the same "
+                "occupancy; the kernel's own ncu DRAM bytes (1.00x its algorithmic bytes) are in profiles/r02_ncu_vote.md",
     }
 
 

@@ -123,8 +123,8 @@ def vote(rep, md, bench_json=None):
         rv = json.load(open(bench_json))["roofline_vote"]
         fg = rv["fg_px_per_image"]
         tests = int(16 * fg * k * hn)                       # the kernel's own tests (the refit's +1 vote is k_refit's)
-    lines = [f"# ncu --set full, k_vote2 inside one bench step (16 images x ~{fg:.0f} px, {hn} hyp, K={k})", "",
-             "`ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_vote2 -c 1 python "
+    lines = [f"# ncu --set full, k_vote3 inside one bench step (16 images x ~{fg:.0f} px, {hn} hyp, K={k})", "",
+             "`ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_vote3 -c 1 python "
              "benchmarks/profile_step.py 1` -> `python benchmarks/ncu_tables.py vote ...`", "",
              f"Kernel: `{r[col['Kernel Name']][:100]}`", "", "| metric | value | unit |", "|---|---|---|"]
     for m in VOTE_METRICS:

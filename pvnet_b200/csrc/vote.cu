@@ -14,7 +14,7 @@
 //                   major); every later kernel streams these coalesced lists instead of
 //                   gathering sectors from the field again
 //   k_gen_hyp       ray-ray intersections, bit-exact op sequence of the reference
-//   k_vote2         persistent kernel of autonomous warps: a warp takes (image, keypoint, 256
+//   k_vote3         persistent kernel of autonomous warps: a warp takes (image, keypoint, 256
 //                   hypotheses, pixel segment), stages 64 pixels at a time in its private
 //                   shared memory as the two edge functionals of the inlier cone, keeps 8
 //                   hypotheses per lane and their counts in registers; the [hn,vn,tn]
@@ -29,13 +29,13 @@
 // theta the angle between the pixel's direction n and d = hypothesis - pixel, that is
 // |theta| < theta_T (cos theta_T = thresh), i.e.
 //     m = |d| sin(theta_T - |theta|) = sin(theta_T) (d.u) - cos(theta_T) |d.v| > 0,
-// u = n/|n|, v = (-u_y, u_x): two linear functionals of the hypothesis per pixel.  k_vote2
-// evaluates them in tile-centred coordinates (4 FFMA), m (1 FADD), and compares with a
+// u = n/|n|, v = (-u_y, u_x): two linear functionals of the hypothesis per pixel.  k_vote3
+// evaluates them in segment-centred coordinates (4 FMA as 2 FFMA2), m (1 FADD), and compares with a
 // per-hypothesis guard band B (DESIGN.md section 3 bounds both the reference's rounding,
 // <= (7 + 1/T) ulp on the cosine, and ours): m > B counts, |m| <= B (or NaN) is re-decided by
 // exact_inlier(), the reference's own instruction sequence.  Tests outside the band cannot
 // change sign under either rounding, so the counts are identical to the reference's, at
-// ~8 issue slots per test (13.6 in round 1's num*|num| - T^2 d^2 form, kept as k_vote for A/B).
+// 5.5 issue slots per test (13.6 in round 1's num*|num| - T^2 d^2 form, kept as k_vote for A/B).
 #include "common.cuh"
 
 #include <cfloat>
@@ -535,26 +535,38 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 4)
 }
 
 // ------------------------------------------------------------------ the vote (round 2)
-// Same decomposition as k_vote -- persistent CTAs over (pixel tile, keypoint, hypothesis group);
-// warps split wh (hypothesis groups of 32*HPL) x wp (contiguous pixel chunks); each lane owns HPL
-// hypotheses -- but the tile is staged from the COMPACT lists (coalesced 4-/8-byte streams) as the
-// two edge functionals of the inlier cone in tile-centred coordinates,
+// k_vote3: persistent kernel of AUTONOMOUS WARPS.  A warp pulls (image, keypoint, group of 32*HPL hypotheses,
+// pixel segment) items from a ticket counter, keeps its hypotheses and counts in registers for the whole segment,
+// stages 64 pixels at a time from the COMPACT lists (coalesced 4-/8-byte streams) into its private 3 KB of shared
+// memory (next sub-chunk prefetched into registers during the sweep; only __syncwarp) and publishes the counts
+// with one RED per hypothesis.  No CTA barrier after the prologue.  (An earlier form with CTA-wide tiles spent 48 %
+// of its stall samples outside the test loop: dependent global loads of staging / hypothesis set-up, three CTA
+// barriers per item.)
+//
+// The test.  Staged per pixel: the two edge functionals of the inlier cone in segment-centred coordinates,
 //     s = sin(theta_T) u,  c = cos(theta_T) v:   num = h'.s - p'.s,   perp = h'.c - p'.c,
 // so one test is  num = fma(hx', sx, fma(hy', sy, -s.p'));  perp = fma(hx', cx, fma(hy', cy, -c.p'));
-// m = num - |perp|;  inlier if m > B;  uncertain if !(|m| > B).
-// B = beta (|hx'| + |hy'| + r1) + b0 per hypothesis and tile (|d| <= |h'|_1 + r1): beta carries the
+// m = num - |perp|;  inlier if m > B;  IN BAND if !(|m| > B).
+// B = beta (|hx'| + |hy'| + r1) + b0 per hypothesis and segment (|d| <= |h'|_1 + r1): beta carries the
 // reference's rounding band (7 + 1/T) ulp T / sin(theta_T) and ours, see DESIGN.md section 3.
-// Uncertain tests are not counted by the fast path; a warp whose lanes flag any re-walks the 4-pixel
-// group and decides exactly those with exact_inlier() on the raw values.
 //
-// Instruction mix (ncu on the first version -- 4 FFMA + FADD + 2 FSETP + IADD per test -- showed the
-// half-rate ALU pipe busier than the FMA pipe and 29 % of the issue slots lost to its bursts):
-//   * two hypotheses ride in one FFMA2 (fma.rn.f32x2): same FMA-pipe time, half the issue slots;
-//     the pixel operands are stored pre-duplicated so a pair comes straight out of LDS.128;
-//   * the count is taken on the FMA pipe:  cnt += fma.sat(m, 2^64, -B 2^64)  is exactly 1 when
-//     m > B and exactly 0 otherwise (the product is exact, |m - B| >= ulp(B) >= 2^-23 b0 when they
-//     differ, NaN saturates to 0), so the ALU pipe only sees the one FSETP of the guard band.
-// Per test: 2 issue slots of FFMA2 + FADD + FFMA.SAT + FADD + FSETP = 6 slots, 7 FMA-pipe cycles.
+// Instruction mix (profiles/r02_micro_vote_mix.txt: every step below is a measured row):
+//   * two hypotheses ride in one FFMA2 (fma.rn.f32x2): half the issue slots of 4 FFMA; the pixel operands are
+//     stored pre-duplicated so a pair comes straight out of LDS.128;
+//   * the count is taken on the FMA pipes:  cnt += fma.sat(m, 2^64, -B 2^64)  is exactly 1 when m > B and exactly
+//     0 otherwise (the product is exact, |m - B| >= ulp(B) >= 2^-23 b0 when they differ, NaN saturates to 0);
+//   * the guard band is NOT tested per test (one FSETP.OR per test made a serial predicate chain and a branch per
+//     pixel group: 8.7 vs 8.0 cycles per 32 tests in the microbenchmark at our 4 warps per sub-partition, and
+//     4.57 vs 3.96 ms on the config-4 layer): every hypothesis keeps  mab = min over the sub-chunk of |m|  -- one
+//     FMNMX3.NAN with |.| operand modifiers per TWO tests, on the otherwise idle ALU pipe -- compared with B
+//     once per 64 pixels.  A hypothesis with !(mab > B) is re-walked by the whole warp (2 pixels per lane, the
+//     same fma chains bit for bit) and exactly its in-band tests are decided by exact_inlier() on the raw values
+//     and added with one RED.  The fast path never counts an in-band test (m <= B adds 0): nothing counted twice.
+// Per test: 2 FFMA2 + FADD + FFMA.SAT + FADD + 1/2 FMNMX3 = 5.5 issue slots, no branch inside a sub-chunk.
+// Measured and rejected on the way (config-4 layer, ms, planted / random field): staging the cone EDGES so that
+// m = min(m+, m-) is an FMNMX (4.24 / 4.06: the ALU pipe is the scarcer one); two 2-input FMNMX instead of the
+// FMNMX3 (4.18 / 4.09); packed FADD2 count adds (3.83 / 3.77 at 4 pixels per step, 3.69 / 3.63 at 8: within
+// 1 % of this form's 3.72 / 3.66); HPL = 4 with 3 CTAs per SM (4.24 / 4.17).
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float a, float b)
 {
@@ -584,21 +596,22 @@ __device__ __forceinline__ void lds_2x64(uint32_t addr, f32x2 &a, f32x2 &b)
 }
 constexpr float VT_SCALE = 18446744073709551616.f;     // 2^64
 
-// Work decomposition (second ncu pass: with CTA-wide tiles, 48 % of the stall samples sat OUTSIDE the
-// test loop -- the dependent global loads of staging / hypothesis set-up, and three CTA barriers per
-// item): warps are autonomous.  A warp pulls (image, keypoint, group of 32*HPL hypotheses, pixel
-// segment) items from a ticket counter, keeps its hypotheses and counts in registers for the whole
-// segment, stages 64 pixels at a time into its PRIVATE 3 KB of shared memory (next sub-chunk
-// prefetched into registers during the sweep; only __syncwarp), and publishes the counts with one RED
-// per hypothesis.  No CTA barrier after the prologue.
 constexpr int VT_SUB = 64;        // pixels per staged sub-chunk (2 per lane)
+
+__device__ __forceinline__ float min3_nan_abs(float a, float b, float c)     // min(a, |b|, |c|), NaN if any is
+{
+    float r;
+    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(fabsf(b)), "f"(fabsf(c)));
+    return r;
+}
 
 template <int HPL, int G>
 __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
-    k_vote2(const unsigned *__restrict__ pix, const float2 *__restrict__ direct, const int *__restrict__ tn_arr, int npx,
+    k_vote3(const unsigned *__restrict__ pix, const float2 *__restrict__ direct, const int *__restrict__ tn_arr, int npx,
             int cap, int nb, int vn, int hn, int HT, int h0, const float2 *__restrict__ hyp, int *__restrict__ counts,
-            unsigned *__restrict__ ticket, float thresh, float sn, float cs, float beta, float b0)
+            unsigned *__restrict__ ticket, float thresh, float sn, float cs, float beta, float b0, int items_per_warp)
 {
+    static_assert(G % 2 == 0 && VT_SUB % G == 0, "pixels are swept in pairs");
     // per warp, per pixel 48 bytes: {sx,sx,sy,sy} {ns,ns,cx,cx} {cy,cy,nc,nc}
     __shared__ float4 rec_all[VT_WARPS * 3 * VT_SUB];
     __shared__ int seg_prefix[VT_MAX_B + 1];
@@ -608,256 +621,8 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
     const int HC = 32 * HPL;
     const int hcn = (hn + HC - 1) / HC;
     if (tid == 0) {
-        // pixels per item: the largest power-of-two multiple of VT_SUB (<= 4096) that still leaves ~6 items per
-        // resident warp, so hypotheses are set up rarely and the tail stays short
-        long long px = 0;
-        for (int i = 0; i < nb; ++i) px += tn_arr[i];
-        const long long want = (long long)gridDim.x * VT_WARPS * 6;
-        int seg = 4096;
-        while (seg > 4 * VT_SUB && (px / seg + nb) * vn * hcn < want) seg >>= 1;
-        int acc = 0;
-        for (int i = 0; i < nb; ++i) {
-            seg_prefix[i] = acc;
-            acc += (tn_arr[i] + seg - 1) / seg;
-        }
-        seg_prefix[nb] = acc;
-        s_seg = seg;
-    }
-    __syncthreads();
-    const int SEG = s_seg;
-    const long long n_items = (long long)seg_prefix[nb] * vn * hcn;
-    const float qnan = __int_as_float(0x7fc00000);
-    float4 *rec = rec_all + warp * (3 * VT_SUB);
-    const uint32_t rec_u = ptx_smem_u32(rec);
-
-    for (;;) {
-        unsigned item_u = 0;
-        if (lane == 0) item_u = atomicAdd(ticket, 1u);
-        const long long it = (long long)__shfl_sync(0xffffffffu, item_u, 0);
-        if (it >= n_items) break;
-        const int hc = (int)(it % hcn);
-        const long long r = it / hcn;
-        const int k = (int)(r % vn);
-        const int g = (int)(r / vn);
-        int lo = 0, hi = nb;                         // b with seg_prefix[b] <= g < seg_prefix[b+1]
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (seg_prefix[mid] <= g) lo = mid; else hi = mid;
-        }
-        const int b = lo;
-        const int tn = tn_arr[b];
-        const int t0 = (g - seg_prefix[b]) * SEG;
-        const int len = min(SEG, tn - t0);
-        const unsigned *pix_t = pix + (size_t)b * npx + t0;
-        const float2 *dir_t = direct + ((size_t)b * vn + k) * cap + t0;
-
-        // ---- this lane's hypotheses (issued first: their latency overlaps the bounding-box pass)
-        const int hbase = hc * HC;
-        const float2 *hyp_row = hyp + ((size_t)b * vn + k) * HT + h0;
-        float2 hraw[HPL];                           // consumed by the centring below; the rare exact path reloads
-#pragma unroll
-        for (int j = 0; j < HPL; ++j) {
-            const int h = hbase + j * 32 + lane;
-            hraw[j] = (h < hn) ? __ldg(hyp_row + h) : make_float2(0.f, 0.f);
-        }
-        // first sub-chunk's raw data
-        unsigned pp[2];
-        float2 pn[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int i = e * 32 + lane;
-            pp[e] = (i < len) ? __ldg(pix_t + i) : 0u;
-            pn[e] = (i < len) ? __ldg(dir_t + i) : make_float2(0.f, 0.f);
-        }
-        // ---- bounding box of the segment (the list is row-major: rows from its ends, columns by a pass)
-        int xmin = 0x7fffffff, xmax = -1;
-        for (int i = lane; i < len; i += 32) {
-            const int x = (int)(__ldg(pix_t + i) & 0xffffu);
-            xmin = min(xmin, x);
-            xmax = max(xmax, x);
-        }
-        xmin = __reduce_min_sync(0xffffffffu, xmin);
-        xmax = __reduce_max_sync(0xffffffffu, xmax);
-        const int ymin = (int)(__ldg(pix_t) >> 16), ymax = (int)(__ldg(pix_t + len - 1) >> 16);
-        const float xc = (float)((xmin + xmax) >> 1), yc = (float)((ymin + ymax) >> 1);
-        const float r1 = (float)(max((int)xc - xmin, xmax - (int)xc) + max((int)yc - ymin, ymax - (int)yc));
-
-        f32x2 hx2[HPL / 2], hy2[HPL / 2];
-        float bd[HPL], nb2[HPL], cnt[HPL];          // band, -band * 2^64, count (exact small integers in fp32)
-#pragma unroll
-        for (int j = 0; j < HPL; j += 2) {
-            float hxv[2], hyv[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int h = hbase + (j + e) * 32 + lane;
-                hxv[e] = hyv[e] = 0.f;
-                bd[j + e] = -1.f;                   // padding: never uncertain, count discarded
-                if (h < hn) {
-                    hxv[e] = hraw[j + e].x - xc;
-                    hyv[e] = hraw[j + e].y - yc;
-                    bd[j + e] = fmaf(beta, fabsf(hxv[e]) + fabsf(hyv[e]) + r1, b0);
-                    if (!(bd[j + e] < 1e18f)) bd[j + e] = qnan;     // absurdly far / non-finite: exact path
-                }
-                nb2[j + e] = -bd[j + e] * VT_SCALE;
-                cnt[j + e] = 0.f;
-            }
-            hx2[j / 2] = pk2(hxv[0], hxv[1]);
-            hy2[j / 2] = pk2(hyv[0], hyv[1]);
-        }
-
-        for (int c0 = 0; c0 < len; c0 += VT_SUB) {
-            const int clen = min(VT_SUB, len - c0);
-            // ---- stage this sub-chunk from the prefetched registers: cone functionals, duplicated for FFMA2
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int i = e * 32 + lane;
-                const unsigned p = pp[e];
-                const float2 n = pn[e];
-                const float xr = (float)(int)(p & 0xffff) - xc, yr = (float)(int)(p >> 16) - yc;
-                const float n2 = fmaf(n.x, n.x, n.y * n.y);
-                const float rinv = rsqrtf(n2);
-                const float ux = n.x * rinv, uy = n.y * rinv;
-                float sx = sn * ux, sy = sn * uy, cx = -cs * uy, cy = cs * ux;
-                float ns = -fmaf(sx, xr, sy * yr), nc = -fmaf(cx, xr, cy * yr);
-                if (!(n2 > 1e-11f && n2 < 1e30f)) sx = sy = cx = cy = ns = nc = qnan;   // -> exact path
-                if (i >= clen) {                    // padding pixel: m = -1e30, never counted, never uncertain
-                    sx = sy = cx = cy = nc = 0.f;
-                    ns = -1e30f;
-                }
-                rec[3 * i] = make_float4(sx, sx, sy, sy);
-                rec[3 * i + 1] = make_float4(ns, ns, cx, cx);
-                rec[3 * i + 2] = make_float4(cy, cy, nc, nc);
-            }
-            __syncwarp();
-            // ---- prefetch the next sub-chunk
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int i = c0 + VT_SUB + e * 32 + lane;
-                pp[e] = (i < len) ? __ldg(pix_t + i) : 0u;
-                pn[e] = (i < len) ? __ldg(dir_t + i) : make_float2(0.f, 0.f);
-            }
-            // ---- sweep: G pixels x HPL hypotheses per step; the guard-band flag is OR-ed into ONE predicate over the
-            // group (FSETP.LEU.OR chains) and checked with one vote.  (Two branch-free variants were measured
-            // and lost: one check per 64-pixel sub-chunk re-walks 26 % of the sub-chunks at B ~ 2.6e-3 px; per-pixel
-            // bits compile to FSETP + SEL chains on the half-rate ALU pipe: 2.74 vs 2.94e12 tests/s.  So did one
-            // band per LANE (max over its 8 hypotheses, FMNMX3 band check): the heavy tail of |h'| inflates it,
-            // 2.16e12.)
-            for (int i0 = 0; i0 < clen; i0 += G) {
-                bool unc = false;
-                const uint32_t base = rec_u + (uint32_t)i0 * 48u;
-#pragma unroll
-                for (int u = 0; u < G; ++u) {
-                    f32x2 SX, SY, NS, CX, CY, NC;
-                    lds_2x64(base + (uint32_t)u * 48u, SX, SY);
-                    lds_2x64(base + (uint32_t)u * 48u + 16u, NS, CX);
-                    lds_2x64(base + (uint32_t)u * 48u + 32u, CY, NC);
-#pragma unroll
-                    for (int j = 0; j < HPL / 2; ++j) {
-                        const f32x2 num2 = fma2(hx2[j], SX, fma2(hy2[j], SY, NS));
-                        const f32x2 per2 = fma2(hx2[j], CX, fma2(hy2[j], CY, NC));
-                        float n0, n1, q0, q1;
-                        upk2(num2, n0, n1);
-                        upk2(per2, q0, q1);
-                        const float m0 = n0 - fabsf(q0), m1 = n1 - fabsf(q1);
-                        cnt[2 * j] += fma_sat(m0, VT_SCALE, nb2[2 * j]);
-                        cnt[2 * j + 1] += fma_sat(m1, VT_SCALE, nb2[2 * j + 1]);
-                        unc |= !(fabsf(m0) > bd[2 * j]);
-                        unc |= !(fabsf(m1) > bd[2 * j + 1]);
-                    }
-                }
-                if (__any_sync(0xffffffffu, unc)) {
-                    if (unc) {
-                        for (int u = 0; u < G; ++u) {
-                            const int pi = i0 + u;
-                            if (pi >= clen) break;
-                            const float4 ra = rec[3 * pi], rb = rec[3 * pi + 1], rc = rec[3 * pi + 2];
-#pragma unroll
-                            for (int j = 0; j < HPL; ++j) {
-                                float hxa, hxb, hya, hyb;
-                                upk2(hx2[j / 2], hxa, hxb);
-                                upk2(hy2[j / 2], hya, hyb);
-                                const float hxs = (j & 1) ? hxb : hxa, hys = (j & 1) ? hyb : hya;
-                                const float num = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
-                                const float perp = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
-                                const float m = num - fabsf(perp);
-                                if (hbase + j * 32 + lane < hn && !(fabsf(m) > bd[j])) {
-                                    const unsigned p = pix_t[c0 + pi];
-                                    const float2 nraw = dir_t[c0 + pi];
-                                    const float2 hp = hyp_row[hbase + j * 32 + lane];
-                                    cnt[j] += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hp.x, hp.y,
-                                                           thresh)
-                                                  ? 1.f
-                                                  : 0.f;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-        }
-
-        // ---- one RED per hypothesis
-#pragma unroll
-        for (int j = 0; j < HPL; ++j) {
-            const int h = hbase + j * 32 + lane;
-            const int c = (int)cnt[j];
-            if (h < hn && c) atomicAdd(counts + ((size_t)b * vn + k) * HT + h0 + h, c);
-        }
-    }
-}
-
-// ------------------------------------------------------------------ the vote, deferred guard band
-// k_vote3 = k_vote2's decomposition (autonomous warps, ticket counter, private 3 KB staging, compact lists) with
-// a branch-free test loop.  Two changes to the arithmetic:
-//   * the two EDGES of the inlier cone are staged instead of (num, perp):  m+ = num - perp,  m- = num + perp,
-//     each one affine functional of h' -- (s -+ c).h' - (s -+ c).p' -- so  m = num - |perp| = min(m+, m-)  costs an
-//     FMNMX on the ALU pipe instead of an FADD on the (binding) FMA pipe;
-//   * the guard band is not tested per test: every hypothesis keeps  mab = min over the sub-chunk of |m|
-//     (one FMNMX3.NAN with |.| operand modifiers per TWO tests, ALU pipe), compared with B once per 64 pixels.  A
-//     hypothesis with mab <= B (or NaN) is re-walked by the whole warp -- 2 pixels per lane, the same fma chains
-//     bit for bit -- and exactly its in-band tests are decided by exact_inlier() and added with one RED.  The
-//     fast path never counts an in-band test (m <= B adds 0), so nothing is counted twice.
-// Per test: 2 FFMA2 + FMNMX + FFMA.SAT + FADD + 1/2 FMNMX3 = 5.5 issue slots, 6 FMA-pipe cycles, 3 ALU-pipe
-// cycles (k_vote2: 6 slots + the group branch, 7 FMA-pipe cycles, and a serial FSETP.OR predicate chain).
-// Error budget: the staged coefficients are fma(sn,ux,cs uy) etc. (<= 2u relative each), the constant one fma
-// more: < 10u (|h'|_1 + r1) all told, inside the 18u the band reserves for our side (vote_consts).
-__device__ __forceinline__ float min_nan(float a, float b)
-{
-    float r;
-    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ float min3_nan_abs(float a, float b, float c)     // min(a, |b|, |c|), NaN if any is
-{
-    float r;
-    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(fabsf(b)), "f"(fabsf(c)));
-    return r;
-}
-
-// m from the two staged functionals: FORM 0 = cone edges (min), FORM 1/2 = num - |perp|
-template <int FORM>
-__device__ __forceinline__ float combine(float f1, float f2)
-{
-    return FORM == 0 ? min_nan(f1, f2) : f1 - fabsf(f2);
-}
-
-template <int HPL, int G, int FORM>
-__global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
-    k_vote3(const unsigned *__restrict__ pix, const float2 *__restrict__ direct, const int *__restrict__ tn_arr, int npx,
-            int cap, int nb, int vn, int hn, int HT, int h0, const float2 *__restrict__ hyp, int *__restrict__ counts,
-            unsigned *__restrict__ ticket, float thresh, float sn, float cs, float beta, float b0, int items_per_warp)
-{
-    static_assert(G % 2 == 0 && VT_SUB % G == 0, "pixels are swept in pairs");
-    // per warp, per pixel 48 bytes: {ap,ap,bp,bp} {cp,cp,am,am} {bm,bm,cm,cm}:  m+ = ap hx' + bp hy' + cp, m- likewise
-    __shared__ float4 rec_all[VT_WARPS * 3 * VT_SUB];
-    __shared__ int seg_prefix[VT_MAX_B + 1];
-    __shared__ int s_seg;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int HC = 32 * HPL;
-    const int hcn = (hn + HC - 1) / HC;
-    if (tid == 0) {
+        // pixels per item: the largest power-of-two multiple of VT_SUB (<= 4096) that still leaves items_per_warp items
+        // per resident warp, so hypotheses are set up rarely and the tail of the ticket queue stays short
         long long px = 0;
         for (int i = 0; i < nb; ++i) px += tn_arr[i];
         const long long want = (long long)gridDim.x * VT_WARPS * items_per_warp;
@@ -938,7 +703,6 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
         };
         f32x2 hx2[HPL / 2], hy2[HPL / 2];
         float nb2[HPL], cnt[HPL], mab[HPL];         // -band * 2^64, count (exact small integers in fp32), min |m|
-        float mabB[FORM == 1 ? HPL : 1];            // FORM 1: odd pixels' minimum (two 2-input FMNMX instead of one FMNMX3)
 #pragma unroll
         for (int j = 0; j < HPL; j += 2) {
             float hxv[2], hyv[2];
@@ -951,7 +715,6 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                 nb2[j + e] = -bd * VT_SCALE;
                 cnt[j + e] = 0.f;
                 mab[j + e] = finf;
-                if (FORM == 1) mabB[j + e] = finf;
             }
             hx2[j / 2] = pk2(hxv[0], hxv[1]);
             hy2[j / 2] = pk2(hyv[0], hyv[1]);
@@ -968,23 +731,16 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                 const float n2 = fmaf(n.x, n.x, n.y * n.y);
                 const float rinv = rsqrtf(n2);
                 const float ux = n.x * rinv, uy = n.y * rinv;
-                float ap, bp, am, bm;
-                if (FORM == 0) {                    // cone edges  s - c,  s + c   (c = cs (-uy, ux))
-                    ap = fmaf(sn, ux, cs * uy), bp = fmaf(sn, uy, -(cs * ux));
-                    am = fmaf(sn, ux, -(cs * uy)), bm = fmaf(sn, uy, cs * ux);
-                } else {                            // s and c themselves:  m = f1 - |f2|
-                    ap = sn * ux, bp = sn * uy;
-                    am = -cs * uy, bm = cs * ux;
-                }
-                float cp = -fmaf(ap, xr, bp * yr), cm = -fmaf(am, xr, bm * yr);
-                if (!(n2 > 1e-11f && n2 < 1e30f)) ap = bp = am = bm = cp = cm = qnan;   // -> exact path
+                float sx = sn * ux, sy = sn * uy, cx = -cs * uy, cy = cs * ux;
+                float ns = -fmaf(sx, xr, sy * yr), nc = -fmaf(cx, xr, cy * yr);
+                if (!(n2 > 1e-11f && n2 < 1e30f)) sx = sy = cx = cy = ns = nc = qnan;   // -> exact path
                 if (i >= clen) {                    // padding pixel: m = -1e30, never counted, never in band
-                    ap = bp = am = bm = 0.f;
-                    cp = cm = -1e30f;
+                    sx = sy = cx = cy = nc = 0.f;
+                    ns = -1e30f;
                 }
-                rec[3 * i] = make_float4(ap, ap, bp, bp);
-                rec[3 * i + 1] = make_float4(cp, cp, am, am);
-                rec[3 * i + 2] = make_float4(bm, bm, cm, cm);
+                rec[3 * i] = make_float4(sx, sx, sy, sy);
+                rec[3 * i + 1] = make_float4(ns, ns, cx, cx);
+                rec[3 * i + 2] = make_float4(cy, cy, nc, nc);
             }
             __syncwarp();
 #pragma unroll
@@ -999,39 +755,32 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                 const uint32_t base = rec_u + (uint32_t)i0 * 48u;
 #pragma unroll
                 for (int u = 0; u < G; u += 2) {
-                    f32x2 AP0, BP0, CP0, AM0, BM0, CM0, AP1, BP1, CP1, AM1, BM1, CM1;
-                    lds_2x64(base + (uint32_t)u * 48u, AP0, BP0);
-                    lds_2x64(base + (uint32_t)u * 48u + 16u, CP0, AM0);
-                    lds_2x64(base + (uint32_t)u * 48u + 32u, BM0, CM0);
-                    lds_2x64(base + (uint32_t)u * 48u + 48u, AP1, BP1);
-                    lds_2x64(base + (uint32_t)u * 48u + 64u, CP1, AM1);
-                    lds_2x64(base + (uint32_t)u * 48u + 80u, BM1, CM1);
+                    f32x2 SX0, SY0, NS0, CX0, CY0, NC0, SX1, SY1, NS1, CX1, CY1, NC1;
+                    lds_2x64(base + (uint32_t)u * 48u, SX0, SY0);
+                    lds_2x64(base + (uint32_t)u * 48u + 16u, NS0, CX0);
+                    lds_2x64(base + (uint32_t)u * 48u + 32u, CY0, NC0);
+                    lds_2x64(base + (uint32_t)u * 48u + 48u, SX1, SY1);
+                    lds_2x64(base + (uint32_t)u * 48u + 64u, NS1, CX1);
+                    lds_2x64(base + (uint32_t)u * 48u + 80u, CY1, NC1);
 #pragma unroll
                     for (int j = 0; j < HPL / 2; ++j) {
-                        const f32x2 p0 = fma2(hx2[j], AP0, fma2(hy2[j], BP0, CP0));
-                        const f32x2 q0 = fma2(hx2[j], AM0, fma2(hy2[j], BM0, CM0));
-                        const f32x2 p1 = fma2(hx2[j], AP1, fma2(hy2[j], BP1, CP1));
-                        const f32x2 q1 = fma2(hx2[j], AM1, fma2(hy2[j], BM1, CM1));
+                        const f32x2 p0 = fma2(hx2[j], SX0, fma2(hy2[j], SY0, NS0));       // num,  pixel u
+                        const f32x2 q0 = fma2(hx2[j], CX0, fma2(hy2[j], CY0, NC0));       // perp, pixel u
+                        const f32x2 p1 = fma2(hx2[j], SX1, fma2(hy2[j], SY1, NS1));       // pixel u + 1
+                        const f32x2 q1 = fma2(hx2[j], CX1, fma2(hy2[j], CY1, NC1));
                         float p0a, p0b, q0a, q0b, p1a, p1b, q1a, q1b;
                         upk2(p0, p0a, p0b);
                         upk2(q0, q0a, q0b);
                         upk2(p1, p1a, p1b);
                         upk2(q1, q1a, q1b);
-                        const float m0a = combine<FORM>(p0a, q0a), m0b = combine<FORM>(p0b, q0b);
-                        const float m1a = combine<FORM>(p1a, q1a), m1b = combine<FORM>(p1b, q1b);
+                        const float m0a = p0a - fabsf(q0a), m0b = p0b - fabsf(q0b);
+                        const float m1a = p1a - fabsf(q1a), m1b = p1b - fabsf(q1b);
                         cnt[2 * j] += fma_sat(m0a, VT_SCALE, nb2[2 * j]);
                         cnt[2 * j + 1] += fma_sat(m0b, VT_SCALE, nb2[2 * j + 1]);
                         cnt[2 * j] += fma_sat(m1a, VT_SCALE, nb2[2 * j]);
                         cnt[2 * j + 1] += fma_sat(m1b, VT_SCALE, nb2[2 * j + 1]);
-                        if (FORM == 1) {
-                            mab[2 * j] = min_nan(mab[2 * j], fabsf(m0a));
-                            mabB[2 * j] = min_nan(mabB[2 * j], fabsf(m1a));
-                            mab[2 * j + 1] = min_nan(mab[2 * j + 1], fabsf(m0b));
-                            mabB[2 * j + 1] = min_nan(mabB[2 * j + 1], fabsf(m1b));
-                        } else {
-                            mab[2 * j] = min3_nan_abs(mab[2 * j], m0a, m1a);
-                            mab[2 * j + 1] = min3_nan_abs(mab[2 * j + 1], m0b, m1b);
-                        }
+                        mab[2 * j] = min3_nan_abs(mab[2 * j], m0a, m1a);
+                        mab[2 * j + 1] = min3_nan_abs(mab[2 * j + 1], m0b, m1b);
                     }
                 }
             }
@@ -1042,10 +791,6 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                 const float bd = nb2[j] * (-1.f / VT_SCALE);      // exact (power of two)
                 if (!(mab[j] > bd)) fl |= 1u << j;
                 mab[j] = finf;
-                if (FORM == 1) {
-                    if (!(mabB[j] > bd)) fl |= 1u << j;
-                    mabB[j] = finf;
-                }
             }
             unsigned lanes = __ballot_sync(0xffffffffu, fl != 0);
             while (lanes) {                                        // rare: ~1 hypothesis in 1000 per sub-chunk
@@ -1066,9 +811,9 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                         const int pi = e * 32 + lane;
                         if (pi < clen) {
                             const float4 ra = rec[3 * pi], rb = rec[3 * pi + 1], rc = rec[3 * pi + 2];
-                            const float mp = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
-                            const float mm = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
-                            const float m = combine<FORM>(mp, mm);
+                            const float num = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
+                            const float perp = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
+                            const float m = num - fabsf(perp);
                             if (!(fabsf(m) > bd)) {
                                 const unsigned p = __ldg(pix_t + c0 + pi);
                                 const float2 nraw = __ldg(dir_t + c0 + pi);
@@ -1707,13 +1452,12 @@ int launch_gen_hyp(const Samples &sm, int rng_stream, int b, int h, int w, int v
     return PVNET_OK;
 }
 
-// Guard-band constants of k_vote2 for a threshold T.  With u = 2^-24:
+// Guard-band constants of k_vote3 for a threshold T.  With u = 2^-24:
 //   reference: fl(cos) = cos (1 + delta), |delta| <= eta = (7 + 1/T) u  (two sqrt of an fma, the fma of
 //   the numerator with its inner product, one multiply, one division) plus u rad from rounding d;
 //   in m = |d| sin(theta_T - |theta|) that is a band of (eta T / sin(theta_T) + u) |d|;
 //   ours: unit vector, functionals, centring and the two fma chains: < 8 u (|h'|_1 + r1).
-//   (k_vote3's edge functionals: < 10 u.)
-// beta = 1.25 (1.1 eta T / s + u) + 18 u; b0 = 1e-5 covers |d| < 1e-6 (norm test of the reference).
+// beta = 1.25 (1.1 eta T / s + u) + 16 u; b0 = 1e-5 covers |d| < 1e-6 (norm test of the reference).
 // Outside T in [0.05, 1 - 1e-6] (and for NaN) beta is NaN: every test takes the exact path.
 struct VoteConsts {
     float sn, cs, beta, b0;
@@ -1727,7 +1471,7 @@ VoteConsts vote_consts(float thresh)
         const double eta = (7.0 + 1.0 / T) * u * 1.05;
         c.sn = (float)sn;
         c.cs = (float)T;
-        c.beta = (float)(1.25 * (1.1 * eta * T / sn + u) + 18.0 * u);
+        c.beta = (float)(1.25 * (1.1 * eta * T / sn + u) + 16.0 * u);
     } else {
         c.sn = 0.f;
         c.cs = 1.f;
@@ -1743,14 +1487,14 @@ int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int
 {
     const int npx = h * w;
     static const int impl = [] {
-        const char *e = getenv("PVNET_VOTE_IMPL");     // tuning knob: 0 = round-1 kernel (k_vote), 2 = k_vote2, 3 = k_vote3 (default)
+        const char *e = getenv("PVNET_VOTE_IMPL");     // tuning knob: 0 = round-1 kernel (k_vote, A/B), 3 = k_vote3 (default)
         return e ? atoi(e) : 3;
     }();
     static const int hpl_env = [] {
-        const char *e = getenv("PVNET_VOTE_HPL");      // tuning knob: hypotheses per lane of k_vote2 (4 or 8)
+        const char *e = getenv("PVNET_VOTE_HPL");      // tuning knob: hypotheses per lane of k_vote3 (4 or 8)
         return e ? atoi(e) : 8;
     }();
-    const int HPL = (impl >= 2 && hpl_env == 8 && hn > 128) ? 8 : 4;
+    const int HPL = (impl != 0 && hpl_env == 8 && hn > 128) ? 8 : 4;
     static const int ctas_per_sm = [] {
         const char *e = getenv("PVNET_VOTE_CTAS");     // tuning knob: resident vote CTAs per SM
         return e ? atoi(e) : 0;
@@ -1776,45 +1520,22 @@ int launch_vote(const float *vertex, const Strides &st, int b, int h, int w, int
     const unsigned grid = (unsigned)(pvnet::sm_count() * per_sm);
     PV_CUDA(cudaMemsetAsync(ws.ticket, 0, sizeof(unsigned), s));
     static const int grp = [] {
-        const char *e = getenv("PVNET_VOTE_GROUP");    // tuning knob: pixels per unrolled step (4 or 8); k_vote2: per band check
-        return e ? atoi(e) : (impl == 3 ? 4 : 8);
+        const char *e = getenv("PVNET_VOTE_GROUP");    // tuning knob: pixels per unrolled step of the sweep (4 or 8)
+        return e ? atoi(e) : 4;
     }();
-#define VOTE2(H_, G_)                                                                                                  \
-    k_vote2<H_, G_><<<grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tn, npx, ws.cap, b, vn, hn, HT, h0, ws.hyp, ws.counts, \
-                                                ws.ticket, thresh, vc.sn, vc.cs, vc.beta, vc.b0)
     static const int items_pw = [] {
         const char *e = getenv("PVNET_VOTE_ITEMS");    // tuning knob: work items per resident warp the segment length aims at
-        return e ? atoi(e) : 6;
+        return e ? atoi(e) : 16;                       // (config-4 layer: 3.96 / 3.81 / 3.73 / 3.73 ms at 6 / 10 / 16 / 24)
     }();
-    static const int form = [] {
-        const char *e = getenv("PVNET_VOTE_FORM");     // tuning knob: arithmetic form of k_vote3 (0, 1, 2: see the kernel)
-        return e ? atoi(e) : 2;
-    }();
-#define VOTE3F(H_, G_, F_)                                                                                             \
-    k_vote3<H_, G_, F_><<<grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tn, npx, ws.cap, b, vn, hn, HT, h0, ws.hyp,     \
-                                                    ws.counts, ws.ticket, thresh, vc.sn, vc.cs, vc.beta, vc.b0, items_pw)
 #define VOTE3(H_, G_)                                                                                                  \
-    do {                                                                                                               \
-        if (form == 1) VOTE3F(H_, G_, 1);                                                                              \
-        else if (form == 2) VOTE3F(H_, G_, 2);                                                                         \
-        else VOTE3F(H_, G_, 0);                                                                                        \
-    } while (0)
-    if (impl == 3) {
-        if (HPL == 8 && grp == 8) VOTE3(8, 8);
-        else if (HPL == 8) VOTE3(8, 4);
-        else if (grp == 8) VOTE3(4, 8);
-        else VOTE3(4, 4);
-        PV_LAUNCHED("k_vote3");
-        return PVNET_OK;
-    }
+    k_vote3<H_, G_><<<grid, VT_THREADS, 0, s>>>(ws.pix, ws.direct, ws.tn, npx, ws.cap, b, vn, hn, HT, h0, ws.hyp, ws.counts, \
+                                                ws.ticket, thresh, vc.sn, vc.cs, vc.beta, vc.b0, items_pw)
+    if (HPL == 8 && grp == 8) VOTE3(8, 8);
+    else if (HPL == 8) VOTE3(8, 4);
+    else if (grp == 8) VOTE3(4, 8);
+    else VOTE3(4, 4);
 #undef VOTE3
-#undef VOTE3F
-    if (HPL == 8 && grp == 8) VOTE2(8, 8);
-    else if (HPL == 8) VOTE2(8, 4);
-    else if (grp == 8) VOTE2(4, 8);
-    else VOTE2(4, 4);
-#undef VOTE2
-    PV_LAUNCHED("k_vote2");
+    PV_LAUNCHED("k_vote3");
     return PVNET_OK;
 }
 
@@ -2045,7 +1766,7 @@ int pvnet_vote_cov_with_mean(const void *mask, int mask_elem_size, const float *
 
 // ransac_voting_layer_v3 followed by estimate_voting_distribution_with_mean on its result, the
 // sequence of tools/train_linemod.py:119-130 (UncertaintyEvalWrapper), as ONE launch sequence: the
-// mask is compacted and the field gathered once, and when both thresholds agree one k_vote2 launch
+// mask is compacted and the field gathered once, and when both thresholds agree one k_vote3 launch
 // scores the v3 and the covariance hypotheses together.  See include/pvnet_b200.h.
 int pvnet_ransac_voting_pipeline(const void *mask, int mask_elem_size, int mask_mode, const float *vertex,
                                  const int64_t vertex_strides[5], const int32_t *idxs, const int32_t *cov_idxs,
