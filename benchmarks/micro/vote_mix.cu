@@ -82,6 +82,18 @@ __global__ void __launch_bounds__(256) k_mix(int reps, float seed, float *out, l
                     upk2(p1, p1a, p1b);
                     upk2(q1, q1a, q1b);
                     float m0a, m0b, m1a, m1b;
+                    if (V == 16 || V == 17) {               // -m: negative exactly when num > |perp|
+                        m0a = fabsf(q0a) - p0a, m0b = fabsf(q0b) - p0b, m1a = fabsf(q1a) - p1a, m1b = fabsf(q1b) - p1b;
+                        cnt[2 * j] += __float_as_uint(m0a) >> 31;
+                        cnt[2 * j + 1] += __float_as_uint(m0b) >> 31;
+                        cnt[2 * j] += __float_as_uint(m1a) >> 31;
+                        cnt[2 * j + 1] += __float_as_uint(m1b) >> 31;
+                        if (V == 16) {
+                            mab[2 * j] = min3_nan_abs(mab[2 * j], m0a, m1a);
+                            mab[2 * j + 1] = min3_nan_abs(mab[2 * j + 1], m0b, m1b);
+                        }
+                        continue;
+                    }
                     if (V == 11 || V == 15) {
                         m0a = p0a - fabsf(q0a), m0b = p0b - fabsf(q0b), m1a = p1a - fabsf(q1a), m1b = p1b - fabsf(q1b);
                     } else {
@@ -256,5 +268,7 @@ int main()
     run<13>("13: = 2 with four band predicates", sms);
     run<14>("14: 2 FFMA2 + FMNMX + 2 FFMA.SAT + 2 FADD", sms);
     run<15>("15: 2 FFMA2 + FADD + FFMA.SAT + FADD + 1/2 FMNMX3", sms);
+    run<16>("16: 2 FFMA2 + FADD + LEA.HI + 1/2 FMNMX3", sms);
+    run<17>("17: 2 FFMA2 + FADD + LEA.HI  (no band tracking)", sms);
     return 0;
 }

@@ -702,7 +702,8 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
             if (!(bd < 1e18f)) bd = qnan;           // absurdly far / non-finite: every test exact
         };
         f32x2 hx2[HPL / 2], hy2[HPL / 2];
-        float nb2[HPL], cnt[HPL], mab[HPL];         // -band * 2^64, count (exact small integers in fp32), min |m|
+        float bdv[HPL], mab[HPL];                   // band, min |m| over the current sub-chunk
+        int cnt[HPL];
 #pragma unroll
         for (int j = 0; j < HPL; j += 2) {
             float hxv[2], hyv[2];
@@ -712,8 +713,8 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                 float bd = -1.f;                    // padding: never in band, count discarded
                 hxv[e] = hyv[e] = 0.f;
                 if (h < hn) centre(hraw[j + e], hxv[e], hyv[e], bd);
-                nb2[j + e] = -bd * VT_SCALE;
-                cnt[j + e] = 0.f;
+                bdv[j + e] = bd;
+                cnt[j + e] = 0;
                 mab[j + e] = finf;
             }
             hx2[j / 2] = pk2(hxv[0], hxv[1]);
@@ -773,14 +774,15 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                         upk2(q0, q0a, q0b);
                         upk2(p1, p1a, p1b);
                         upk2(q1, q1a, q1b);
-                        const float m0a = p0a - fabsf(q0a), m0b = p0b - fabsf(q0b);
-                        const float m1a = p1a - fabsf(q1a), m1b = p1b - fabsf(q1b);
-                        cnt[2 * j] += fma_sat(m0a, VT_SCALE, nb2[2 * j]);
-                        cnt[2 * j + 1] += fma_sat(m0b, VT_SCALE, nb2[2 * j + 1]);
-                        cnt[2 * j] += fma_sat(m1a, VT_SCALE, nb2[2 * j]);
-                        cnt[2 * j + 1] += fma_sat(m1b, VT_SCALE, nb2[2 * j + 1]);
-                        mab[2 * j] = min3_nan_abs(mab[2 * j], m0a, m1a);
-                        mab[2 * j + 1] = min3_nan_abs(mab[2 * j + 1], m0b, m1b);
+                        // e = -m = |perp| - num: its sign bit IS the fast decision (LEA.HI adds it to the count)
+                        const float e0a = fabsf(q0a) - p0a, e0b = fabsf(q0b) - p0b;
+                        const float e1a = fabsf(q1a) - p1a, e1b = fabsf(q1b) - p1b;
+                        cnt[2 * j] += (int)(__float_as_uint(e0a) >> 31);
+                        cnt[2 * j + 1] += (int)(__float_as_uint(e0b) >> 31);
+                        cnt[2 * j] += (int)(__float_as_uint(e1a) >> 31);
+                        cnt[2 * j + 1] += (int)(__float_as_uint(e1b) >> 31);
+                        mab[2 * j] = min3_nan_abs(mab[2 * j], e0a, e1a);
+                        mab[2 * j + 1] = min3_nan_abs(mab[2 * j + 1], e0b, e1b);
                     }
                 }
             }
@@ -788,8 +790,7 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
             unsigned fl = 0;
 #pragma unroll
             for (int j = 0; j < HPL; ++j) {
-                const float bd = nb2[j] * (-1.f / VT_SCALE);      // exact (power of two)
-                if (!(mab[j] > bd)) fl |= 1u << j;
+                if (!(mab[j] > bdv[j])) fl |= 1u << j;
                 mab[j] = finf;
             }
             unsigned lanes = __ballot_sync(0xffffffffu, fl != 0);
@@ -805,7 +806,7 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                     const float2 hp = __ldg(hyp_row + h);
                     float hxs, hys, bd;
                     centre(hp, hxs, hys, bd);
-                    int add = 0;
+                    int add = 0;                            // exact decision minus what the sweep counted
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int pi = e * 32 + lane;
@@ -813,13 +814,14 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
                             const float4 ra = rec[3 * pi], rb = rec[3 * pi + 1], rc = rec[3 * pi + 2];
                             const float num = fmaf(hxs, ra.x, fmaf(hys, ra.z, rb.x));
                             const float perp = fmaf(hxs, rb.z, fmaf(hys, rc.x, rc.z));
-                            const float m = num - fabsf(perp);
-                            if (!(fabsf(m) > bd)) {
+                            const float ev = fabsf(perp) - num;
+                            if (!(fabsf(ev) > bd)) {
                                 const unsigned p = __ldg(pix_t + c0 + pi);
                                 const float2 nraw = __ldg(dir_t + c0 + pi);
-                                add += exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hp.x, hp.y, thresh)
-                                           ? 1
-                                           : 0;
+                                add += (exact_inlier(nraw.x, nraw.y, (float)(p & 0xffff), (float)(p >> 16), hp.x, hp.y, thresh)
+                                            ? 1
+                                            : 0) -
+                                       (int)(__float_as_uint(ev) >> 31);
                             }
                         }
                     }
@@ -833,8 +835,7 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 3)
 #pragma unroll
         for (int j = 0; j < HPL; ++j) {
             const int h = hbase + j * 32 + lane;
-            const int c = (int)cnt[j];
-            if (h < hn && c) atomicAdd(cnt_row + h, c);
+            if (h < hn && cnt[j]) atomicAdd(cnt_row + h, cnt[j]);
         }
     }
 }
