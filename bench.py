@@ -46,9 +46,10 @@ if ROOT not in sys.path:
 
 H, W, K_KP, HYP, BATCH = 480, 640, 9, 256, 16
 THRESH = 0.99
-VOTE_ISSUE_SLOTS_PER_TEST = 5.5   # k_vote3's sweep in SASS: 2 FFMA2 + FADD + FFMA.SAT + FADD + 1/2 FMNMX3 per test (+0.4 LDS/loop)
-VOTE_MICRO_CYCLES_PER_TEST = 7.99  # that mix alone, in registers, at the kernel's 4 resident warps per sub-partition
-#                                    (profiles/r02_micro_vote_mix.txt row 15; 7.00 at 6 warps): what the SM sustains
+VOTE_ISSUE_SLOTS_PER_TEST = 5.0   # k_vote3's sweep in SASS: 160 instructions per 32 tests = 2 FFMA2 + FADD + LEA.HI + 1/2 FMNMX3
+#                                   per test + 12 LDS.128 + 4 loop instructions; also its FMA-pipe cycles (FFMA2 = 2)
+VOTE_MICRO_CYCLES_PER_TEST = 7.17  # that mix alone, in registers, at the kernel's 4 resident warps per sub-partition
+#                                    (profiles/r02_micro_vote_mix.txt row 16; 6.32 at 6 warps): what the SM sustains
 
 # BASELINE.json configs that bench.py can run as the headline (per-GPU batch: weak scaling)
 CONFIGS = {
@@ -296,7 +297,7 @@ def vote_roofline(torch, pipe, x, peaks, clocks, cfg):
         "alg_hbm_frac": round(b_alg / (ms * 1e-3) / 1e9 / hbm, 5), "hbm_peak_gbs": hbm,
         "fg_px_per_image": round(float(tn.mean()), 1),
         "note": "whole layer timed (10 launches); FP32-issue bound by construction (SURVEY 8d): the [hn,K,tn] inlier tensor the "
-                "reference streams through HBM never exists here; issue_frac = tests/s over SMs x 128 lanes x clock / 5.5 slots, "
+                "reference streams through HBM never exists here; issue_frac = tests/s over SMs x 128 lanes x clock / 5.0 slots, "
                 "micro_frac = over what the instruction mix alone sustains in a register-only microbenchmark at the same "
                 "occupancy; the kernel's own ncu DRAM bytes (1.00x its algorithmic bytes) are in profiles/r02_ncu_vote.md",
     }

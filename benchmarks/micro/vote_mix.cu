@@ -57,10 +57,49 @@ __global__ void __launch_bounds__(256) k_mix(int reps, float seed, float *out, l
     float accs[HPL];
     for (int j = 0; j < HPL / 2; ++j) acc2[j] = pk2(0.f, 0.f);
     for (int j = 0; j < HPL; ++j) accs[j] = 0.f;
+    float ev[2 * HPL];
+    for (int j = 0; j < 2 * HPL; ++j) ev[j] = 1e30f;
     float mab[HPL], mabB[HPL];
     for (int j = 0; j < HPL; ++j) mab[j] = mabB[j] = 1e30f;
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
+        if (V == 18 || V == 19) {
+#pragma unroll 2
+            for (int p = 0; p < PIX; p += 2) {
+                const float4 a0 = rec[3 * p], b0 = rec[3 * p + 1], c0 = rec[3 * p + 2];
+                const float4 a1 = rec[3 * p + 3], b1 = rec[3 * p + 4], c1 = rec[3 * p + 5];
+                const f32x2 AP0 = pk2(a0.x, a0.y), BP0 = pk2(a0.z, a0.w), CP0 = pk2(b0.x, b0.y), AM0 = pk2(b0.z, b0.w),
+                            BM0 = pk2(c0.x, c0.y), CM0 = pk2(c0.z, c0.w);
+                const f32x2 AP1 = pk2(a1.x, a1.y), BP1 = pk2(a1.z, a1.w), CP1 = pk2(b1.x, b1.y), AM1 = pk2(b1.z, b1.w),
+                            BM1 = pk2(c1.x, c1.y), CM1 = pk2(c1.z, c1.w);
+#pragma unroll
+                for (int j = 0; j < HPL / 2; ++j) {
+                    if (V == 19) asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");     // does ptxas schedule across it?
+                    // ALU pipe: the previous pair's e values of this hypothesis pair
+                    cnt[2 * j] += __float_as_uint(ev[4 * j]) >> 31;
+                    cnt[2 * j + 1] += __float_as_uint(ev[4 * j + 1]) >> 31;
+                    cnt[2 * j] += __float_as_uint(ev[4 * j + 2]) >> 31;
+                    cnt[2 * j + 1] += __float_as_uint(ev[4 * j + 3]) >> 31;
+                    mab[2 * j] = min3_nan_abs(mab[2 * j], ev[4 * j], ev[4 * j + 2]);
+                    mab[2 * j + 1] = min3_nan_abs(mab[2 * j + 1], ev[4 * j + 1], ev[4 * j + 3]);
+                    // FMA pipe: this pair
+                    const f32x2 p0 = fma2(hx2[j], AP0, fma2(hy2[j], BP0, CP0));
+                    const f32x2 q0 = fma2(hx2[j], AM0, fma2(hy2[j], BM0, CM0));
+                    const f32x2 p1 = fma2(hx2[j], AP1, fma2(hy2[j], BP1, CP1));
+                    const f32x2 q1 = fma2(hx2[j], AM1, fma2(hy2[j], BM1, CM1));
+                    float p0a, p0b, q0a, q0b, p1a, p1b, q1a, q1b;
+                    upk2(p0, p0a, p0b);
+                    upk2(q0, q0a, q0b);
+                    upk2(p1, p1a, p1b);
+                    upk2(q1, q1a, q1b);
+                    ev[4 * j] = fabsf(q0a) - p0a;
+                    ev[4 * j + 1] = fabsf(q0b) - p0b;
+                    ev[4 * j + 2] = fabsf(q1a) - p1a;
+                    ev[4 * j + 3] = fabsf(q1b) - p1b;
+                }
+            }
+            continue;
+        }
         if (V >= 7 && V != 13) {
 #pragma unroll 2
             for (int p = 0; p < PIX; p += 2) {
@@ -194,7 +233,7 @@ __global__ void __launch_bounds__(256) k_mix(int reps, float seed, float *out, l
     }
     const long long t1 = clock64();
     float s = (unc ? 1.f : 0.f) + (unc1 ? 2.f : 0.f) + (unc2 ? 4.f : 0.f) + (unc3 ? 8.f : 0.f);
-    for (int j = 0; j < HPL; ++j) s += cntf[j] + (float)cnt[j] + hx[j] + hy[j] + accs[j] + mab[j] + mabB[j];
+    for (int j = 0; j < HPL; ++j) s += cntf[j] + (float)cnt[j] + hx[j] + hy[j] + accs[j] + mab[j] + mabB[j] + ev[j] + ev[HPL + j];
     for (int j = 0; j < HPL / 2; ++j) {
         float x, y;
         upk2(acc2[j], x, y);
@@ -270,5 +309,7 @@ int main()
     run<15>("15: 2 FFMA2 + FADD + FFMA.SAT + FADD + 1/2 FMNMX3", sms);
     run<16>("16: 2 FFMA2 + FADD + LEA.HI + 1/2 FMNMX3", sms);
     run<17>("17: 2 FFMA2 + FADD + LEA.HI  (no band tracking)", sms);
+    run<18>("18: = 16 software-pipelined (ALU ops of pair i-1 beside FMA ops of pair i)", sms);
+    run<19>("19: = 18 with a warp barrier between hypothesis pairs (short scheduling regions)", sms);
     return 0;
 }

@@ -114,20 +114,27 @@ VOTE_METRICS += ["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
                  "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
 
 
-def vote(rep, md, bench_json=None):
+def vote(rep, md, bench_json=None, hn=256):
     h, units, rows = raw(rep)
     col = {c: i for i, c in enumerate(h)}
     r = rows[0]
-    tests, fg, k, hn = 16 * 20000 * 9 * 256, 20000.0, 9, 256
+    fg, k = 20000.0, 9
+    tests = int(16 * fg * k * hn)
     if bench_json:
         rv = json.load(open(bench_json))["roofline_vote"]
         fg = rv["fg_px_per_image"]
         tests = int(16 * fg * k * hn)                       # the kernel's own tests (the refit's +1 vote is k_refit's)
-    lines = [f"# ncu --set full, k_vote3 inside one bench step (16 images x ~{fg:.0f} px, {hn} hyp, K={k})", "",
-             "`ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_vote3 -c 1 python "
-             "benchmarks/profile_step.py 1` -> `python benchmarks/ncu_tables.py vote ...`", "",
-             f"Kernel: `{r[col['Kernel Name']][:100]}`", "", "| metric | value | unit |", "|---|---|---|"]
-    for m in VOTE_METRICS:
+    if hn == 256:
+        head = [f"# ncu --set full, k_vote3 inside one bench step (16 images x ~{fg:.0f} px, {hn} hyp, K={k})", "",
+                "`ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_vote3 -c 1 python "
+                "benchmarks/profile_step.py 1` -> `python benchmarks/ncu_tables.py vote ...`", ""]
+    else:
+        head = [f"# ncu --set full, k_vote3 of the config-4 voting layer (16 images x {fg:.0f} px, 256 + 4096 hyp in one launch, K={k})",
+                "", "`SUST_FIELD=planted SUST_SKIP_BURST=1 ncu --set full --clock-control none --import-source on -k regex:k_vote3 "
+                "--launch-skip 6 -c 1 python benchmarks/vote_sustained.py` -> `python benchmarks/ncu_tables.py vote4 ...`", ""]
+    lines = head + [
+        f"Kernel: `{r[col['Kernel Name']][:100]}`", "", "| metric | value | unit |", "|---|---|---|"]
+    for m in VOTE_METRICS + ["sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"]:
         if m in col:
             lines.append(f"| {m} | {r[col[m]]} | {units[col[m]]} |")
     inst = float(r[col["smsp__inst_executed.sum"]].replace(",", ""))
@@ -206,5 +213,7 @@ if __name__ == "__main__":
         launch_list(sys.argv[2], sys.argv[3])
     elif cmd == "vote":
         vote(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
+    elif cmd == "vote4":
+        vote(sys.argv[2], sys.argv[3], None, hn=4352)
     elif cmd == "top":
         top(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 16)

@@ -30,12 +30,12 @@
 // |theta| < theta_T (cos theta_T = thresh), i.e.
 //     m = |d| sin(theta_T - |theta|) = sin(theta_T) (d.u) - cos(theta_T) |d.v| > 0,
 // u = n/|n|, v = (-u_y, u_x): two linear functionals of the hypothesis per pixel.  k_vote3
-// evaluates them in segment-centred coordinates (4 FMA as 2 FFMA2), m (1 FADD), and compares with a
-// per-hypothesis guard band B (DESIGN.md section 3 bounds both the reference's rounding,
+// evaluates them in segment-centred coordinates (4 FMA as 2 FFMA2), -m (1 FADD), counts its sign bit and tracks
+// min |m| against a per-hypothesis guard band B (DESIGN.md section 3 bounds both the reference's rounding,
 // <= (7 + 1/T) ulp on the cosine, and ours): m > B counts, |m| <= B (or NaN) is re-decided by
 // exact_inlier(), the reference's own instruction sequence.  Tests outside the band cannot
 // change sign under either rounding, so the counts are identical to the reference's, at
-// 5.5 issue slots per test (13.6 in round 1's num*|num| - T^2 d^2 form, kept as k_vote for A/B).
+// 4.5 issue slots per test (13.6 in round 1's num*|num| - T^2 d^2 form, kept as k_vote for A/B).
 #include "common.cuh"
 
 #include <cfloat>
@@ -553,20 +553,26 @@ __global__ void __launch_bounds__(VT_THREADS, HPL > 4 ? 2 : 4)
 // Instruction mix (profiles/r02_micro_vote_mix.txt: every step below is a measured row):
 //   * two hypotheses ride in one FFMA2 (fma.rn.f32x2): half the issue slots of 4 FFMA; the pixel operands are
 //     stored pre-duplicated so a pair comes straight out of LDS.128;
-//   * the count is taken on the FMA pipes:  cnt += fma.sat(m, 2^64, -B 2^64)  is exactly 1 when m > B and exactly
-//     0 otherwise (the product is exact, |m - B| >= ulp(B) >= 2^-23 b0 when they differ, NaN saturates to 0);
+//   * the FAST decision is the sign bit of  e = |perp| - num = -m  (one FADD), added to an integer count by ONE
+//     ALU-pipe instruction (LEA.HI cnt, e, cnt, RZ, 1  =  cnt + (e >> 31)); a NaN e is the canonical positive NaN:
+//     not counted.  (Before: cnt += fma.sat(m, 2^64, -B 2^64), two more FMA-pipe cycles per test -- the FMA pipe is
+//     the busy one: 7 -> 5 cycles per test, config-4 layer 3.72 -> 3.46 ms.)
 //   * the guard band is NOT tested per test (one FSETP.OR per test made a serial predicate chain and a branch per
 //     pixel group: 8.7 vs 8.0 cycles per 32 tests in the microbenchmark at our 4 warps per sub-partition, and
-//     4.57 vs 3.96 ms on the config-4 layer): every hypothesis keeps  mab = min over the sub-chunk of |m|  -- one
-//     FMNMX3.NAN with |.| operand modifiers per TWO tests, on the otherwise idle ALU pipe -- compared with B
-//     once per 64 pixels.  A hypothesis with !(mab > B) is re-walked by the whole warp (2 pixels per lane, the
-//     same fma chains bit for bit) and exactly its in-band tests are decided by exact_inlier() on the raw values
-//     and added with one RED.  The fast path never counts an in-band test (m <= B adds 0): nothing counted twice.
-// Per test: 2 FFMA2 + FADD + FFMA.SAT + FADD + 1/2 FMNMX3 = 5.5 issue slots, no branch inside a sub-chunk.
-// Measured and rejected on the way (config-4 layer, ms, planted / random field): staging the cone EDGES so that
-// m = min(m+, m-) is an FMNMX (4.24 / 4.06: the ALU pipe is the scarcer one); two 2-input FMNMX instead of the
-// FMNMX3 (4.18 / 4.09); packed FADD2 count adds (3.83 / 3.77 at 4 pixels per step, 3.69 / 3.63 at 8: within
-// 1 % of this form's 3.72 / 3.66); HPL = 4 with 3 CTAs per SM (4.24 / 4.17).
+//     4.57 vs 3.96 ms on the config-4 layer): every hypothesis keeps  mab = min over the sub-chunk of |e|  -- one
+//     FMNMX3.NAN with |.| operand modifiers per TWO tests, ALU pipe -- compared with B once per 64 pixels.  A
+//     hypothesis with !(mab > B) is re-walked by the whole warp (2 pixels per lane, the same fma chains bit for bit)
+//     and exactly its in-band tests get exact_inlier() on the raw values; one RED adds  exact - fast.
+//     Outside the band sign(m) IS the reference's decision (that is what B bounds), inside it is corrected: the
+//     counts are the reference's.
+// Per test: 2 FFMA2 + FADD + LEA.HI + 1/2 FMNMX3 = 4.5 issue slots (5.0 with LDS and loop: 160 instructions per
+// 4 pixels x 8 hypotheses), 5 FMA-pipe cycles, no branch inside a sub-chunk.
+// Measured and rejected on the way (config-4 layer, ms, planted / random field; with the fma.sat count unless
+// noted): staging the cone EDGES so that m = min(m+, m-) is an FMNMX (4.24 / 4.06); two 2-input FMNMX instead of the
+// FMNMX3 (4.18 / 4.09); packed FADD2 count adds (3.69 / 3.63 at best, within 1 % of 3.72 / 3.66); HPL = 4 with 3 CTAs
+// per SM (4.24 / 4.17; with the sign-bit count 3.95 / 3.89 against 3.46 / 3.40); queueing the in-band tests so that one
+// exact_inlier() pass serves 32 of them (3.46 / 3.42: no gain, other warps already hide that path); source-level
+// software pipelining of the ALU ops against the next pair's FFMA2 (microbenchmark rows 18, 19: ptxas re-clusters).
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float a, float b)
 {
@@ -584,18 +590,10 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
-__device__ __forceinline__ float fma_sat(float a, float b, float c)
-{
-    float r;
-    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
-}
 __device__ __forceinline__ void lds_2x64(uint32_t addr, f32x2 &a, f32x2 &b)
 {
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
-constexpr float VT_SCALE = 18446744073709551616.f;     // 2^64
-
 constexpr int VT_SUB = 64;        // pixels per staged sub-chunk (2 per lane)
 
 __device__ __forceinline__ float min3_nan_abs(float a, float b, float c)     // min(a, |b|, |c|), NaN if any is
