@@ -16,7 +16,6 @@ timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --cloc
   --log-file gpurun_out/launches_final.csv python benchmarks/profile_step.py 2 > gpurun_out/ncu_list.log 2>&1
 timeout 500 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_vote3 -c 1 \
   -o gpurun_out/vote_final python benchmarks/profile_step.py 1 > gpurun_out/ncu_vote_final.log 2>&1
-timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
 timeout 600 python benchmarks/gpu_baselines.py > gpurun_out/gpu_baselines.jsonl 2> gpurun_out/gpu_baselines.err
 SUST_FIELD=planted timeout 200 python benchmarks/vote_sustained.py > gpurun_out/vote_sustained_final.jsonl 2> gpurun_out/vote_sustained_final.err
 SUST_FIELD=random timeout 200 python benchmarks/vote_sustained.py >> gpurun_out/vote_sustained_final.jsonl 2>> gpurun_out/vote_sustained_final.err

@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "pvnet_b200", "_lib", "libpvnet_b200.so")
-OPS = ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "SYNCS", "ELECT", "FFMA2", "FFMA.SAT", "REDG", "LDS.128",
+OPS = ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "SYNCS", "ELECT", "FFMA2", "FMNMX3", "LEA.HI", "REDG", "LDS.128",
        "DSETP", "DFMA"]
 
 
