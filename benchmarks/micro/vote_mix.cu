@@ -1,4 +1,4 @@
-// vote_mix.cu -- microbenchmark of k_vote2's inner loop in isolation: which instruction mix per inlier
+// vote_mix.cu -- microbenchmark of the vote kernel's inner loop in isolation (every form it went through): which instruction mix per inlier
 // test does the SM sustain?  One CTA per SM-slot, no global traffic inside the timed loop: every lane keeps
 // HPL hypotheses in registers and sweeps a 64-pixel record tile from shared memory over and over.
 // Variants (template V):
@@ -293,12 +293,12 @@ int main()
     printf("cycles per test-warp (32 inlier tests) per SM sub-partition; columns: 2, 4, 6, 8 resident warps per sub-partition\n");
     run<0>("0: 4 FFMA + FADD + FSETP + IADD + FSETP(band)", sms);
     run<1>("1: 4 FFMA + FADD + FFMA.SAT + FADD + FSETP(band)", sms);
-    run<2>("2: 2 FFMA2 + FADD + FFMA.SAT + FADD + FSETP(band)  [k_vote2]", sms);
+    run<2>("2: 2 FFMA2 + FADD + FFMA.SAT + FADD + FSETP(band)  [round 2, first kernel]", sms);
     run<3>("3: 2 FFMA2 + FADD + FFMA.SAT + FADD  (no band check)", sms);
     run<4>("4: 2 FFMA2 + FADD + FSETP + IADD + FSETP(band)", sms);
     run<5>("5: 2 FFMA2 only", sms);
     run<6>("6: 4 FFMA only", sms);
-    run<7>("7: 2 FFMA2 + FMNMX + FFMA.SAT + FADD + 1/2 FMNMX3  [k_vote3]", sms);
+    run<7>("7: 2 FFMA2 + FMNMX + FFMA.SAT + FADD + 1/2 FMNMX3  (cone edges)", sms);
     run<8>("8: 2 FFMA2 + FMNMX + FFMA.SAT + 1/2 IADD3 + 1/2 FMNMX3", sms);
     run<9>("9: 2 FFMA2 + FMNMX + FFMA.SAT + FADD  (no band tracking)", sms);
     run<10>("10: 2 FFMA2 + FMNMX + FFMA.SAT + 1/2 FADD2 + 1/2 FMNMX3", sms);
@@ -307,7 +307,7 @@ int main()
     run<13>("13: = 2 with four band predicates", sms);
     run<14>("14: 2 FFMA2 + FMNMX + 2 FFMA.SAT + 2 FADD", sms);
     run<15>("15: 2 FFMA2 + FADD + FFMA.SAT + FADD + 1/2 FMNMX3", sms);
-    run<16>("16: 2 FFMA2 + FADD + LEA.HI + 1/2 FMNMX3", sms);
+    run<16>("16: 2 FFMA2 + FADD + LEA.HI + 1/2 FMNMX3  [k_vote3, shipped]", sms);
     run<17>("17: 2 FFMA2 + FADD + LEA.HI  (no band tracking)", sms);
     run<18>("18: = 16 software-pipelined (ALU ops of pair i-1 beside FMA ops of pair i)", sms);
     run<19>("19: = 18 with a warp barrier between hypothesis pairs (short scheduling regions)", sms);

@@ -1,6 +1,6 @@
 """GPU parity tests of round 2's voting path: the fused v3 + covariance pipeline
 (`pvnet_ransac_voting_pipeline`) at BASELINE configs 4 and 5's exact shapes, config 3's 12-point
-sweep, the device-side sampler, and an adversarial test of k_vote2's guard band.
+sweep, the device-side sampler, and an adversarial test of k_vote3's guard band.
 
 Bar (same as tests/test_gpu_vote.py): hypotheses and inlier counts bit-exact against the oracle /
 the exact-sequence kernel; keypoints within 1e-4; covariances atol 1e-4 + rtol 1e-4.
@@ -122,7 +122,7 @@ def test_config3_sweep_counts_vs_exact_kernel(n_fg, hn):
 @pytest.mark.parametrize("T", [0.99, 0.999, 0.9, 0.5])
 def test_guard_band_adversarial(T):
     """Every pixel's direction sits within +-4e-6 (relative, in angle) of the cone edge of a hypothesis
-    that the sampled pairs reproduce: nearly every test is inside or next to k_vote2's guard band."""
+    that the sampled pairs reproduce: nearly every test is inside or next to k_vote3's guard band."""
     rng = np.random.default_rng(11)
     th = np.arccos(float(np.float32(T)))
     mask_np = syn.disc_mask(6000)
