@@ -163,6 +163,42 @@ def test_pose_pipeline_run_from_host_buffers():
         assert torch.equal(kp2[i], got_kp[i])
 
 
+def test_pose_pipeline_graph_mode_equals_eager():
+    """PoseKeypointPipeline(graph=True): each input buffer's device work is captured once and replayed; with the
+    device sampler rewound the replays return exactly what the eager pipeline returns, and they keep drawing fresh
+    samples when it is not rewound."""
+    net = _net()
+    rng = np.random.default_rng(2)
+    pts3d = rng.uniform(-0.1, 0.1, (9, 3)).astype(np.float32)
+    K = np.array([[572.4114, 0., 325.2611], [0., 573.57043, 242.04899], [0., 0., 1.]])
+    kw = dict(round_hyp_num=64, with_covariance=True, cov_round_hyp_num=64, cov_min_hyp_num=128, points_3d=pts3d,
+              camera_matrix=K)
+    eager = PoseKeypointPipeline(net, **kw)
+    graph = PoseKeypointPipeline(net, graph=True, **kw)
+    hosts = [torch.from_numpy(rng.integers(0, 256, (2, 96, 128, 3), dtype=np.uint8)).pin_memory() for _ in range(5)]
+
+    def run(pipe):
+        kp = [torch.full([2, 9, 2], float("nan")).pin_memory() for _ in hosts]
+        cov = [torch.full([2, 9, 2, 2], float("nan")).pin_memory() for _ in hosts]
+        pose = [torch.full([2, 3, 4], float("nan"), dtype=torch.float64).pin_memory() for _ in hosts]
+        rv.reset_device_rng(DEV)
+        pipe.run(hosts, out_host=kp, cov_host=cov, pose_host=pose)
+        return kp, cov, pose
+    torch.manual_seed(13)
+    run(graph)                                   # first run: warm-up + capture of the two graphs
+    assert all(g is not None for g in graph._graphs)
+    e = run(eager)
+    g1 = run(graph)                              # pure replays
+    for a, b in zip(e, g1):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    kp_a = [t.clone() for t in g1[0]]
+    graph.run(hosts, out_host=g1[0])             # sampler not rewound: fresh samples
+    assert any(not torch.equal(a, b) for a, b in zip(kp_a, g1[0]))
+    with pytest.raises(ValueError):
+        PoseKeypointPipeline(net, rng="batched", graph=True)
+
+
 def test_pipeline_with_pose_and_pixel_major_equals_separate_calls():
     """PoseKeypointPipeline(points_3d, camera_matrix): keypoints / covariances / poses equal the ones obtained by
     calling the reference-shaped API step by step (NCHW output + permuted view, then v3 + with_mean with the same
