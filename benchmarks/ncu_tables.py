@@ -205,6 +205,48 @@ def top(rep, kid, n=16):
         print(f"{100 * sm / tot:5.1f}% {f}:{ln:>4} {src}")
 
 
+def stalls(rep, label):
+    """Markdown: key throughput metrics of the (single) captured kernel + where the warp-stall samples fall,
+    per block of 100 SASS instructions (ncu --set full --import-source on)."""
+    h, units, rows = raw(rep)
+    col = {c: i for i, c in enumerate(h)}
+    r = rows[0]
+    keys = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+            "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+            "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.sum",
+            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "l1tex__t_requests_pipe_lsu_mem_local_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum"]
+    print(f"### {label}\n\n`{r[col['Kernel Name']][:70]}`\n\n| metric | value |\n|---|---|")
+    for k in keys:
+        if k in col:
+            print(f"| `{k}` | {r[col[k]]} {units[col[k]]} |")
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    srows = list(csv.reader(out.splitlines()))
+    sh, data = srows[1], srows[2:]
+    isamp, iexe = sh.index("# Samples"), sh.index("Instructions Executed")
+    st = [i for i, c in enumerate(sh) if c.startswith("stall_") and "Not Issued" not in c]
+    tot = sum(int(x[isamp]) for x in data)
+    print(f"\nWarp-stall samples: {tot} over {len(data)} SASS instructions; blocks of 100 instructions holding >= 1 %:\n")
+    print("| SASS index | samples | % | warp-instr. executed per (tile, warp) | top stall reasons | first instruction |\n|---|---|---|---|---|---|")
+    for k in range(0, len(data), 100):
+        seg = data[k:k + 100]
+        sm = sum(int(x[isamp]) for x in seg)
+        if sm < 0.01 * tot:
+            continue
+        ex = sum(int(x[iexe]) for x in seg) / 153600.0
+        agg = {}
+        for x in seg:
+            for i in st:
+                if x[i].isdigit():
+                    agg[sh[i][6:]] = agg.get(sh[i][6:], 0) + int(x[i])
+        top = ", ".join(f"{n} {v}" for n, v in sorted(agg.items(), key=lambda z: -z[1])[:3])
+        print(f"| {k} | {sm} | {100 * sm / tot:.1f} | {ex:.0f} | {top} | `{seg[0][1].strip()[:38]}` |")
+    print()
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "conv":
@@ -215,5 +257,7 @@ if __name__ == "__main__":
         vote(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
     elif cmd == "vote4":
         vote(sys.argv[2], sys.argv[3], None, hn=4352)
+    elif cmd == "stalls":
+        stalls(sys.argv[2], sys.argv[3])
     elif cmd == "top":
         top(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 16)

@@ -296,6 +296,10 @@ PVNET_API int pvnet_conv_set_multicast(int on);
 /* Test hook: 1 (default) runs single-CTA tiles of the per-tap kernel on its persistent variant
  * (continuous TMA ring, two TMEM accumulator stages); 0 = one tile per CTA. */
 PVNET_API int pvnet_conv_set_persistent(int on);
+/* Test hook / tuning knob: epilogue warp sets of the fused-head column kernel (convraw.0) in plans built
+ * afterwards.  1 = one set of four warps (default), 2 = two sets alternating tiles (measured no faster: the
+ * launch is tensor-pipe bound), 0 = default (environment variable PVNET_HEAD_EPI, else 1). */
+PVNET_API int pvnet_conv_set_head_epilogue_sets(int sets);
 
 /* Resnet18_8s.forward (lib/networks/model_repository.py:64-80), eval mode, whole batch.
  *
@@ -332,6 +336,12 @@ PVNET_API int pvnet_backbone_set_conv(pvnet_backbone_t *m, int slot, const float
  * vertex layout [b,h,w,K,2] the voting layer's gather reads without sector waste (the contiguous
  * form of the permuted view of tools/demo.py:48-50). */
 PVNET_API int pvnet_backbone_set_output_layout(pvnet_backbone_t *m, int pixel_major);
+/* The last decoder upsampling, F.interpolate(x2s_up, scale_factor=2, mode='bilinear', align_corners=True)
+ * (model_repository.py:75), can run inside convraw.0's operand loader: the full-resolution
+ * [b,h,w,s2dim] tensor is then never written, the output is bit-identical.  on = 1 selects the fused
+ * form, 0 the separate upsampling launch, -1 = default (environment variable PVNET_FUSE_UP; off: the
+ * fused form measured slower on B200). */
+PVNET_API int pvnet_backbone_set_fused_upsample(pvnet_backbone_t *m, int on);
 PVNET_API int pvnet_backbone_workspace_bytes(const pvnet_backbone_t *m, int b, int h, int w, size_t *bytes);
 PVNET_API int pvnet_backbone_forward(pvnet_backbone_t *m, const float *image_nchw, int b, int h, int w,
                                      float *out_nchw, void *mask_out, int mask_elem_size,

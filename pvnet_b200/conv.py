@@ -27,6 +27,11 @@ def set_multicast(mode: int):
     _native.check(_native.lib().pvnet_conv_set_multicast(int(mode)), "pvnet_conv_set_multicast")
 
 
+def set_head_epilogue_sets(sets: int):
+    """Test hook (pvnet_conv_set_head_epilogue_sets): epilogue warp sets of the fused-head kernel, 0 = default."""
+    _native.check(_native.lib().pvnet_conv_set_head_epilogue_sets(int(sets)), "pvnet_conv_set_head_epilogue_sets")
+
+
 def set_persistent(on: bool):
     """Test hook (pvnet_conv_set_persistent): persistent variant of the per-tap kernel."""
     _native.check(_native.lib().pvnet_conv_set_persistent(int(bool(on))), "pvnet_conv_set_persistent")

@@ -12,6 +12,7 @@
 //   C1 [b,H,  W,   s2+8]     up(conv2s) -> [0,s2) image        -> [s2,s2+3), zeros to +8
 #include "conv_tc.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 using namespace pvnet;
@@ -41,7 +42,22 @@ struct pvnet_backbone {
     bool stem_tc = false;                // stem runs as a 4x4 conv on the space-to-depth image
     bool raw_split = false;              // convraw.0 reads the upsampled features and the image slice from two dense buffers
     int out_nhwc = 0;                    // output layout: 0 = [b,C,H,W] (reference), 1 = pixel-major [b,H,W,C]
+    int fuse_up = -1;                    // 1/2 -> 1 upsampling inside convraw.0's loader: -1 = default (PVNET_FUSE_UP, off)
+    bool up2_fused = false;              // the current plan has no separate 1/2 -> 1 upsampling launch
 };
+
+// default of the fused 1/2 -> 1 upsampling (tuning knob PVNET_FUSE_UP, read once): OFF.  Measured on B200
+// (profiles/r02_ncu_convraw_fused.md): bit-identical output, but the interpolation runs on
+// convraw.0's epilogue warps, whose per-tile chain (three TMEM round trips + the head MMA) is already as long
+// as the tile's MMAs -- 0.77 ms fused against 0.43 + 0.17 ms for the two separate launches.
+static int env_fuse_up()
+{
+    static const int v = [] {
+        const char *e = getenv("PVNET_FUSE_UP");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
 
 // where the image comes from: float32 NCHW (already normalised) or raw uint8 HWC + mean/std
 struct ImageSrc {
@@ -189,6 +205,7 @@ int build_plans(pvnet_backbone *m, const Buffers &B, int b, int h, int w)
     ConvDesc draw = cd(m, CV_CONVRAW0, B.C1, c1s, 0, c1s, B.R0, m->raw, 0, m->raw, b, h, w, 3, 1, 1, 2, nullptr, 0, 0,
                        /*round_out=*/0);
     m->raw_split = false;
+    m->up2_fused = false;
     if (g_conv_mode != 1 && m->s2 % 8 == 0) {
         ConvDesc ds = draw;
         ds.in_cs = m->s2;
@@ -200,6 +217,13 @@ int build_plans(pvnet_backbone *m, const Buffers &B, int b, int h, int w)
         if (conv_col_eligible(ds)) {
             draw = ds;
             m->raw_split = true;
+            // F.interpolate(x2s_up, scale 2) (model_repository.py:75) inside convraw.0's operand loader: conv2s.0's
+            // half-resolution output U2 is the source, the full-resolution tensor is never written
+            const bool want = (m->fuse_up < 0 ? env_fuse_up() : m->fuse_up) != 0;
+            if (want && m->s2 == 32 && m->raw == 32 && m->seg_dim + m->ver_dim <= 32) {
+                draw.up_src = B.U2;
+                m->up2_fused = true;
+            }
         }
     }
     if ((rc = plan(CV_CONVRAW0, draw))) return rc;
@@ -241,6 +265,14 @@ int pvnet_backbone_set_output_layout(pvnet_backbone_t *m, int pixel_major)
 {
     PV_CHECK_ARG(m, "null handle");
     m->out_nhwc = pixel_major ? 1 : 0;
+    return PVNET_OK;
+}
+
+int pvnet_backbone_set_fused_upsample(pvnet_backbone_t *m, int on)
+{
+    PV_CHECK_ARG(m, "null handle");
+    m->fuse_up = on < 0 ? -1 : (on ? 1 : 0);
+    m->p_ws = nullptr;   // replan
     return PVNET_OK;
 }
 
@@ -351,7 +383,9 @@ int run_stage(pvnet_backbone *m, const Stage &st, const Buffers &B, const ImageS
     }
     case ST_UP8: return launch_upsample2x(B.U8, B.C4, b, h8, w8, m->s8, c4s, 0, s);
     case ST_UP4: return launch_upsample2x(B.U4, B.C2, b, h4, w4, m->s4, c2s, 0, s);
-    case ST_UP2: return launch_upsample2x(B.U2, B.C1, b, h2, w2, m->s2, m->raw_split ? m->s2 : c1s, 0, s);
+    case ST_UP2:
+        if (m->up2_fused) return PVNET_OK;     // interpolated inside convraw.0
+        return launch_upsample2x(B.U2, B.C1, b, h2, w2, m->s2, m->raw_split ? m->s2 : c1s, 0, s);
     case ST_HEAD:
         if (m->head_fused) return PVNET_OK;    // already written by convraw.0's epilogue
         return launch_head(B.R0, m->w[CV_HEAD], m->bias[CV_HEAD], out_nchw, mask_out, mask_elem_size, m->seg_dim,

@@ -326,10 +326,10 @@ __global__ void __launch_bounds__(256)
             const float4 c = __ldg(reinterpret_cast<const float4 *>(ip + ioff[r][2]));
 #pragma unroll
             for (int o = 0; o < 2; ++o) {
-                t[r][o].x = wx[o][0] * a.x + wx[o][1] * bq.x + wx[o][2] * c.x;
-                t[r][o].y = wx[o][0] * a.y + wx[o][1] * bq.y + wx[o][2] * c.y;
-                t[r][o].z = wx[o][0] * a.z + wx[o][1] * bq.z + wx[o][2] * c.z;
-                t[r][o].w = wx[o][0] * a.w + wx[o][1] * bq.w + wx[o][2] * c.w;
+                t[r][o].x = lerp3(wx[o][0], a.x, wx[o][1], bq.x, wx[o][2], c.x);
+                t[r][o].y = lerp3(wx[o][0], a.y, wx[o][1], bq.y, wx[o][2], c.y);
+                t[r][o].z = lerp3(wx[o][0], a.z, wx[o][1], bq.z, wx[o][2], c.z);
+                t[r][o].w = lerp3(wx[o][0], a.w, wx[o][1], bq.w, wx[o][2], c.w);
             }
         }
         float *op = out + cg * 4;
@@ -338,10 +338,10 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
             for (int ox = 0; ox < 2; ++ox) {
                 float4 v;
-                v.x = ptx::round_tf32(wy[oy][0] * t[0][ox].x + wy[oy][1] * t[1][ox].x + wy[oy][2] * t[2][ox].x);
-                v.y = ptx::round_tf32(wy[oy][0] * t[0][ox].y + wy[oy][1] * t[1][ox].y + wy[oy][2] * t[2][ox].y);
-                v.z = ptx::round_tf32(wy[oy][0] * t[0][ox].z + wy[oy][1] * t[1][ox].z + wy[oy][2] * t[2][ox].z);
-                v.w = ptx::round_tf32(wy[oy][0] * t[0][ox].w + wy[oy][1] * t[1][ox].w + wy[oy][2] * t[2][ox].w);
+                v.x = ptx::round_tf32(lerp3(wy[oy][0], t[0][ox].x, wy[oy][1], t[1][ox].x, wy[oy][2], t[2][ox].x));
+                v.y = ptx::round_tf32(lerp3(wy[oy][0], t[0][ox].y, wy[oy][1], t[1][ox].y, wy[oy][2], t[2][ox].y));
+                v.z = ptx::round_tf32(lerp3(wy[oy][0], t[0][ox].z, wy[oy][1], t[1][ox].z, wy[oy][2], t[2][ox].z));
+                v.w = ptx::round_tf32(lerp3(wy[oy][0], t[0][ox].w, wy[oy][1], t[1][ox].w, wy[oy][2], t[2][ox].w));
                 *reinterpret_cast<float4 *>(op + o00 + (unsigned)oy * orow + (unsigned)ox * (unsigned)out_cs) = v;
             }
     }

@@ -30,6 +30,7 @@
 namespace pvnet {
 
 int g_conv_mode = 0;
+int g_head_epi = 0;     // test hook: epilogue warp sets of the fused-head kernel (0 = PVNET_HEAD_EPI / default 1)
 
 namespace {
 
@@ -51,19 +52,135 @@ struct ColGeom {
     int head_nhwc;          // fused head writes pixel-major [b,H,W,cout] instead of the reference's NCHW
 };
 
+// fused bilinear x2 upsampling of the first split_chunk channel chunks (UP variant of the kernel)
+struct ColUp {
+    const float *src;       // half-resolution source [b,h,w,cs], dense
+    int h, w, cs;
+    float sy, sx;           // ATen's align_corners scale (in-1)/(out-1)
+    unsigned zero;          // always 0; opaque to the compiler (see up_fill_chunk)
+};
+
+// Fused upsampling (UP variant of the kernel): epilogue warp q interpolates channel chunk q (8 channels)
+// of one tile's halo box -- (COL_TH+2) x (COL_TW+2) full-resolution pixels, zero outside the image like
+// the TMA box it replaces -- straight into the operand stage, in the 32-byte-swizzled layout TMA would
+// have written (16-byte half `hf` of box row rr sits at rr*32 + ((hf ^ (rr>>2 & 1)) << 4): address bit 4
+// XOR bit 7).  Arithmetic is k_upsample2x's (backbone_aux.cu), i.e. ATen's upsample_bilinear2d with
+// align_corners: src = scale*dst, out = h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11), rounded to tf32.
+// Lane = (box column, half): it walks its column top to bottom, keeping the horizontally interpolated
+// source rows in registers (10 rows x 2 loads for 18 outputs instead of 4 loads per output).  With
+// scale 2 the source row pair of output row y0-1+i is (E, E+1), E = y0/2 - 1 + i/2, except in the
+// last image row when scale*y rounds below E (then it is (E-1, E)): a three-row window with one zero
+// weight covers both, as in k_upsample2x.
+__device__ __forceinline__ float4 ldg_nc_v4_volatile(const float *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void up_fill_chunk(const ColUp &u, const ColGeom &g, int img, int y0, int x0, int q, int lane,
+                                              uint32_t stage_addr)
+{
+    constexpr int PITCH = COL_TW + 2, ROWS = COL_TH + 2, NSLOT = COL_TH / 2 + 3;
+    const bool act = lane < 2 * PITCH;                 // lanes 20..31 only take part in the shuffles
+    const int c = act ? lane >> 1 : 0, hf = lane & 1;
+    const int x = x0 - 1 + c;
+    const bool vx = act && x >= 0 && x < g.Wo;
+    const int xc = min(max(x, 0), g.Wo - 1);
+    const float fx = u.sx * (float)xc;
+    const int xlo = (int)fx;
+    const int xhi = min(xlo + 1, u.w - 1);
+    const float w1x_ = fx - (float)xlo;
+    const int R0 = (y0 >> 1) - 2;
+    // Vertical weights: lane r works out box row r's window weights once; the row loop fetches them with
+    // three shuffles (the weights are the same for the whole warp: ~20 instructions per row otherwise).
+    // Rows outside the image get zero weights -- the conv's zero padding -- and columns outside get zero
+    // horizontal weights, so no output needs a select.
+    float wa_l = 0.f, wb_l = 0.f, wc_l = 0.f;
+    {
+        const int y = y0 - 1 + lane;
+        if (lane < ROWS && y >= 0 && y < g.Ho) {
+            const float fy = u.sy * (float)y;
+            const int ylo = (int)fy;
+            const float h1 = fy - (float)ylo, h0 = 1.f - h1;
+            const bool low = ylo < R0 + 1 + (lane >> 1);   // source pair is rows (E-1, E) rather than (E, E+1)
+            wa_l = low ? h0 : 0.f;
+            wb_l = low ? h1 : h0;
+            wc_l = low ? 0.f : h1;
+        }
+    }
+    const float *base = u.src + (size_t)img * u.h * u.w * u.cs + q * 8 + hf * 4;
+    const unsigned rstride = (unsigned)u.w * (unsigned)u.cs;      // 32-bit element offsets inside one image
+    const unsigned olo = (unsigned)xlo * (unsigned)u.cs, ohi = (unsigned)xhi * (unsigned)u.cs;
+    // All 2 x 10 source loads are issued before anything consumes them (volatile asm keeps them together).
+    // Window slot 0 (row R0) only ever carries the zero weight: for the first two box rows the source
+    // pair is always (E, E+1), see above -- it is not loaded.
+    float4 a[NSLOT - 1], b[NSLOT - 1];
+#pragma unroll
+    for (int j = 1; j < NSLOT; ++j) {
+        a[j - 1] = b[j - 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) {
+            const unsigned ro = (unsigned)min(max(R0 + j, 0), u.h - 1) * rstride;
+            a[j - 1] = ldg_nc_v4_volatile(base + (ro + olo));
+            b[j - 1] = ldg_nc_v4_volatile(base + (ro + ohi));
+        }
+    }
+    // ... and nothing may consume them before the last one has landed: ptxas otherwise starts on the first
+    // output rows as soon as their three source rows are there and parks the remaining loads behind those
+    // stores (3-4 exposed L2 round trips per tile instead of one).  The interpolation weight is made to
+    // depend on every load through an AND with a kernel parameter that is always zero.
+    unsigned dep = 0;
+#pragma unroll
+    for (int j = 0; j < NSLOT - 1; ++j) dep |= __float_as_uint(a[j].x) | __float_as_uint(b[j].x);
+    float w1x = __uint_as_float(__float_as_uint(w1x_) | (dep & u.zero)), w0x = 1.f - w1x_;
+    if (!vx) w0x = w1x = 0.f;
+    float4 t[NSLOT];
+    t[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 1; j < NSLOT; ++j) {
+        t[j].x = __fmaf_rn(w1x, b[j - 1].x, __fmul_rn(w0x, a[j - 1].x));   // lerp3 with a zero third weight
+        t[j].y = __fmaf_rn(w1x, b[j - 1].y, __fmul_rn(w0x, a[j - 1].y));
+        t[j].z = __fmaf_rn(w1x, b[j - 1].z, __fmul_rn(w0x, a[j - 1].z));
+        t[j].w = __fmaf_rn(w1x, b[j - 1].w, __fmul_rn(w0x, a[j - 1].w));
+    }
+    // store address of box row rr = i*PITCH + c: rr*32 + ((hf ^ bit 2 of rr) << 4)
+    const uint32_t sbase = stage_addr + (uint32_t)(c * 32);
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+        const float wa = __shfl_sync(0xffffffffu, wa_l, i), wb = __shfl_sync(0xffffffffu, wb_l, i),
+                    wc = __shfl_sync(0xffffffffu, wc_l, i);
+        const int e = i >> 1;
+        // Rounding to tf32 (nearest, ties away -- cvt.rna.tf32, what k_upsample2x stores): add half an ulp of
+        // the 10-bit mantissa; the 13 low bits that remain are ignored by the tensor core (kind::tf32 reads the
+        // upper 19 bits), so they need not be cleared.  Exactly the values the separate launch feeds the MMA.
+        float4 o;
+        o.x = __uint_as_float(__float_as_uint(lerp3(wa, t[e].x, wb, t[e + 1].x, wc, t[e + 2].x)) + 0x1000u);
+        o.y = __uint_as_float(__float_as_uint(lerp3(wa, t[e].y, wb, t[e + 1].y, wc, t[e + 2].y)) + 0x1000u);
+        o.z = __uint_as_float(__float_as_uint(lerp3(wa, t[e].z, wb, t[e + 1].z, wc, t[e + 2].z)) + 0x1000u);
+        o.w = __uint_as_float(__float_as_uint(lerp3(wa, t[e].w, wb, t[e + 1].w, wc, t[e + 2].w)) + 0x1000u);
+        const int rr = i * PITCH + c;
+        if (act) ptx::sts128(sbase + (uint32_t)(i * PITCH * 32) + (uint32_t)((hf ^ ((rr >> 2) & 1)) << 4), o);
+    }
+}
+
 
 // EPI = number of epilogue warp sets (4 warps each).  ncu showed the stem and layer1 launches
 // epilogue-bound (epilogue warps never wait on tfull; 39 % of samples on the residual load): with
 // EPI = 2 the sets alternate tiles, one per TMEM accumulator stage.
-template <int KC, bool HEAD, int KH, int EPI>
-__global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
+// UP (with HEAD, KC = 8, 4 interpolated chunks + 1 TMA chunk per tile, ring = 2 tiles): the first
+// split_chunk chunks of every tile are produced by the epilogue warps (up_fill_chunk) instead of TMA.
+// Epilogue warp q fills chunk q of tile it+2 between the two halves of tile it's epilogue (after the
+// activated tile went back to TMEM, while the head MMA is pending), into stage ((it+2)&1)*5 + q; its
+// empty barrier completed with tile it's MMAs, which the warp has already seen through tfull.
+template <int KC, bool HEAD, int KH, int EPI, bool UP = false>
+__global__ void __launch_bounds__(64 + 128 * EPI, (EPI == 2 && !HEAD) ? 1 : 2)
     k_conv_col(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmO, const ColGeom g,
                const float *__restrict__ bias, const float *__restrict__ res, float *__restrict__ out,
                const float *__restrict__ head_w, const float *__restrict__ head_b, float *__restrict__ head_out,
-               void *__restrict__ mask)
+               void *__restrict__ mask, const ColUp up)
 {
+    static_assert(!UP || (HEAD && KC == 8 && KH == 3), "fused upsampling: convraw.0 form only");
     constexpr int ROWB = KC * 4;                       // bytes per K-major row
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -150,6 +267,13 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                 const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
                 const int y0 = tyi * COL_TH, x0 = txi * COL_TW;
                 for (int cc = 0; cc < g.cin_chunks; ++cc) {
+                    if (UP && cc < g.split_chunk) {     // filled by the epilogue warps
+                        if (++s == g.stages) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
+                        continue;
+                    }
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
                     ptx::mbar_arrive_expect_tx(&full[s], tx_bytes);
                     uint8_t *st = sA + (size_t)s * stage_bytes;
@@ -265,6 +389,26 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
         const uint32_t stage_u = ptx::smem_u32(sHB) + (uint32_t)epi_set * 16384u + (uint32_t)q * (EPI == 2 ? 4096u : 8192u);
         uint32_t nstore = 0;
         uint32_t it = (uint32_t)epi_set;
+        // UP: this warp's chunk q of the CTA's itj-th tile -> stage (itj&1)*chunks + q (the ring holds two tiles)
+        auto up_fill = [&](int tile_j, uint32_t itj) {
+            const int img_j = tile_j / tiles_per_img;
+            const int trem_j = tile_j - img_j * tiles_per_img;
+            const int tyj = trem_j / g.tiles_x, txj = trem_j - tyj * g.tiles_x;
+            const uint32_t sj = (itj & 1u) * (uint32_t)g.cin_chunks + (uint32_t)q;
+            ptx::mbar_wait(&empty[sj], ((itj >> 1) & 1u) ^ 1u);
+            up_fill_chunk(up, g, img_j, tyj * COL_TH, txj * COL_TW, q, lane,
+                          ptx::smem_u32(sA) + sj * (uint32_t)stage_bytes);
+            ptx::fence_proxy_async();       // generic-proxy stores -> visible to the MMA's async-proxy reads
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&full[sj]);
+        };
+        if constexpr (UP) {
+            // the first two tiles of the CTA (EPI = 2: each set fills the one it will finish)
+            for (int p = 0; p < 2; ++p) {
+                const int tile_p = (int)blockIdx.x + p * (int)gridDim.x;
+                if ((EPI == 1 || p == epi_set) && tile_p < g.total_tiles) up_fill(tile_p, (uint32_t)p);
+            }
+        }
         for (int tile = blockIdx.x + epi_set * gridDim.x; tile < g.total_tiles; tile += EPI * gridDim.x, it += EPI) {
             const uint32_t as = it & 1u;
             const int img = tile / tiles_per_img;
@@ -332,6 +476,10 @@ __global__ void __launch_bounds__(64 + 128 * EPI, EPI == 2 ? 1 : 2)
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&a2full[as]);
+                    if constexpr (UP) {
+                        const int tile_n = tile + 2 * (int)gridDim.x;
+                        if (tile_n < g.total_tiles) up_fill(tile_n, it + 2u);
+                    }
                     ptx::mbar_wait(&d2full[as], (it >> 1) & 1u);
                     ptx::tc_fence_after();
                     uint32_t d2[32];
@@ -410,6 +558,7 @@ struct ColPlan {
     CUtensorMap tmA, tmA2, tmB, tmH, tmO;
     ColGeom g;
     int kc, head, epi;
+    ColUp up;
     unsigned grid;
     size_t smem;
     const float *bias, *res;
@@ -460,7 +609,10 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
 {
     ColPlan *p = new (storage) ColPlan();
     PV_CHECK_ARG(conv_col_eligible(d), "conv(col): layer not eligible for the column kernel");
-    PV_CHECK_ARG(d.in && d.w && d.bias && (d.out || head), "conv(col): null pointer");
+    PV_CHECK_ARG((d.in || d.up_src) && d.w && d.bias && (d.out || head), "conv(col): null pointer");
+    PV_CHECK_ARG(!d.up_src || (head && d.in2 && col_kc(d.Cin + d.Cin2) == 8 && d.Cin == 32 && d.Cin2 == 8 && d.ksize == 3 &&
+                               d.H % 2 == 0 && d.W % 2 == 0 && (uintptr_t)d.up_src % 16 == 0),
+                 "conv(col): fused upsampling needs the convraw.0 form (32 upsampled + 8 direct channels, fused head)");
     PV_CHECK_ARG(d.in_cs % 4 == 0 && d.in_co % 4 == 0 && d.out_cs % 4 == 0 && d.out_co % 4 == 0,
                  "conv(col): channel strides/offsets must be multiples of 4 floats");
     PV_CHECK_ARG(!d.res || (d.res_cs % 4 == 0 && d.res_co % 4 == 0), "conv(col): residual stride/offset alignment");
@@ -491,6 +643,13 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     g.head_seg = head ? head->seg_dim : 0;
     g.mask_esz = head ? head->mask_esz : 0;
     g.head_nhwc = 0;
+    p->up.src = d.up_src;
+    p->up.h = d.H / 2;
+    p->up.w = d.W / 2;
+    p->up.cs = d.Cin;
+    p->up.sy = (float)(p->up.h - 1) / (float)(2 * p->up.h - 1);   // launch_upsample2x's scales
+    p->up.sx = (float)(p->up.w - 1) / (float)(2 * p->up.w - 1);
+    p->up.zero = 0;
     // Resident weights whenever at least 2 A stages (one channel chunk with all its taps each) still
     // fit next to them; otherwise the KH*KW weight tiles of a chunk travel with its A box.  Two CTAs
     // per SM when the footprint allows.
@@ -509,13 +668,18 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
                col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, false) > SMEM_LIMIT)
             --stages;
     }
+    if (d.up_src) {     // the ring is exactly two tiles: stage = (tile parity) * chunks + chunk
+        stages = 2 * g.cin_chunks;
+        PV_CHECK_ARG(resident && col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, true) <= SMEM_LIMIT,
+                     "conv(col): fused upsampling does not fit in shared memory");
+    }
     g.stages = stages;
     g.resident = resident ? 1 : 0;
     p->smem = col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, resident);
     p->kc = kc;
     p->head = head ? 1 : 0;
     if (head) p->hd = *head;
-    {
+    if (!d.up_src) {
         const float *base = d.in + d.in_co;
         cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.b};
         cuuint64_t strides[3] = {(cuuint64_t)d.in_cs * 4, (cuuint64_t)d.W * d.in_cs * 4,
@@ -525,7 +689,7 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
         int rc = tma_encode(&p->tmA, base, 4, dims, strides, box, kc * 4);
         if (rc) return rc;
     }
-    p->tmA2 = p->tmA;
+    if (!d.up_src) p->tmA2 = p->tmA;
     if (d.in2) {
         PV_CHECK_ARG(d.in2_cs % 4 == 0 && d.in2_co % 4 == 0 && d.Cin2 > 0, "conv(col): second source stride/offset alignment");
         cuuint64_t dims[4] = {(cuuint64_t)d.Cin2, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.b};
@@ -535,6 +699,7 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
                              (cuuint32_t)(COL_TH + (d.ksize - 1) * d.dilation), 1};
         int rc = tma_encode(&p->tmA2, d.in2 + d.in2_co, 4, dims, strides, box, kc * 4);
         if (rc) return rc;
+        if (d.up_src) p->tmA = p->tmA2;     // the first source is interpolated in the kernel, not read by TMA
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)d.ksize * d.ksize * g.cin_pad, (cuuint64_t)d.Cout};
@@ -572,6 +737,15 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     // are then 8 single buffers instead of 4 double ones) when the CTA is alone on its SM anyway and
     // the variant exists: the short-K layers are epilogue-bound (ncu: stem tensor pipe 40 %).
     p->epi = (env_epi == 2 && !head && kc != 8 && per_sm == 1) ? 2 : 1;
+    // Fused head (convraw.0), tuning knob PVNET_HEAD_EPI=2: two epilogue warp sets alternating tiles (set s owns
+    // TMEM stage s, the EPI = 2 protocol) with two CTAs per SM still resident at 96 registers per thread.
+    // Measured no gain (0.449 against 0.429 ms): the launch is bound by the tensor pipe (sm__pipe_tc_cycles_active
+    // 75 %: 45 N=32 MMAs per tile at the 40-cycle shared-memory operand floor), not by its epilogue.  Default 1.
+    static const int env_head_epi = [] {
+        const char *e = getenv("PVNET_HEAD_EPI");
+        return e ? atoi(e) : 1;
+    }();
+    if (head && kc == 8 && (g_head_epi ? g_head_epi : env_head_epi) == 2) p->epi = 2;
     long long grid = (long long)sm_count() * per_sm;
     if (grid > g.total_tiles) grid = g.total_tiles;
     p->grid = (unsigned)grid;
@@ -594,24 +768,29 @@ void conv_col_set_head_ptrs(void *storage, float *out_nchw, void *mask, int mask
 int conv_col_launch_at(const void *storage, cudaStream_t s)
 {
     const ColPlan &p = *static_cast<const ColPlan *>(storage);
-    const void *fn = (p.kc == 32 && !p.head) ? (p.epi == 2 ? (const void *)k_conv_col<32, false, 3, 2> : (const void *)k_conv_col<32, false, 3, 1>)
+    const void *fn = p.up.src ? (p.epi == 2 ? (const void *)k_conv_col<8, true, 3, 2, true> : (const void *)k_conv_col<8, true, 3, 1, true>)
+                     : (p.kc == 32 && !p.head) ? (p.epi == 2 ? (const void *)k_conv_col<32, false, 3, 2> : (const void *)k_conv_col<32, false, 3, 1>)
                      : (p.kc == 16 && !p.head) ? (p.epi == 2 ? (const void *)k_conv_col<16, false, 4, 2> : (const void *)k_conv_col<16, false, 4, 1>)
                      : (p.kc == 8 && !p.head) ? (const void *)k_conv_col<8, false, 3, 1>
-                     : p.kc == 32 ? (const void *)k_conv_col<32, true, 3, 1> : (const void *)k_conv_col<8, true, 3, 1>;
+                     : p.kc == 32 ? (const void *)k_conv_col<32, true, 3, 1>
+                     : p.epi == 2 ? (const void *)k_conv_col<8, true, 3, 2> : (const void *)k_conv_col<8, true, 3, 1>;
     const cudaError_t attr_err = ensure_max_smem(fn, (int)SMEM_LIMIT);
     PV_CUDA(attr_err);
     const HeadDesc &h = p.hd;
-#define COL_LAUNCH(KC_, HEAD_, KH_, EPI_)                                                                         \
-    k_conv_col<KC_, HEAD_, KH_, EPI_><<<p.grid, 64 + 128 * EPI_, p.smem, s>>>(p.tmA, p.tmA2, p.tmB, p.tmH, p.tmO, p.g, p.bias, p.res, p.out,           \
+#define COL_LAUNCH(KC_, HEAD_, KH_, EPI_, UP_)                                                                    \
+    k_conv_col<KC_, HEAD_, KH_, EPI_, UP_><<<p.grid, 64 + 128 * EPI_, p.smem, s>>>(p.tmA, p.tmA2, p.tmB, p.tmH, p.tmO, p.g, p.bias, p.res, p.out,      \
                                                                 p.head ? h.w : nullptr, p.head ? h.bias : nullptr, \
-                                                                p.head ? h.out_nchw : nullptr, p.head ? h.mask : nullptr)
-    if (p.kc == 32 && !p.head && p.epi == 2) COL_LAUNCH(32, false, 3, 2);
-    else if (p.kc == 32 && !p.head) COL_LAUNCH(32, false, 3, 1);
-    else if (p.kc == 16 && !p.head && p.epi == 2) COL_LAUNCH(16, false, 4, 2);
-    else if (p.kc == 16 && !p.head) COL_LAUNCH(16, false, 4, 1);
-    else if (p.kc == 8 && !p.head) COL_LAUNCH(8, false, 3, 1);
-    else if (p.kc == 32) COL_LAUNCH(32, true, 3, 1);
-    else COL_LAUNCH(8, true, 3, 1);
+                                                                p.head ? h.out_nchw : nullptr, p.head ? h.mask : nullptr, p.up)
+    if (p.up.src && p.epi == 2) COL_LAUNCH(8, true, 3, 2, true);
+    else if (p.up.src) COL_LAUNCH(8, true, 3, 1, true);
+    else if (p.kc == 32 && !p.head && p.epi == 2) COL_LAUNCH(32, false, 3, 2, false);
+    else if (p.kc == 32 && !p.head) COL_LAUNCH(32, false, 3, 1, false);
+    else if (p.kc == 16 && !p.head && p.epi == 2) COL_LAUNCH(16, false, 4, 2, false);
+    else if (p.kc == 16 && !p.head) COL_LAUNCH(16, false, 4, 1, false);
+    else if (p.kc == 8 && !p.head) COL_LAUNCH(8, false, 3, 1, false);
+    else if (p.kc == 32) COL_LAUNCH(32, true, 3, 1, false);
+    else if (p.epi == 2) COL_LAUNCH(8, true, 3, 2, false);
+    else COL_LAUNCH(8, true, 3, 1, false);
 #undef COL_LAUNCH
     PV_LAUNCHED("k_conv_col");
     return PVNET_OK;
@@ -620,6 +799,13 @@ int conv_col_launch_at(const void *storage, cudaStream_t s)
 }  // namespace pvnet
 
 extern "C" {
+// test hook: epilogue warp sets of the fused-head column kernel (plans built afterwards); 0 = default
+int pvnet_conv_set_head_epilogue_sets(int sets)
+{
+    PV_CHECK_ARG(sets >= 0 && sets <= 2, "sets must be 0, 1 or 2");
+    pvnet::g_head_epi = sets;
+    return PVNET_OK;
+}
 // test hook: 0 auto, 1 force the per-tap kernel, 2 force the column kernel
 int pvnet_conv_set_mode(int mode)
 {

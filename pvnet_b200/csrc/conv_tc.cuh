@@ -27,6 +27,11 @@ struct ConvDesc {
     // concatenated input write dense records of their own
     const float *in2 = nullptr;
     int in2_cs = 0, in2_co = 0, Cin2 = 0;
+    // optional fused upsampling (column kernel with the fused head only): channels [0, Cin) are NOT read
+    // from `in` but are F.interpolate(up_src, scale 2, bilinear, align_corners=True) of the dense
+    // half-resolution tensor up_src [b,H/2,W/2,Cin], interpolated inside the kernel straight into the
+    // operand stages (model_repository.py:75: the upsampled tensor is never written)
+    const float *up_src = nullptr;
 };
 
 // Optional fused 1x1 head (convraw.3 + argmax) for the column kernel's epilogue.
@@ -67,6 +72,13 @@ int launch_head(const float *in, const float *w, const float *bias, float *out, 
                 int seg_dim, int Cout, int b, int H, int W, int nhwc, cudaStream_t s);
 
 #ifdef __CUDACC__
+// Three-slot interpolation sum with a FIXED rounding sequence (one weight of the window is zero): both
+// upsampling implementations -- k_upsample2x and the column kernel's fused loader -- go through it, so they
+// agree to the last bit whatever contraction the compiler would have picked for `a*b + c*d + e*f`.
+__device__ __forceinline__ float lerp3(float w0, float a, float w1, float b, float w2, float c)
+{
+    return __fmaf_rn(w2, c, __fmaf_rn(w1, b, __fmul_rn(w0, a)));
+}
 // Coalesced residual fetch shared by the conv epilogues (128-pixel tiles TW pixels wide, one pixel
 // per thread, epilogue warp q owns tile rows q*32/TW ...).  Load i of lane l reads the 16-byte chunk
 // (l % 8) of warp-pixel 4*i + l/8, i.e. four full 128-byte lines per instruction instead of 32

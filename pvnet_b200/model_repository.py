@@ -63,6 +63,7 @@ class _NativeEntry:
     def __init__(self, handle, keep, key):
         self.handle, self.keep, self.key = handle, keep, key
         self.packs = 1
+        self.fuse_up = -1            # what pvnet_backbone_set_fused_upsample was last told (-1: library default)
         self._fin = weakref.finalize(self, _NativeEntry._destroy, handle.value)
 
     @staticmethod
@@ -81,6 +82,7 @@ class _NativeState:
         self.entries = {}          # device index -> _NativeEntry
         self.workspaces = {}       # (device index, stream) -> uint8 tensor
         self.pack_count = 0        # how many times weights were folded + packed (tests assert on it)
+        self.fuse_up = -1          # -1 library default (separate launch), 0 separate upsampling launch, 1 fused
 
 
 class Resnet18_8s(nn.Module):
@@ -152,6 +154,20 @@ class Resnet18_8s(nn.Module):
 
     def native_pack_count(self):
         return self._nat.pack_count
+
+    def set_fused_upsample(self, on=None):
+        """A/B switch of the 1/2 -> 1 upsampling inside convraw.0's loader (pvnet_backbone_set_fused_upsample):
+        None = library default (separate launch), False = separate k_upsample2x launch, True = fused."""
+        self._nat.fuse_up = -1 if on is None else int(bool(on))
+        return self
+
+    def _sync_options(self, dev):
+        dev = torch.device(dev)
+        ent = self._nat.entries[dev.index if dev.index is not None else torch.cuda.current_device()]
+        if ent.fuse_up != self._nat.fuse_up:
+            _native.check(_native.lib().pvnet_backbone_set_fused_upsample(ent.handle, self._nat.fuse_up),
+                          "pvnet_backbone_set_fused_upsample")
+            ent.fuse_up = self._nat.fuse_up
 
     def _prepare_native(self, device):
         """Fold BatchNorm (eval statistics) into the conv weights, pack them K-major, round
@@ -239,6 +255,7 @@ class Resnet18_8s(nn.Module):
         dev = x.device
         with torch.cuda.device(dev):
             handle = self._prepare_native(dev)
+            self._sync_options(dev)
             L = _native.lib()
             n = ctypes.c_size_t()
             _native.check(L.pvnet_backbone_workspace_bytes(handle, b, h, w, ctypes.byref(n)),
@@ -270,6 +287,7 @@ class Resnet18_8s(nn.Module):
         dev = x.device
         with torch.cuda.device(dev):
             handle = self._prepare_native(dev)
+            self._sync_options(dev)
             L = _native.lib()
             n = ctypes.c_size_t()
             _native.check(L.pvnet_backbone_workspace_bytes(handle, b, h, w, ctypes.byref(n)), "pvnet_backbone_workspace_bytes")
