@@ -271,6 +271,21 @@ int launch_maxpool(const float *in, float *out, int b, int H, int W, int C, int 
 // as ATen's upsample_bilinear2d: scale=(in-1)/(out-1) in fp32, src=scale*dst, i0=(int)src,
 // l1=src-i0, l0=1-l1, out = h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11).
 // in NHWC [b,h,w,C] dense -> out NHWC [b,2h,2w,out_cs] at out_co; values rounded to tf32.
+// w0*a + w1*b with lerp3's rounding sequence (fmul, then fma), four lanes
+__device__ __forceinline__ float4 lerp2_4(float w0, const float4 &a, float w1, const float4 &b)
+{
+    return make_float4(__fmaf_rn(w1, b.x, __fmul_rn(w0, a.x)), __fmaf_rn(w1, b.y, __fmul_rn(w0, a.y)),
+                       __fmaf_rn(w1, b.z, __fmul_rn(w0, a.z)), __fmaf_rn(w1, b.w, __fmul_rn(w0, a.w)));
+}
+// cvt.rna.tf32.f32 (nearest, ties away) as integer add + mask: identical for every finite input and infinity,
+// two instructions per value instead of the four the conversion compiles to
+__device__ __forceinline__ float4 round_tf32_4(const float4 &v)
+{
+    return make_float4(__uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u),
+                       __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u),
+                       __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u),
+                       __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u));
+}
 __global__ void __launch_bounds__(256)
     k_upsample2x(const float *__restrict__ in, float *__restrict__ out, int h, int w, int C, int out_cs, int out_co,
                  float sy, float sx)
@@ -290,12 +305,15 @@ __global__ void __launch_bounds__(256)
     const int n = blockIdx.y / h, j = blockIdx.y - n * h;
 
     float wy[2][3], wx[2][3];
+    bool pat[2][2];                                     // [o][0] = uy, [o][1] = ux
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
         const float fy = sy * (float)(2 * j + o), fx = sx * (float)(2 * k + o);
         const int y0 = (int)fy, x0 = (int)fx;
         const float h1 = fy - (float)y0, h0 = 1.f - h1, w1 = fx - (float)x0, w0 = 1.f - w1;
         const bool uy = y0 >= j, ux = x0 >= k;          // source pair is rows (j, j+1) rather than (j-1, j)
+        pat[o][0] = uy;
+        pat[o][1] = ux;
         wy[o][0] = uy ? 0.f : h0;
         wy[o][1] = uy ? h0 : h1;
         wy[o][2] = uy ? h1 : 0.f;
@@ -316,6 +334,35 @@ __global__ void __launch_bounds__(256)
     const unsigned o00 = (((unsigned)n * 2u * h + 2u * j) * Wo + 2u * k) * (unsigned)out_cs + (unsigned)out_co;
     const unsigned orow = Wo * (unsigned)out_cs;
 
+    // All blocks but those of the first row / column (and a last one whose scale*index rounds down) have the same
+    // pattern: output 2j reads source rows (j-1, j), output 2j+1 rows (j, j+1), same for columns -- two-term sums (8 instead of 12
+    // floating-point instructions per float4; the kernel is issue-bound).  lerp3 with its zero weight rounds
+    // identically (fmul of the first product, fma of the second; adding 0*x changes nothing), so both paths and the
+    // column kernel's fused loader agree to the last bit.
+    const bool interior = !pat[0][0] && pat[1][0] && !pat[0][1] && pat[1][1];
+    if (interior) {
+        const float a0 = wx[0][0], a1 = wx[0][1], b0 = wx[1][1], b1 = wx[1][2];      // column weights of outputs 2k, 2k+1
+        const float p0 = wy[0][0], p1 = wy[0][1], q0 = wy[1][1], q1 = wy[1][2];      // row weights of outputs 2j, 2j+1
+        for (int cg = threadIdx.x; cg < c4; cg += 8) {
+            const float *ip = in + cg * 4;
+            float4 t[3][2];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(ip + ioff[r][0]));
+                const float4 bq = __ldg(reinterpret_cast<const float4 *>(ip + ioff[r][1]));
+                const float4 c = __ldg(reinterpret_cast<const float4 *>(ip + ioff[r][2]));
+                t[r][0] = lerp2_4(a0, a, a1, bq);
+                t[r][1] = lerp2_4(b0, bq, b1, c);
+            }
+            float *op = out + cg * 4;
+#pragma unroll
+            for (int ox = 0; ox < 2; ++ox) {
+                *reinterpret_cast<float4 *>(op + o00 + (unsigned)ox * (unsigned)out_cs) = round_tf32_4(lerp2_4(p0, t[0][ox], p1, t[1][ox]));
+                *reinterpret_cast<float4 *>(op + o00 + orow + (unsigned)ox * (unsigned)out_cs) = round_tf32_4(lerp2_4(q0, t[1][ox], q1, t[2][ox]));
+            }
+        }
+        return;
+    }
     for (int cg = threadIdx.x; cg < c4; cg += 8) {
         const float *ip = in + cg * 4;
         float4 t[3][2];                                   // per source row: the two horizontally interpolated values
@@ -338,11 +385,11 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
             for (int ox = 0; ox < 2; ++ox) {
                 float4 v;
-                v.x = ptx::round_tf32(lerp3(wy[oy][0], t[0][ox].x, wy[oy][1], t[1][ox].x, wy[oy][2], t[2][ox].x));
-                v.y = ptx::round_tf32(lerp3(wy[oy][0], t[0][ox].y, wy[oy][1], t[1][ox].y, wy[oy][2], t[2][ox].y));
-                v.z = ptx::round_tf32(lerp3(wy[oy][0], t[0][ox].z, wy[oy][1], t[1][ox].z, wy[oy][2], t[2][ox].z));
-                v.w = ptx::round_tf32(lerp3(wy[oy][0], t[0][ox].w, wy[oy][1], t[1][ox].w, wy[oy][2], t[2][ox].w));
-                *reinterpret_cast<float4 *>(op + o00 + (unsigned)oy * orow + (unsigned)ox * (unsigned)out_cs) = v;
+                v.x = lerp3(wy[oy][0], t[0][ox].x, wy[oy][1], t[1][ox].x, wy[oy][2], t[2][ox].x);
+                v.y = lerp3(wy[oy][0], t[0][ox].y, wy[oy][1], t[1][ox].y, wy[oy][2], t[2][ox].y);
+                v.z = lerp3(wy[oy][0], t[0][ox].z, wy[oy][1], t[1][ox].z, wy[oy][2], t[2][ox].z);
+                v.w = lerp3(wy[oy][0], t[0][ox].w, wy[oy][1], t[1][ox].w, wy[oy][2], t[2][ox].w);
+                *reinterpret_cast<float4 *>(op + o00 + (unsigned)oy * orow + (unsigned)ox * (unsigned)out_cs) = round_tf32_4(v);
             }
     }
 }

@@ -619,7 +619,21 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     PV_CHECK_ARG(!head || (d.Cout == 32 && col_kc(d.Cin + d.Cin2) != 16 && head->cout >= 1 && head->cout <= 32 && head->w && head->bias &&
                            head->out_nchw && (!head->mask || head->mask_esz == 1 || head->mask_esz == 8)),
                  "conv(col): bad fused-head description");
-    const int kc = col_kc(d.Cin + d.Cin2);
+    int kc = col_kc(d.Cin + d.Cin2);
+    // Half chunks (tuning knob PVNET_COL_HALF_CHUNKS=1, default off): a 3x3 layer with 144 KB of resident weights
+    // (layer1.*, conv2s.0) has room for only TWO 23 KB stages of 32 channels; the same bytes as four 12 KB stages of
+    // 16 channels (64-byte rows) keep three box requests in flight instead of one.  Measured: conv2s.0 0.357 against
+    // 0.329 ms, layer1 unchanged -- these launches are not waiting for their operand boxes (tensor pipe at the N<=64
+    // shared-memory floor), the extra barrier round per 18 MMAs only costs.
+    static const int env_half = [] {
+        const char *e = getenv("PVNET_COL_HALF_CHUNKS");
+        return e ? atoi(e) : 0;
+    }();
+    if (env_half && kc == 32 && d.ksize == 3 && !head &&
+        col_smem(32, 3, (d.Cin + d.Cin2) / 32, d.Cout, d.dilation, 3, 0, true) > SMEM_LIMIT &&
+        col_smem(32, 3, (d.Cin + d.Cin2) / 32, d.Cout, d.dilation, 2, 0, true) <= SMEM_LIMIT &&
+        col_smem(16, 3, (d.Cin + d.Cin2) / 16, d.Cout, d.dilation, 4, 0, true) <= SMEM_LIMIT)
+        kc = 16;
     ColGeom &g = p->g;
     g.KW = g.KH = d.ksize;
     g.pad_l = g.pad_t = d.ksize == 4 ? 2 : 1;
@@ -770,6 +784,7 @@ int conv_col_launch_at(const void *storage, cudaStream_t s)
     const ColPlan &p = *static_cast<const ColPlan *>(storage);
     const void *fn = p.up.src ? (p.epi == 2 ? (const void *)k_conv_col<8, true, 3, 2, true> : (const void *)k_conv_col<8, true, 3, 1, true>)
                      : (p.kc == 32 && !p.head) ? (p.epi == 2 ? (const void *)k_conv_col<32, false, 3, 2> : (const void *)k_conv_col<32, false, 3, 1>)
+                     : (p.kc == 16 && !p.head && p.g.KH == 3) ? (p.epi == 2 ? (const void *)k_conv_col<16, false, 3, 2> : (const void *)k_conv_col<16, false, 3, 1>)
                      : (p.kc == 16 && !p.head) ? (p.epi == 2 ? (const void *)k_conv_col<16, false, 4, 2> : (const void *)k_conv_col<16, false, 4, 1>)
                      : (p.kc == 8 && !p.head) ? (const void *)k_conv_col<8, false, 3, 1>
                      : p.kc == 32 ? (const void *)k_conv_col<32, true, 3, 1>
@@ -785,6 +800,8 @@ int conv_col_launch_at(const void *storage, cudaStream_t s)
     else if (p.up.src) COL_LAUNCH(8, true, 3, 1, true);
     else if (p.kc == 32 && !p.head && p.epi == 2) COL_LAUNCH(32, false, 3, 2, false);
     else if (p.kc == 32 && !p.head) COL_LAUNCH(32, false, 3, 1, false);
+    else if (p.kc == 16 && !p.head && p.g.KH == 3 && p.epi == 2) COL_LAUNCH(16, false, 3, 2, false);
+    else if (p.kc == 16 && !p.head && p.g.KH == 3) COL_LAUNCH(16, false, 3, 1, false);
     else if (p.kc == 16 && !p.head && p.epi == 2) COL_LAUNCH(16, false, 4, 2, false);
     else if (p.kc == 16 && !p.head) COL_LAUNCH(16, false, 4, 1, false);
     else if (p.kc == 8 && !p.head) COL_LAUNCH(8, false, 3, 1, false);
