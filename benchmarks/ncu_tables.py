@@ -64,8 +64,12 @@ def conv(rep, md, js, batch=16):
              "regex:\"k_conv_tap_p|k_conv_col|k_conv_tc\" -c 25 python benchmarks/profile_step.py 1`"
              " -> `python benchmarks/ncu_tables.py conv ...`", "",
              "Times are under the profiler (serialised, cold): use shares. TFLOP/s = 2*GMAC*16 / time.", "",
-             "| layer | kernel | grid | us | TFLOP/s | tensor pipe % | L2 % | DRAM % | DRAM read MB | DRAM write MB | regs |",
-             "|---|---|---|---|---|---|---|---|---|---|---|"]
+             "`tensor pipe %` = the MMA sub-pipe doing math (max of the sm__*tensor*pct metrics); `tc active %` = "
+             "`sm__pipe_tc_cycles_active` (the tensor-core pipe occupied, operand fetch included); `tc smem %` = "
+             "`l1tex__data_pipe_tc_wavefronts_mem_shared` (the MMAs' shared-memory operand reads as a share of the L1 "
+             "data pipe): a narrow layer shows a busy pipe that mostly waits for its A operand.", "",
+             "| layer | kernel | grid | us | TFLOP/s | tensor pipe % | tc active % | tc smem % | L2 % | DRAM % | DRAM read MB | DRAM write MB | regs |",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     tot_us = rd = wr = 0.0
     for i, r in enumerate(rows[:25]):
         name = r[col["Kernel Name"]]
@@ -82,7 +86,11 @@ def conv(rep, md, js, batch=16):
         l2 = float(r[col["lts__throughput.avg.pct_of_peak_sustained_elapsed"]])
         dr = float(r[col["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]])
         tf = 2 * gm[i] * batch * 1e9 / (us * 1e-6) / 1e12
-        lines.append(f"| {LAYERS[i]} | `{short}` | {r[col['launch__grid_size']]} | {us:.1f} | {tf:.0f} | {tp:.1f} | "
+        tca = num(r[col["sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed"]]) \
+            if "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed" in col else float("nan")
+        tcs = num(r[col["l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]]) \
+            if "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed" in col else float("nan")
+        lines.append(f"| {LAYERS[i]} | `{short}` | {r[col['launch__grid_size']]} | {us:.1f} | {tf:.0f} | {tp:.1f} | {tca:.1f} | {tcs:.1f} | "
                      f"{l2:.1f} | {dr:.1f} | {rmb:.1f} | {wmb:.1f} | {r[col['launch__registers_per_thread']]} |")
         tot_us += us
         rd += rmb
