@@ -339,8 +339,9 @@ PVNET_API int pvnet_backbone_set_output_layout(pvnet_backbone_t *m, int pixel_ma
 /* The last decoder upsampling, F.interpolate(x2s_up, scale_factor=2, mode='bilinear', align_corners=True)
  * (model_repository.py:75), can run inside convraw.0's operand loader: the full-resolution
  * [b,h,w,s2dim] tensor is then never written, the output is bit-identical.  on = 1 selects the fused
- * form, 0 the separate upsampling launch, -1 = default (environment variable PVNET_FUSE_UP; off: the
- * fused form measured slower on B200). */
+ * form with the interpolation on convraw.0's epilogue warps (two CTAs per SM), 2 the form with eight
+ * dedicated interpolation warps (one CTA per SM, four-tile operand ring), 0 the separate upsampling
+ * launch, -1 = default (environment variable PVNET_FUSE_UP; see DESIGN.md section 5 for the measurements). */
 PVNET_API int pvnet_backbone_set_fused_upsample(pvnet_backbone_t *m, int on);
 PVNET_API int pvnet_backbone_workspace_bytes(const pvnet_backbone_t *m, int b, int h, int w, size_t *bytes);
 PVNET_API int pvnet_backbone_forward(pvnet_backbone_t *m, const float *image_nchw, int b, int h, int w,

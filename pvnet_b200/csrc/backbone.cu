@@ -219,9 +219,10 @@ int build_plans(pvnet_backbone *m, const Buffers &B, int b, int h, int w)
             m->raw_split = true;
             // F.interpolate(x2s_up, scale 2) (model_repository.py:75) inside convraw.0's operand loader: conv2s.0's
             // half-resolution output U2 is the source, the full-resolution tensor is never written
-            const bool want = (m->fuse_up < 0 ? env_fuse_up() : m->fuse_up) != 0;
-            if (want && m->s2 == 32 && m->raw == 32 && m->seg_dim + m->ver_dim <= 32) {
+            const int want = m->fuse_up < 0 ? env_fuse_up() : m->fuse_up;
+            if (want != 0 && m->s2 == 32 && m->raw == 32 && m->seg_dim + m->ver_dim <= 32) {
                 draw.up_src = B.U2;
+                draw.up_mode = want == 2 ? 2 : 1;
                 m->up2_fused = true;
             }
         }
@@ -271,7 +272,7 @@ int pvnet_backbone_set_output_layout(pvnet_backbone_t *m, int pixel_major)
 int pvnet_backbone_set_fused_upsample(pvnet_backbone_t *m, int on)
 {
     PV_CHECK_ARG(m, "null handle");
-    m->fuse_up = on < 0 ? -1 : (on ? 1 : 0);
+    m->fuse_up = on < 0 ? -1 : (on == 2 ? 2 : (on ? 1 : 0));
     m->p_ws = nullptr;   // replan
     return PVNET_OK;
 }

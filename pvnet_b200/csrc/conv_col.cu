@@ -77,10 +77,92 @@ __device__ __forceinline__ float4 ldg_nc_v4_volatile(const float *p)
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+// Box rows [I0, I1) of one lane's column: loads the window slots these rows need (slot 0 never: it only ever
+// carries the zero weight, see above), interpolates horizontally, then vertically row by row.
+template <int I0, int I1>
+__device__ __forceinline__ void up_fill_rows(const float *base, unsigned rstride, unsigned olo, unsigned ohi, int R0, int uh,
+                                             bool act, bool vx, float w1x_, unsigned zero, float wa_l, float wb_l, float wc_l,
+                                             uint32_t sbase, int c, int hf)
+{
+    constexpr int PITCH = COL_TW + 2;
+    constexpr int S0 = I0 >> 1, S1 = ((I1 - 1) >> 1) + 2;      // window slots of these rows
+    constexpr int L0 = S0 < 1 ? 1 : S0, NL = S1 - L0 + 1;      // slots actually loaded
+    // All source loads are issued before anything consumes them (volatile asm keeps them together) ...
+    float4 a[NL], b[NL];
+#pragma unroll
+    for (int j = L0; j <= S1; ++j) {
+        a[j - L0] = b[j - L0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) {
+            const unsigned ro = (unsigned)min(max(R0 + j, 0), uh - 1) * rstride;
+            a[j - L0] = ldg_nc_v4_volatile(base + (ro + olo));
+            b[j - L0] = ldg_nc_v4_volatile(base + (ro + ohi));
+        }
+    }
+    // ... and nothing may consume them before the last one has landed: ptxas otherwise starts on the first
+    // output rows as soon as their three source rows are there and parks the remaining loads behind those
+    // stores (3-4 exposed L2 round trips per tile instead of one).  The interpolation weight is made to
+    // depend on every load through an AND with a kernel parameter that is always zero.
+    unsigned dep = 0;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) dep |= __float_as_uint(a[j].x) | __float_as_uint(b[j].x);
+    float w1x = __uint_as_float(__float_as_uint(w1x_) | (dep & zero)), w0x = 1.f - w1x_;
+    if (!vx) w0x = w1x = 0.f;
+    float4 t[S1 - S0 + 1];
+    if (S0 == 0) t[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = L0; j <= S1; ++j) {
+        t[j - S0].x = __fmaf_rn(w1x, b[j - L0].x, __fmul_rn(w0x, a[j - L0].x));   // lerp3 with a zero third weight
+        t[j - S0].y = __fmaf_rn(w1x, b[j - L0].y, __fmul_rn(w0x, a[j - L0].y));
+        t[j - S0].z = __fmaf_rn(w1x, b[j - L0].z, __fmul_rn(w0x, a[j - L0].z));
+        t[j - S0].w = __fmaf_rn(w1x, b[j - L0].w, __fmul_rn(w0x, a[j - L0].w));
+    }
+#pragma unroll
+    for (int i = I0; i < I1; ++i) {
+        const float wa = __shfl_sync(0xffffffffu, wa_l, i), wb = __shfl_sync(0xffffffffu, wb_l, i),
+                    wc = __shfl_sync(0xffffffffu, wc_l, i);
+        const int e = (i >> 1) - S0;
+        // Rounding to tf32 (nearest, ties away -- cvt.rna.tf32, what k_upsample2x stores): add half an ulp of
+        // the 10-bit mantissa; the 13 low bits that remain are ignored by the tensor core (kind::tf32 reads the
+        // upper 19 bits), so they need not be cleared.  Exactly the values the separate launch feeds the MMA.
+        float4 o;
+        o.x = __uint_as_float(__float_as_uint(lerp3(wa, t[e].x, wb, t[e + 1].x, wc, t[e + 2].x)) + 0x1000u);
+        o.y = __uint_as_float(__float_as_uint(lerp3(wa, t[e].y, wb, t[e + 1].y, wc, t[e + 2].y)) + 0x1000u);
+        o.z = __uint_as_float(__float_as_uint(lerp3(wa, t[e].z, wb, t[e + 1].z, wc, t[e + 2].z)) + 0x1000u);
+        o.w = __uint_as_float(__float_as_uint(lerp3(wa, t[e].w, wb, t[e + 1].w, wc, t[e + 2].w)) + 0x1000u);
+        const int rr = i * PITCH + c;
+        if (act) ptx::sts128(sbase + (uint32_t)(i * PITCH * 32) + (uint32_t)((hf ^ ((rr >> 2) & 1)) << 4), o);
+    }
+}
+
+// L2 prefetch of the source lines a later up_fill_chunk of the same warp will read (same addresses; no data comes
+// back, so no registers are held): ncu showed the dedicated interpolation warps waiting ~2k cycles per load batch --
+// half of the 157 MB source has left the L2 by the time convraw.0 runs.  One 16-byte half per 32-byte sector suffices.
+__device__ __forceinline__ void up_prefetch_chunk(const ColUp &u, const ColGeom &g, int img, int y0, int x0, int q, int lane)
+{
+    constexpr int PITCH = COL_TW + 2, NSLOT = COL_TH / 2 + 3;
+    if (lane >= 2 * PITCH || (lane & 1)) return;
+    const int xc = min(max(x0 - 1 + (lane >> 1), 0), g.Wo - 1);
+    const int xlo = (int)(u.sx * (float)xc);
+    const int xhi = min(xlo + 1, u.w - 1);
+    const int R0 = (y0 >> 1) - 2;
+    const float *base = u.src + (size_t)img * u.h * u.w * u.cs + q * 8;
+    const unsigned rstride = (unsigned)u.w * (unsigned)u.cs;
+    const unsigned olo = (unsigned)xlo * (unsigned)u.cs, ohi = (unsigned)xhi * (unsigned)u.cs;
+#pragma unroll
+    for (int j = 1; j < NSLOT; ++j) {
+        const unsigned ro = (unsigned)min(max(R0 + j, 0), u.h - 1) * rstride;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (ro + olo)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (ro + ohi)));
+    }
+}
+
+// PARTS = 1: the whole column at once (20 loads in flight, ~130 registers); PARTS = 2: rows 0-8, then rows 9-17
+// (12 + 14 loads, for the 112-register variant with dedicated interpolation warps).
+template <int PARTS>
 __device__ __forceinline__ void up_fill_chunk(const ColUp &u, const ColGeom &g, int img, int y0, int x0, int q, int lane,
                                               uint32_t stage_addr)
 {
-    constexpr int PITCH = COL_TW + 2, ROWS = COL_TH + 2, NSLOT = COL_TH / 2 + 3;
+    constexpr int PITCH = COL_TW + 2, ROWS = COL_TH + 2;
     const bool act = lane < 2 * PITCH;                 // lanes 20..31 only take part in the shuffles
     const int c = act ? lane >> 1 : 0, hf = lane & 1;
     const int x = x0 - 1 + c;
@@ -111,54 +193,12 @@ __device__ __forceinline__ void up_fill_chunk(const ColUp &u, const ColGeom &g, 
     const float *base = u.src + (size_t)img * u.h * u.w * u.cs + q * 8 + hf * 4;
     const unsigned rstride = (unsigned)u.w * (unsigned)u.cs;      // 32-bit element offsets inside one image
     const unsigned olo = (unsigned)xlo * (unsigned)u.cs, ohi = (unsigned)xhi * (unsigned)u.cs;
-    // All 2 x 10 source loads are issued before anything consumes them (volatile asm keeps them together).
-    // Window slot 0 (row R0) only ever carries the zero weight: for the first two box rows the source
-    // pair is always (E, E+1), see above -- it is not loaded.
-    float4 a[NSLOT - 1], b[NSLOT - 1];
-#pragma unroll
-    for (int j = 1; j < NSLOT; ++j) {
-        a[j - 1] = b[j - 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (act) {
-            const unsigned ro = (unsigned)min(max(R0 + j, 0), u.h - 1) * rstride;
-            a[j - 1] = ldg_nc_v4_volatile(base + (ro + olo));
-            b[j - 1] = ldg_nc_v4_volatile(base + (ro + ohi));
-        }
-    }
-    // ... and nothing may consume them before the last one has landed: ptxas otherwise starts on the first
-    // output rows as soon as their three source rows are there and parks the remaining loads behind those
-    // stores (3-4 exposed L2 round trips per tile instead of one).  The interpolation weight is made to
-    // depend on every load through an AND with a kernel parameter that is always zero.
-    unsigned dep = 0;
-#pragma unroll
-    for (int j = 0; j < NSLOT - 1; ++j) dep |= __float_as_uint(a[j].x) | __float_as_uint(b[j].x);
-    float w1x = __uint_as_float(__float_as_uint(w1x_) | (dep & u.zero)), w0x = 1.f - w1x_;
-    if (!vx) w0x = w1x = 0.f;
-    float4 t[NSLOT];
-    t[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 1; j < NSLOT; ++j) {
-        t[j].x = __fmaf_rn(w1x, b[j - 1].x, __fmul_rn(w0x, a[j - 1].x));   // lerp3 with a zero third weight
-        t[j].y = __fmaf_rn(w1x, b[j - 1].y, __fmul_rn(w0x, a[j - 1].y));
-        t[j].z = __fmaf_rn(w1x, b[j - 1].z, __fmul_rn(w0x, a[j - 1].z));
-        t[j].w = __fmaf_rn(w1x, b[j - 1].w, __fmul_rn(w0x, a[j - 1].w));
-    }
-    // store address of box row rr = i*PITCH + c: rr*32 + ((hf ^ bit 2 of rr) << 4)
-    const uint32_t sbase = stage_addr + (uint32_t)(c * 32);
-#pragma unroll
-    for (int i = 0; i < ROWS; ++i) {
-        const float wa = __shfl_sync(0xffffffffu, wa_l, i), wb = __shfl_sync(0xffffffffu, wb_l, i),
-                    wc = __shfl_sync(0xffffffffu, wc_l, i);
-        const int e = i >> 1;
-        // Rounding to tf32 (nearest, ties away -- cvt.rna.tf32, what k_upsample2x stores): add half an ulp of
-        // the 10-bit mantissa; the 13 low bits that remain are ignored by the tensor core (kind::tf32 reads the
-        // upper 19 bits), so they need not be cleared.  Exactly the values the separate launch feeds the MMA.
-        float4 o;
-        o.x = __uint_as_float(__float_as_uint(lerp3(wa, t[e].x, wb, t[e + 1].x, wc, t[e + 2].x)) + 0x1000u);
-        o.y = __uint_as_float(__float_as_uint(lerp3(wa, t[e].y, wb, t[e + 1].y, wc, t[e + 2].y)) + 0x1000u);
-        o.z = __uint_as_float(__float_as_uint(lerp3(wa, t[e].z, wb, t[e + 1].z, wc, t[e + 2].z)) + 0x1000u);
-        o.w = __uint_as_float(__float_as_uint(lerp3(wa, t[e].w, wb, t[e + 1].w, wc, t[e + 2].w)) + 0x1000u);
-        const int rr = i * PITCH + c;
-        if (act) ptx::sts128(sbase + (uint32_t)(i * PITCH * 32) + (uint32_t)((hf ^ ((rr >> 2) & 1)) << 4), o);
+    const uint32_t sbase = stage_addr + (uint32_t)(c * 32);   // box row rr = i*PITCH + c sits at rr*32 + ((hf ^ bit 2 of rr) << 4)
+    if (PARTS == 1) {
+        up_fill_rows<0, ROWS>(base, rstride, olo, ohi, R0, u.h, act, vx, w1x_, u.zero, wa_l, wb_l, wc_l, sbase, c, hf);
+    } else {
+        up_fill_rows<0, ROWS / 2>(base, rstride, olo, ohi, R0, u.h, act, vx, w1x_, u.zero, wa_l, wb_l, wc_l, sbase, c, hf);
+        up_fill_rows<ROWS / 2, ROWS>(base, rstride, olo, ohi, R0, u.h, act, vx, w1x_, u.zero, wa_l, wb_l, wc_l, sbase, c, hf);
     }
 }
 
@@ -171,8 +211,11 @@ __device__ __forceinline__ void up_fill_chunk(const ColUp &u, const ColGeom &g, 
 // Epilogue warp q fills chunk q of tile it+2 between the two halves of tile it's epilogue (after the
 // activated tile went back to TMEM, while the head MMA is pending), into stage ((it+2)&1)*5 + q; its
 // empty barrier completed with tile it's MMAs, which the warp has already seen through tfull.
-template <int KC, bool HEAD, int KH, int EPI, bool UP = false>
-__global__ void __launch_bounds__(64 + 128 * EPI, (EPI == 2 && !HEAD) ? 1 : 2)
+// UP = 2: one CTA per SM, EPI = 2, and EIGHT more warps that only interpolate (warp 10 + 4*s + q: chunk q of the
+// tiles of parity s), running ahead of the MMAs through a ring of four tiles; the epilogue warps do no filling.
+constexpr int UP_WARPS = 8;
+template <int KC, bool HEAD, int KH, int EPI, int UP = 0>
+__global__ void __launch_bounds__(64 + 128 * EPI + (UP == 2 ? 32 * UP_WARPS : 0), ((EPI == 2 && !HEAD) || UP == 2) ? 1 : 2)
     k_conv_col(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmO, const ColGeom g,
@@ -180,7 +223,8 @@ __global__ void __launch_bounds__(64 + 128 * EPI, (EPI == 2 && !HEAD) ? 1 : 2)
                const float *__restrict__ head_w, const float *__restrict__ head_b, float *__restrict__ head_out,
                void *__restrict__ mask, const ColUp up)
 {
-    static_assert(!UP || (HEAD && KC == 8 && KH == 3), "fused upsampling: convraw.0 form only");
+    static_assert(UP == 0 || (HEAD && KC == 8 && KH == 3), "fused upsampling: convraw.0 form only");
+    static_assert(UP != 2 || EPI == 2, "dedicated interpolation warps come with two epilogue sets");
     constexpr int ROWB = KC * 4;                       // bytes per K-major row
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -267,7 +311,7 @@ __global__ void __launch_bounds__(64 + 128 * EPI, (EPI == 2 && !HEAD) ? 1 : 2)
                 const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
                 const int y0 = tyi * COL_TH, x0 = txi * COL_TW;
                 for (int cc = 0; cc < g.cin_chunks; ++cc) {
-                    if (UP && cc < g.split_chunk) {     // filled by the epilogue warps
+                    if (UP != 0 && cc < g.split_chunk) {     // filled by the epilogue / interpolation warps
                         if (++s == g.stages) {
                             s = 0;
                             ph ^= 1u;
@@ -380,6 +424,32 @@ __global__ void __launch_bounds__(64 + 128 * EPI, (EPI == 2 && !HEAD) ? 1 : 2)
                 __syncwarp();
             }
         }
+    } else if (UP == 2 && warp >= 2 + 4 * EPI) {
+        // dedicated interpolation warps: set s = tiles of parity s, chunk q; ring slot = tile index mod ring tiles
+        const int iw = warp - (2 + 4 * EPI), iset = iw >> 2, q = iw & 3;
+        const uint32_t ring_tiles = (uint32_t)(g.stages / g.cin_chunks);
+        uint32_t it = (uint32_t)iset;
+        for (int tile = blockIdx.x + iset * gridDim.x; tile < g.total_tiles; tile += 2 * gridDim.x, it += 2) {
+            const int img = tile / tiles_per_img;
+            const int trem = tile - img * tiles_per_img;
+            const int tyi = trem / g.tiles_x, txi = trem - tyi * g.tiles_x;
+            const uint32_t use = it / ring_tiles;
+            const uint32_t sj = (it - use * ring_tiles) * (uint32_t)g.cin_chunks + (uint32_t)q;
+            {   // this warp's next tile: its source lines start moving into L2 now
+                const int tile_n = tile + 2 * (int)gridDim.x;
+                if (tile_n < g.total_tiles) {
+                    const int img_n = tile_n / tiles_per_img;
+                    const int trem_n = tile_n - img_n * tiles_per_img;
+                    const int tyn = trem_n / g.tiles_x, txn = trem_n - tyn * g.tiles_x;
+                    up_prefetch_chunk(up, g, img_n, tyn * COL_TH, txn * COL_TW, q, lane);
+                }
+            }
+            ptx::mbar_wait(&empty[sj], (use & 1u) ^ 1u);
+            up_fill_chunk<2>(up, g, img, tyi * COL_TH, txi * COL_TW, q, lane, ptx::smem_u32(sA) + sj * (uint32_t)stage_bytes);
+            ptx::fence_proxy_async();       // generic-proxy stores -> visible to the MMA's async-proxy reads
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&full[sj]);
+        }
     } else {
         const int q = warp & 3;
         const int m = q * 32 + lane;
@@ -396,13 +466,13 @@ __global__ void __launch_bounds__(64 + 128 * EPI, (EPI == 2 && !HEAD) ? 1 : 2)
             const int tyj = trem_j / g.tiles_x, txj = trem_j - tyj * g.tiles_x;
             const uint32_t sj = (itj & 1u) * (uint32_t)g.cin_chunks + (uint32_t)q;
             ptx::mbar_wait(&empty[sj], ((itj >> 1) & 1u) ^ 1u);
-            up_fill_chunk(up, g, img_j, tyj * COL_TH, txj * COL_TW, q, lane,
+            up_fill_chunk<1>(up, g, img_j, tyj * COL_TH, txj * COL_TW, q, lane,
                           ptx::smem_u32(sA) + sj * (uint32_t)stage_bytes);
             ptx::fence_proxy_async();       // generic-proxy stores -> visible to the MMA's async-proxy reads
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&full[sj]);
         };
-        if constexpr (UP) {
+        if constexpr (UP == 1) {
             // the first two tiles of the CTA (EPI = 2: each set fills the one it will finish)
             for (int p = 0; p < 2; ++p) {
                 const int tile_p = (int)blockIdx.x + p * (int)gridDim.x;
@@ -476,7 +546,7 @@ __global__ void __launch_bounds__(64 + 128 * EPI, (EPI == 2 && !HEAD) ? 1 : 2)
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&a2full[as]);
-                    if constexpr (UP) {
+                    if constexpr (UP == 1) {
                         const int tile_n = tile + 2 * (int)gridDim.x;
                         if (tile_n < g.total_tiles) up_fill(tile_n, it + 2u);
                     }
@@ -558,6 +628,7 @@ struct ColPlan {
     CUtensorMap tmA, tmA2, tmB, tmH, tmO;
     ColGeom g;
     int kc, head, epi;
+    int up_mode;            // 0 none, 1 epilogue warps interpolate, 2 dedicated interpolation warps
     ColUp up;
     unsigned grid;
     size_t smem;
@@ -664,6 +735,7 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
     p->up.sy = (float)(p->up.h - 1) / (float)(2 * p->up.h - 1);   // launch_upsample2x's scales
     p->up.sx = (float)(p->up.w - 1) / (float)(2 * p->up.w - 1);
     p->up.zero = 0;
+    p->up_mode = d.up_src ? (d.up_mode == 2 ? 2 : 1) : 0;
     // Resident weights whenever at least 2 A stages (one channel chunk with all its taps each) still
     // fit next to them; otherwise the KH*KW weight tiles of a chunk travel with its A box.  Two CTAs
     // per SM when the footprint allows.
@@ -682,8 +754,8 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
                col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, false) > SMEM_LIMIT)
             --stages;
     }
-    if (d.up_src) {     // the ring is exactly two tiles: stage = (tile parity) * chunks + chunk
-        stages = 2 * g.cin_chunks;
+    if (d.up_src) {     // the ring is exactly two tiles: stage = (tile parity) * chunks + chunk (dedicated warps: four tiles)
+        stages = (d.up_mode == 2 ? 4 : 2) * g.cin_chunks;
         PV_CHECK_ARG(resident && col_smem(kc, d.ksize, g.cin_chunks, g.BN, g.dil, stages, g.head_cout, true) <= SMEM_LIMIT,
                      "conv(col): fused upsampling does not fit in shared memory");
     }
@@ -760,7 +832,8 @@ int conv_col_plan_at(const ConvDesc &d, const HeadDesc *head, void *storage)
         return e ? atoi(e) : 1;
     }();
     if (head && kc == 8 && (g_head_epi ? g_head_epi : env_head_epi) == 2) p->epi = 2;
-    long long grid = (long long)sm_count() * per_sm;
+    if (p->up_mode == 2) p->epi = 2;
+    long long grid = (long long)sm_count() * (p->up_mode == 2 ? 1 : per_sm);
     if (grid > g.total_tiles) grid = g.total_tiles;
     p->grid = (unsigned)grid;
     p->bias = d.bias;
@@ -782,7 +855,8 @@ void conv_col_set_head_ptrs(void *storage, float *out_nchw, void *mask, int mask
 int conv_col_launch_at(const void *storage, cudaStream_t s)
 {
     const ColPlan &p = *static_cast<const ColPlan *>(storage);
-    const void *fn = p.up.src ? (p.epi == 2 ? (const void *)k_conv_col<8, true, 3, 2, true> : (const void *)k_conv_col<8, true, 3, 1, true>)
+    const void *fn = p.up_mode == 2 ? (const void *)k_conv_col<8, true, 3, 2, 2>
+                     : p.up_mode == 1 ? (p.epi == 2 ? (const void *)k_conv_col<8, true, 3, 2, 1> : (const void *)k_conv_col<8, true, 3, 1, 1>)
                      : (p.kc == 32 && !p.head) ? (p.epi == 2 ? (const void *)k_conv_col<32, false, 3, 2> : (const void *)k_conv_col<32, false, 3, 1>)
                      : (p.kc == 16 && !p.head && p.g.KH == 3) ? (p.epi == 2 ? (const void *)k_conv_col<16, false, 3, 2> : (const void *)k_conv_col<16, false, 3, 1>)
                      : (p.kc == 16 && !p.head) ? (p.epi == 2 ? (const void *)k_conv_col<16, false, 4, 2> : (const void *)k_conv_col<16, false, 4, 1>)
@@ -793,21 +867,22 @@ int conv_col_launch_at(const void *storage, cudaStream_t s)
     PV_CUDA(attr_err);
     const HeadDesc &h = p.hd;
 #define COL_LAUNCH(KC_, HEAD_, KH_, EPI_, UP_)                                                                    \
-    k_conv_col<KC_, HEAD_, KH_, EPI_, UP_><<<p.grid, 64 + 128 * EPI_, p.smem, s>>>(p.tmA, p.tmA2, p.tmB, p.tmH, p.tmO, p.g, p.bias, p.res, p.out,      \
+    k_conv_col<KC_, HEAD_, KH_, EPI_, UP_><<<p.grid, 64 + 128 * EPI_ + (UP_ == 2 ? 32 * UP_WARPS : 0), p.smem, s>>>(p.tmA, p.tmA2, p.tmB, p.tmH, p.tmO, p.g, p.bias, p.res, p.out,      \
                                                                 p.head ? h.w : nullptr, p.head ? h.bias : nullptr, \
                                                                 p.head ? h.out_nchw : nullptr, p.head ? h.mask : nullptr, p.up)
-    if (p.up.src && p.epi == 2) COL_LAUNCH(8, true, 3, 2, true);
-    else if (p.up.src) COL_LAUNCH(8, true, 3, 1, true);
-    else if (p.kc == 32 && !p.head && p.epi == 2) COL_LAUNCH(32, false, 3, 2, false);
-    else if (p.kc == 32 && !p.head) COL_LAUNCH(32, false, 3, 1, false);
-    else if (p.kc == 16 && !p.head && p.g.KH == 3 && p.epi == 2) COL_LAUNCH(16, false, 3, 2, false);
-    else if (p.kc == 16 && !p.head && p.g.KH == 3) COL_LAUNCH(16, false, 3, 1, false);
-    else if (p.kc == 16 && !p.head && p.epi == 2) COL_LAUNCH(16, false, 4, 2, false);
-    else if (p.kc == 16 && !p.head) COL_LAUNCH(16, false, 4, 1, false);
-    else if (p.kc == 8 && !p.head) COL_LAUNCH(8, false, 3, 1, false);
-    else if (p.kc == 32) COL_LAUNCH(32, true, 3, 1, false);
-    else if (p.epi == 2) COL_LAUNCH(8, true, 3, 2, false);
-    else COL_LAUNCH(8, true, 3, 1, false);
+    if (p.up_mode == 2) COL_LAUNCH(8, true, 3, 2, 2);
+    else if (p.up_mode == 1 && p.epi == 2) COL_LAUNCH(8, true, 3, 2, 1);
+    else if (p.up_mode == 1) COL_LAUNCH(8, true, 3, 1, 1);
+    else if (p.kc == 32 && !p.head && p.epi == 2) COL_LAUNCH(32, false, 3, 2, 0);
+    else if (p.kc == 32 && !p.head) COL_LAUNCH(32, false, 3, 1, 0);
+    else if (p.kc == 16 && !p.head && p.g.KH == 3 && p.epi == 2) COL_LAUNCH(16, false, 3, 2, 0);
+    else if (p.kc == 16 && !p.head && p.g.KH == 3) COL_LAUNCH(16, false, 3, 1, 0);
+    else if (p.kc == 16 && !p.head && p.epi == 2) COL_LAUNCH(16, false, 4, 2, 0);
+    else if (p.kc == 16 && !p.head) COL_LAUNCH(16, false, 4, 1, 0);
+    else if (p.kc == 8 && !p.head) COL_LAUNCH(8, false, 3, 1, 0);
+    else if (p.kc == 32) COL_LAUNCH(32, true, 3, 1, 0);
+    else if (p.epi == 2) COL_LAUNCH(8, true, 3, 2, 0);
+    else COL_LAUNCH(8, true, 3, 1, 0);
 #undef COL_LAUNCH
     PV_LAUNCHED("k_conv_col");
     return PVNET_OK;

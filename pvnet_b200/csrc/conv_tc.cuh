@@ -32,6 +32,7 @@ struct ConvDesc {
     // half-resolution tensor up_src [b,H/2,W/2,Cin], interpolated inside the kernel straight into the
     // operand stages (model_repository.py:75: the upsampled tensor is never written)
     const float *up_src = nullptr;
+    int up_mode = 1;   // 1: interpolated by the epilogue warps (two CTAs per SM); 2: by eight dedicated warps (one CTA per SM)
 };
 
 // Optional fused 1x1 head (convraw.3 + argmax) for the column kernel's epilogue.

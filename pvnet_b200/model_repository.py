@@ -157,8 +157,9 @@ class Resnet18_8s(nn.Module):
 
     def set_fused_upsample(self, on=None):
         """A/B switch of the 1/2 -> 1 upsampling inside convraw.0's loader (pvnet_backbone_set_fused_upsample):
-        None = library default (separate launch), False = separate k_upsample2x launch, True = fused."""
-        self._nat.fuse_up = -1 if on is None else int(bool(on))
+        None = library default, False / 0 = separate k_upsample2x launch, True / 1 = fused on the epilogue warps,
+        2 = fused on dedicated interpolation warps."""
+        self._nat.fuse_up = -1 if on is None else (2 if on == 2 and on is not True else int(bool(on)))
         return self
 
     def _sync_options(self, dev):

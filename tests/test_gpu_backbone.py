@@ -156,7 +156,8 @@ def test_odd_sizes_multiple_of_8():
 
 @pytest.mark.parametrize("shape", [(2, 480, 640), (1, 72, 104), (3, 16, 16), (1, 256, 264)], ids=str)
 @pytest.mark.parametrize("pixel_major", [False, True], ids=["nchw", "pixel-major"])
-def test_fused_upsample_equals_separate_launch(shape, pixel_major):
+@pytest.mark.parametrize("mode", [1, 2], ids=["epilogue warps", "dedicated warps"])
+def test_fused_upsample_equals_separate_launch(shape, pixel_major, mode):
     """convraw.0 interpolating its upsampled input itself (pvnet_backbone_set_fused_upsample) against the separate
     k_upsample2x launch it replaces: the same ATen arithmetic on the same conv2s.0 output, so the two forwards agree to the last bit
     (partial tiles, image borders and the last-row rounding case of the align_corners scale included)."""
@@ -168,7 +169,7 @@ def test_fused_upsample_equals_separate_launch(shape, pixel_major):
         launches0 = _launches(lambda: net.forward_native(x, with_mask=True, mask_dtype=torch.uint8, pixel_major=pixel_major))
         sep, msep = net.forward_native(x, with_mask=True, mask_dtype=torch.uint8, pixel_major=pixel_major)
         sep, msep = sep.clone(), msep.clone()
-        net.set_fused_upsample(True)
+        net.set_fused_upsample(mode)
         launches1 = _launches(lambda: net.forward_native(x, with_mask=True, mask_dtype=torch.uint8, pixel_major=pixel_major))
         fused, mfused = net.forward_native(x, with_mask=True, mask_dtype=torch.uint8, pixel_major=pixel_major)
         net.set_fused_upsample(None)
@@ -190,7 +191,7 @@ def test_two_epilogue_sets_equal_one(fused):
     for sets in (1, 2):
         pc.set_head_epilogue_sets(sets)
         try:
-            net = _net(18, seed=12).set_fused_upsample(fused)     # a fresh handle: plans are built under the hook
+            net = _net(18, seed=12).set_fused_upsample(1 if fused else 0)     # a fresh handle: plans are built under the hook
             with torch.no_grad():
                 outs.append(net.forward_native(x, with_mask=True, mask_dtype=torch.uint8))
             torch.cuda.synchronize()
