@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU run 28 (and 29: loads batched): 1/2 -> 1 upsampling fused into convraw.0's loader -- equality with the separate launch, backbone tests, bench A/B
+# round 2, GPU run 28b (and 29b: loads batched, 31b: lean interpolation): 1/2 -> 1 upsampling fused into convraw.0's loader -- equality with the separate launch, backbone tests, bench A/B
 cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_backbone.py -m gpu -q -rf --tb=short -s -k fused_upsample 2>&1 | tail -40 > gpurun_out/pytest_fused_up.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU run 30: ncu --set full of convraw.0, fused-upsampling variant and separate variant
+# round 2, GPU run 30b: ncu --set full of convraw.0, fused-upsampling variant and separate variant
 cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_conv_col --launch-skip 7 -c 1 \

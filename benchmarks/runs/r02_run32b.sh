@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU run 32: convraw.0 with two epilogue warp sets (PVNET_HEAD_EPI) x fused / separate upsampling (PVNET_FUSE_UP)
+# round 2, GPU run 32b: convraw.0 with two epilogue warp sets (PVNET_HEAD_EPI) x fused / separate upsampling (PVNET_FUSE_UP)
 cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_backbone.py tests/test_gpu_boundary.py -m gpu -q -rf --tb=short 2>&1 | tail -8 > gpurun_out/pytest_backbone32.log

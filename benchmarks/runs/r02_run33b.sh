@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU run 33: ncu --set full of the fused-upsampling convraw.0 (lean interpolation, one epilogue set)
+# round 2, GPU run 33b: ncu --set full of the fused-upsampling convraw.0 (lean interpolation, one epilogue set)
 cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 PVNET_FUSE_UP=1 PVNET_HEAD_EPI=1 timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_conv_col --launch-skip 7 -c 1 \

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU run 35: the state to be judged after the upsampling work -- full gpu tests, smoke, bench (both arms,
+# round 2, GPU run 35b: the state to be judged after the upsampling work -- full gpu tests, smoke, bench (both arms,
 # configs 2/4/5), step breakdown, ncu launch list
 cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out

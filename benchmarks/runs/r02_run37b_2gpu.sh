@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU run 37 (2 GPUs): nn.DataParallel boundary tests on the committed state, 2-rank bench line
+# round 2, GPU run 37b (2 GPUs): nn.DataParallel boundary tests on the committed state, 2-rank bench line
 cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_boundary.py tests/test_gpu_dropin.py -m gpu -q -rf --tb=short 2>&1 | tail -12 > gpurun_out/pytest_2gpu.log

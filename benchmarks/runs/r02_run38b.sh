@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU run 38 (and 40, with the L2 prefetch in the interpolation warps): committed default path once more (full gpu tests, smoke, bench), then the fused upsampling with eight
+# round 2, GPU run 38b (and 40b, with the L2 prefetch in the interpolation warps): committed default path once more (full gpu tests, smoke, bench), then the fused upsampling with eight
 # dedicated interpolation warps (PVNET_FUSE_UP=2): bit-exactness tests, bench A/B
 cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU run 39: ncu --set full of the fused-upsampling convraw.0 with eight dedicated interpolation warps (PVNET_FUSE_UP=2)
+# round 2, GPU run 39b: ncu --set full of the fused-upsampling convraw.0 with eight dedicated interpolation warps (PVNET_FUSE_UP=2)
 cd "$(dirname "$0")/../.." || exit 1
 mkdir -p gpurun_out
 PVNET_FUSE_UP=2 timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:k_conv_col --launch-skip 7 -c 1 \
