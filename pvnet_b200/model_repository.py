@@ -159,7 +159,7 @@ class Resnet18_8s(nn.Module):
         """A/B switch of the 1/2 -> 1 upsampling inside convraw.0's loader (pvnet_backbone_set_fused_upsample):
         None = library default, False / 0 = separate k_upsample2x launch, True / 1 = fused on the epilogue warps,
         2 = fused on dedicated interpolation warps."""
-        self._nat.fuse_up = -1 if on is None else (2 if on == 2 and on is not True else int(bool(on)))
+        self._nat.fuse_up = -1 if on is None else (2 if on == 2 else int(bool(on)))
         return self
 
     def _sync_options(self, dev):
